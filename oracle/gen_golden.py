@@ -1,0 +1,91 @@
+"""ORACLE support (test infrastructure): generate tests/golden/*.npz by running the REFERENCE's own
+modules (imported from /root/reference, see ref_shim.py) on CPU fp32 with the seeded synthetic
+checkpoints of parrot_tts_b200/synth.py.
+
+Run in the build container:   python oracle/gen_golden.py
+The fixtures are committed; the GPU box (no /root/reference) only reads them.
+Each file records the seed, torch version and the config so it can be regenerated.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from parrot_tts_b200 import configs, synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+VOCAB, PAD, NSPK = 150, 0, 10
+
+
+def tte_case(name, phones, speaker, seed=0):
+    cfg = configs.default_tte_config()
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, PAD, NSPK, seed=seed, dur_mode="spread")
+    model = ref_shim.load_reference_parrot(cfg, VOCAB, PAD, NSPK)
+    model.load_state_dict(sd, strict=True)
+    phones = torch.as_tensor(phones, dtype=torch.long)
+    batch = {"phones": phones, "src_mask": phones != PAD, "speaker": torch.as_tensor(speaker, dtype=torch.long)}
+    with torch.no_grad():
+        logits, src_mask, tgt_mask, log_dur = model(batch, inference=True)
+        ids_list = model.infer(batch)
+    dur = torch.clamp(torch.round(torch.exp(log_dur) - 1), min=0).long()
+    top2 = torch.topk(logits, 2, dim=-1).values
+    ids_flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in ids_list])
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        phones=phones.numpy(), speaker=batch["speaker"].numpy(), src_mask=src_mask.numpy(),
+        log_dur=log_dur.numpy(), dur=dur.numpy(), tgt_mask=tgt_mask.numpy(),
+        ids_flat=ids_flat, ids_lens=np.asarray([len(x) for x in ids_list], dtype=np.int64),
+        argmax=torch.argmax(logits, -1).numpy(),
+        margin=(top2[..., 0] - top2[..., 1]).numpy(),
+        logits_rows=logits[:, ::5, :].numpy().astype(np.float32),
+        logits_row_stride=np.int64(5),
+        seed=np.int64(seed), torch_version=str(torch.__version__), vocab=np.int64(VOCAB), n_speaker=np.int64(NSPK),
+    )
+    print(name, "T =", logits.shape[1], "lens", [len(x) for x in ids_list], "min margin", float((top2[..., 0] - top2[..., 1]).min()))
+
+
+def voc_case(name, code, spkr, seed=0, x=None):
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=seed, weight_norm=True, n_speaker=NSPK)
+    gen = ref_shim.load_reference_vocoder(h)
+    gen.load_state_dict(sd, strict=True)
+    out = {}
+    with torch.no_grad():
+        if x is None:
+            code = torch.as_tensor(code, dtype=torch.long)
+            spkr = torch.as_tensor(spkr, dtype=torch.long).view(-1, 1)
+            wav = gen(code=code, spkr=spkr)
+            out.update(code=code.numpy(), spkr=spkr.numpy())
+        else:
+            from importlib import import_module  # Generator.forward on a float feature map
+            wav = type(gen).__mro__[1].forward(gen, x)
+            out.update(x=x.numpy())
+    out.update(wav=wav.numpy().astype(np.float32), seed=np.int64(seed), torch_version=str(torch.__version__))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, tuple(wav.shape), "abs max", float(wav.abs().max()), "rms", float(wav.pow(2).mean().sqrt()))
+
+
+def main():
+    assert ref_shim.available(), "needs /root/reference (build container only)"
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(1234)
+    # TTE: one utterance; a ragged padded batch (rectangle semantics, SURVEY.md hard part 3)
+    tte_case("tte_b1_s16", torch.randint(2, VOCAB, (1, 16), generator=g), [0])
+    ph = torch.randint(2, VOCAB, (3, 20), generator=g)
+    ph[1, 13:] = PAD
+    ph[2, 7:] = PAD
+    tte_case("tte_b3_ragged", ph, [0, 3, 7])
+    # vocoder: code path B=1 and B=2, plus Generator.forward on a raw feature map
+    voc_case("voc_b1_t24", torch.randint(0, 1000, (1, 24), generator=g), [2])
+    voc_case("voc_b2_t40", torch.randint(0, 1000, (2, 40), generator=g), [0, 9])
+    voc_case("gen_b1_t12", None, None, x=torch.randn(1, 256, 12, generator=g))
+
+
+if __name__ == "__main__":
+    main()

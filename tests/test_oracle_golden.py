@@ -1,0 +1,71 @@
+"""CPU: the oracle restatements reproduce the golden vectors that oracle/gen_golden.py recorded
+from the reference's own modules (integer outputs bit-exact, floats to fp32 round-off)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tte_oracle, voc_oracle
+from parrot_tts_b200 import configs, synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged"])
+def test_tte_oracle_matches_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    cfg = configs.default_tte_config()
+    sd = synth.synth_tte_state_dict(cfg, int(g["vocab"]), 0, int(g["n_speaker"]), seed=int(g["seed"]))
+    batch = {"phones": torch.from_numpy(g["phones"]), "src_mask": torch.from_numpy(g["src_mask"]),
+             "speaker": torch.from_numpy(g["speaker"])}
+    ids, r = tte_oracle.parrot_infer(sd, batch)
+    assert np.array_equal(r["dur"].numpy(), g["dur"])                       # integer: bit-exact
+    assert np.array_equal(r["tgt_mask"].numpy(), g["tgt_mask"])
+    assert [len(x) for x in ids] == g["ids_lens"].tolist()
+    assert np.array_equal(np.concatenate([np.asarray(x) for x in ids]), g["ids_flat"])
+    np.testing.assert_allclose(r["log_dur"].numpy(), g["log_dur"], rtol=0, atol=2e-5)
+    stride = int(g["logits_row_stride"])
+    np.testing.assert_allclose(r["logits"][:, ::stride].numpy(), g["logits_rows"], rtol=0, atol=5e-4)
+
+
+def test_mask_off_by_one():
+    # reference modules/data.py:18 `ids <= len` marks len+1 positions valid [probed in SURVEY 8a/a9]
+    m = tte_oracle.get_mask_from_lengths([3, 5], 5)
+    assert m.int().tolist() == [[1, 1, 1, 1, 0], [1, 1, 1, 1, 1]]
+
+
+def test_round_half_even():
+    import math
+    ld = torch.tensor([math.log(1.5), math.log(2.5), math.log(3.5), -5.0, 0.0])
+    # exp-1 = .5, 1.5, 2.5 -> half-to-even 0, 2, 2 ; negatives clamp to 0
+    assert tte_oracle.round_durations(ld).tolist() == [0, 2, 2, 0, 0]
+
+
+@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40"])
+def test_voc_oracle_matches_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=int(g["seed"]), weight_norm=True)
+    wav = voc_oracle.code_generator_forward(sd, h, torch.from_numpy(g["code"]), torch.from_numpy(g["spkr"]))
+    assert wav.shape == g["wav"].shape
+    np.testing.assert_allclose(wav.numpy(), g["wav"], rtol=0, atol=2e-5)
+    # folded-weight flavour of the checkpoint (after remove_weight_norm()) gives the same audio
+    sd2 = synth.synth_vocoder_state_dict(h, seed=int(g["seed"]), weight_norm=False)
+    wav2 = voc_oracle.code_generator_forward(sd2, h, torch.from_numpy(g["code"]), torch.from_numpy(g["spkr"]))
+    np.testing.assert_allclose(wav2.numpy(), g["wav"], rtol=0, atol=2e-5)
+
+
+def test_generator_oracle_matches_golden(golden_dir):
+    g = _load(golden_dir, "gen_b1_t12")
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=int(g["seed"]), weight_norm=True)
+    wav = voc_oracle.generator_forward(sd, h, torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(wav.numpy(), g["wav"], rtol=0, atol=2e-5)
+
+
+def test_int16_truncates_toward_zero():
+    y = torch.tensor([[0.5 / 32768 * 3, -0.5 / 32768 * 3, 0.99997]])
+    assert voc_oracle.to_int16(y).tolist() == [1, -1, 32767]

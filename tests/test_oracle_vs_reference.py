@@ -1,0 +1,60 @@
+"""CPU, build container only: pin the oracle restatements to the reference's own modules imported
+from /root/reference (skipped where the reference tree is absent, e.g. on the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, tte_oracle, voc_oracle
+from parrot_tts_b200 import configs, synth
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+
+
+@pytest.mark.parametrize("seed,B,S", [(1, 1, 9), (2, 2, 24)])
+def test_tte_oracle_vs_reference(seed, B, S):
+    cfg = configs.default_tte_config()
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=seed)
+    ref = ref_shim.load_reference_parrot(cfg, 150, 0, 10)
+    ref.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    phones = torch.randint(2, 150, (B, S), generator=g)
+    if B > 1:
+        phones[1, S // 2:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.arange(B) % 10}
+    with torch.no_grad():
+        logits, _, tgt_mask, log_dur = ref(batch, inference=True)
+        ids_ref = ref.infer(batch)
+    ids, r = tte_oracle.parrot_infer(sd, batch)
+    assert ids == ids_ref
+    assert torch.equal(r["tgt_mask"], tgt_mask)
+    np.testing.assert_allclose(r["log_dur"].numpy(), log_dur.numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(r["logits"].numpy(), logits.numpy(), atol=5e-4, rtol=0)
+
+
+def test_tte_reference_rejects_overlong():
+    # reference modules/fft.py:18: pe[L] with L >= max_len raises IndexError
+    cfg = configs.default_tte_config(max_len=16)
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=0)
+    phones = torch.randint(2, 150, (1, 16))
+    with pytest.raises(IndexError):
+        tte_oracle.parrot_forward(sd, {"phones": phones, "src_mask": phones != 0, "speaker": torch.zeros(1, dtype=torch.long)})
+
+
+@pytest.mark.parametrize("seed,B,T", [(3, 1, 7), (4, 2, 33)])
+def test_voc_oracle_vs_reference(seed, B, T):
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=seed, weight_norm=True)
+    gen = ref_shim.load_reference_vocoder(h)
+    gen.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    code = torch.randint(0, 1000, (B, T), generator=g)
+    spkr = torch.randint(0, 10, (B, 1), generator=g)
+    with torch.no_grad():
+        ref = gen(code=code, spkr=spkr)
+    wav = voc_oracle.code_generator_forward(sd, h, code, spkr)
+    np.testing.assert_allclose(wav.numpy(), ref.numpy(), atol=2e-5, rtol=0)
+    gen.remove_weight_norm()
+    sd_plain = {k: v for k, v in gen.state_dict().items()}
+    assert "conv_pre.weight" in sd_plain
+    wav2 = voc_oracle.code_generator_forward(sd_plain, h, code, spkr)
+    np.testing.assert_allclose(wav2.numpy(), ref.numpy(), atol=2e-5, rtol=0)
