@@ -1,0 +1,125 @@
+// pb_common.cuh - shared host/device helpers of libparrot_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/parrot_b200.h"
+
+namespace pb {
+
+// ---------------------------------------------------------------- host side: errors ----------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define PB_CUDA(expr)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return pb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define PB_REQUIRE(cond, code, ...)                                            \
+    do {                                                                       \
+        if (!(cond)) { pb::set_error(__VA_ARGS__); return (code); }            \
+    } while (0)
+
+#define PB_TRY(expr)                                                           \
+    do { int _s = (expr); if (_s != PB_OK) return _s; } while (0)
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// TMA descriptor for a row-major f32 matrix [rows, cols] with row pitch `pitch` (floats, multiple of 4),
+// tiled in boxes of [box_rows, box_cols]; out-of-bounds elements read as zero.
+int make_tmap_2d_f32(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t pitch,
+                     int box_cols, int box_rows);
+
+// launch counter (gpu_launches claim of bench.py): every kernel launch goes through PB_LAUNCH
+extern thread_local int64_t g_launch_count;
+#define PB_COUNT_LAUNCH() (++pb::g_launch_count)
+
+// ---------------------------------------------------------------- device side ------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a pipeline bug traps instead of hanging the box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) {
+            printf("[parrot_b200] mbarrier wait timed out: block (%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+// TMA: 2-D tiled load global -> shared, completion on mbarrier (bytes = full box, OOB zero-filled).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+// TMA: 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16).
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pb

@@ -1,0 +1,392 @@
+// voc_api.cu - C ABI of the HiFi-GAN code generator: handle, checkpoint ingestion (weight-norm fold + pack),
+// forward orchestration.  Reference: utils/vocoder/models.py:69-169, utils/vocoder/inference.py:65-74,104-109.
+#include <string.h>
+
+#include "pb_runtime.cuh"
+#include "pb_voc.cuh"
+
+using namespace pb;
+
+namespace {
+
+struct ConvSlot {          // one convolution's packed parameters inside the arena
+    size_t w_off = 0, b_off = 0;
+    int Cin = 0, Cout = 0, K = 0, D = 1, co_tile = 0;
+    bool transposed = false;
+    std::string key;
+};
+
+}  // namespace
+
+struct pb_voc {
+    pb_voc_cfg cfg;
+    int device = 0;
+    bool finalized = false;
+    int hop = 1;
+    std::map<std::string, StagedTensor> staged;
+    // packed parameters: one arena whose layout is a pure function of cfg (so it can be broadcast)
+    DevBuf arena;
+    size_t arena_bytes = 0;
+    ConvSlot conv_pre, conv_post;
+    std::vector<ConvSlot> ups;
+    std::vector<ConvSlot> rb1, rb2;   // index ((i * num_kernels + j) * num_dilations + m)
+    size_t dict_off = 0, spkr_off = 0;
+    DevBuf work;
+    int64_t last_launches = 0;
+    float* A(size_t off) const { return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(arena.ptr) + off); }
+};
+
+static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
+
+static void plan_slot(pb_voc* h, ConvSlot& s, const std::string& key, int Cin, int Cout, int K, int D, bool transposed,
+                      int co_tile) {
+    s.key = key; s.Cin = Cin; s.Cout = Cout; s.K = K; s.D = D; s.transposed = transposed; s.co_tile = co_tile;
+    s.w_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + (size_t)Cin * Cout * K * sizeof(float));
+    s.b_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + (size_t)Cout * sizeof(float));
+}
+
+extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
+    PB_REQUIRE(cfg && out, PB_ERR_INVALID, "pb_voc_create: null argument");
+    PB_REQUIRE(cfg->num_upsamples > 0 && cfg->num_upsamples <= PB_VOC_MAX_UPS && cfg->num_kernels > 0 &&
+                   cfg->num_kernels <= PB_VOC_MAX_RESK && cfg->num_dilations > 0 && cfg->num_dilations <= PB_VOC_MAX_DIL,
+               PB_ERR_INVALID, "pb_voc_create: layer counts out of range");
+    PB_REQUIRE(cfg->upsample_initial_channel % (1 << cfg->num_upsamples) == 0, PB_ERR_INVALID,
+               "pb_voc_create: upsample_initial_channel=%d not divisible by 2^%d", cfg->upsample_initial_channel, cfg->num_upsamples);
+    pb_voc* h = new pb_voc();
+    h->cfg = *cfg;
+    PB_CUDA(cudaGetDevice(&h->device));
+    const int c0 = cfg->upsample_initial_channel;
+    int co = conv_co_tile(c0);
+    if (!co || cfg->model_in_dim % 8) { delete h; set_error("pb_voc_create: unsupported channel counts"); return PB_ERR_INVALID; }
+    plan_slot(h, h->conv_pre, "conv_pre", cfg->model_in_dim, c0, 7, 1, false, co);
+    h->hop = 1;
+    for (int i = 0; i < cfg->num_upsamples; ++i) {
+        const int cin = c0 >> i, cout = c0 >> (i + 1);
+        const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+        h->hop *= u;
+        const int ct = convtr_co_tile(cout, u);
+        if (!ct || (k - u) % 2 || cin % 8) { delete h; set_error("pb_voc_create: unsupported upsample layer %d", i); return PB_ERR_INVALID; }
+        ConvSlot s;
+        plan_slot(h, s, "ups." + std::to_string(i), cin, cout, k, 1, true, ct);
+        h->ups.push_back(s);
+        const int cr = conv_co_tile(cout);
+        if (!cr || cout % 8) { delete h; set_error("pb_voc_create: unsupported resblock width %d", cout); return PB_ERR_INVALID; }
+        for (int j = 0; j < cfg->num_kernels; ++j)
+            for (int m = 0; m < cfg->num_dilations; ++m) {
+                const std::string p = "resblocks." + std::to_string(i * cfg->num_kernels + j);
+                ConvSlot a, b;
+                plan_slot(h, a, p + ".convs1." + std::to_string(m), cout, cout, cfg->resblock_kernel_sizes[j],
+                          cfg->resblock_dilation_sizes[j][m], false, cr);
+                plan_slot(h, b, p + ".convs2." + std::to_string(m), cout, cout, cfg->resblock_kernel_sizes[j], 1, false, cr);
+                h->rb1.push_back(a);
+                h->rb2.push_back(b);
+            }
+    }
+    plan_slot(h, h->conv_post, "conv_post", c0 >> cfg->num_upsamples, 1, 7, 1, false, 1);
+    if (cfg->num_embeddings > 0) {
+        h->dict_off = h->arena_bytes;
+        h->arena_bytes = align_up(h->arena_bytes + (size_t)cfg->num_embeddings * cfg->embedding_dim * sizeof(float));
+        if (cfg->num_speakers > 0) {
+            h->spkr_off = h->arena_bytes;
+            h->arena_bytes = align_up(h->arena_bytes + (size_t)cfg->num_speakers * cfg->embedding_dim * sizeof(float));
+        }
+    }
+    int st = h->arena.reserve(h->arena_bytes);
+    if (st != PB_OK) { delete h; return st; }
+    *out = h;
+    return PB_OK;
+}
+
+extern "C" void pb_voc_destroy(pb_voc* h) {
+    if (!h) return;
+    for (auto& kv : h->staged) if (kv.second.ptr) cudaFree(kv.second.ptr);
+    h->arena.release();
+    h->work.release();
+    delete h;
+}
+
+extern "C" int pb_voc_set_weight(pb_voc* h, const char* key, const void* data, const int64_t* shape, int32_t ndim, int32_t dtype) {
+    PB_REQUIRE(h && key && data && shape && ndim > 0 && ndim <= 4, PB_ERR_INVALID, "pb_voc_set_weight: bad argument");
+    PB_REQUIRE(dtype == 0, PB_ERR_INVALID, "pb_voc_set_weight(%s): only float32 tensors are accepted", key);
+    StagedTensor t;
+    t.shape.assign(shape, shape + ndim);
+    t.dtype = dtype;
+    const size_t nbytes = (size_t)t.numel() * sizeof(float);
+    PB_CUDA(cudaMalloc(&t.ptr, nbytes ? nbytes : 4));
+    PB_CUDA(cudaMemcpy(t.ptr, data, nbytes, cudaMemcpyDefault));
+    auto it = h->staged.find(key);
+    if (it != h->staged.end()) { cudaFree(it->second.ptr); h->staged.erase(it); }
+    h->staged[key] = t;
+    h->finalized = false;
+    return PB_OK;
+}
+
+static int finalize_conv(pb_voc* h, const ConvSlot& s, float* scratch, cudaStream_t st) {
+    const StagedTensor* w = nullptr; const StagedTensor* g = nullptr;
+    auto iw = h->staged.find(s.key + ".weight");
+    auto iv = h->staged.find(s.key + ".weight_v");
+    auto ig = h->staged.find(s.key + ".weight_g");
+    if (iw != h->staged.end()) w = &iw->second;
+    else if (iv != h->staged.end() && ig != h->staged.end()) { w = &iv->second; g = &ig->second; }
+    PB_REQUIRE(w != nullptr, PB_ERR_INVALID, "pb_voc_finalize: missing %s.weight (or weight_g/weight_v)", s.key.c_str());
+    const int n0 = s.transposed ? s.Cin : s.Cout, n1 = s.transposed ? s.Cout : s.Cin;
+    PB_REQUIRE(w->shape.size() == 3 && w->shape[0] == n0 && w->shape[1] == n1 && w->shape[2] == s.K, PB_ERR_INVALID,
+               "pb_voc_finalize: %s has shape [%lld,%lld,%lld], expected [%d,%d,%d]", s.key.c_str(),
+               (long long)(w->shape.size() > 0 ? w->shape[0] : -1), (long long)(w->shape.size() > 1 ? w->shape[1] : -1),
+               (long long)(w->shape.size() > 2 ? w->shape[2] : -1), n0, n1, s.K);
+    if (g) PB_REQUIRE(g->numel() == n0, PB_ERR_INVALID, "pb_voc_finalize: %s.weight_g has %lld elements, expected %d", s.key.c_str(), (long long)g->numel(), n0);
+    PB_TRY(launch_weight_norm_fold((const float*)w->ptr, g ? (const float*)g->ptr : nullptr, scratch, n0, n1 * s.K, st));
+    if (s.Cout == 1) {
+        // conv_post: [1, Cin, K] is already [ci][j]
+        PB_CUDA(cudaMemcpyAsync(h->A(s.w_off), scratch, (size_t)s.Cin * s.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (s.transposed) {
+        PB_TRY(launch_pack_conv_weight(scratch, s.K, (int64_t)s.Cout * s.K, h->A(s.w_off), s.Cout, s.Cin, s.K, s.co_tile, st));
+    } else {
+        PB_TRY(launch_pack_conv_weight(scratch, (int64_t)s.Cin * s.K, s.K, h->A(s.w_off), s.Cout, s.Cin, s.K, s.co_tile, st));
+    }
+    auto ib = h->staged.find(s.key + ".bias");
+    PB_REQUIRE(ib != h->staged.end() && ib->second.numel() == s.Cout, PB_ERR_INVALID, "pb_voc_finalize: missing or mis-shaped %s.bias", s.key.c_str());
+    PB_CUDA(cudaMemcpyAsync(h->A(s.b_off), ib->second.ptr, (size_t)s.Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return PB_OK;
+}
+
+extern "C" int pb_voc_finalize(pb_voc* h, void* stream) {
+    PB_REQUIRE(h, PB_ERR_INVALID, "pb_voc_finalize: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t max_w = 0;
+    auto upd = [&](const ConvSlot& s) { max_w = std::max(max_w, (size_t)s.Cin * s.Cout * s.K); };
+    upd(h->conv_pre); upd(h->conv_post);
+    for (auto& s : h->ups) upd(s);
+    for (auto& s : h->rb1) upd(s);
+    float* scratch = nullptr;
+    PB_CUDA(cudaMalloc(&scratch, max_w * sizeof(float)));
+    int rc = PB_OK;
+    auto run = [&](const ConvSlot& s) { if (rc == PB_OK) rc = finalize_conv(h, s, scratch, st); };
+    run(h->conv_pre);
+    for (auto& s : h->ups) run(s);
+    for (auto& s : h->rb1) run(s);
+    for (auto& s : h->rb2) run(s);
+    run(h->conv_post);
+    if (rc == PB_OK && h->cfg.num_embeddings > 0) {
+        auto id = h->staged.find("dict.weight");
+        if (id == h->staged.end() || id->second.numel() != (int64_t)h->cfg.num_embeddings * h->cfg.embedding_dim) {
+            set_error("pb_voc_finalize: missing or mis-shaped dict.weight"); rc = PB_ERR_INVALID;
+        } else {
+            cudaMemcpyAsync(h->A(h->dict_off), id->second.ptr, id->second.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        }
+        if (rc == PB_OK && h->cfg.num_speakers > 0) {
+            auto is = h->staged.find("spkr.weight");
+            if (is == h->staged.end() || is->second.numel() != (int64_t)h->cfg.num_speakers * h->cfg.embedding_dim) {
+                set_error("pb_voc_finalize: missing or mis-shaped spkr.weight"); rc = PB_ERR_INVALID;
+            } else {
+                cudaMemcpyAsync(h->A(h->spkr_off), is->second.ptr, is->second.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            }
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(e);
+    for (auto& kv : h->staged) if (kv.second.ptr) cudaFree(kv.second.ptr);
+    h->staged.clear();
+    h->finalized = true;
+    return PB_OK;
+}
+
+extern "C" int pb_voc_arena_bytes(pb_voc* h, int64_t* bytes) {
+    PB_REQUIRE(h && bytes, PB_ERR_INVALID, "pb_voc_arena_bytes: null argument");
+    *bytes = (int64_t)h->arena_bytes;
+    return PB_OK;
+}
+extern "C" void* pb_voc_arena_ptr(pb_voc* h) { return h ? h->arena.ptr : nullptr; }
+// Non-root ranks call this after receiving the broadcast arena.
+extern "C" int pb_voc_mark_finalized(pb_voc* h) {
+    PB_REQUIRE(h, PB_ERR_INVALID, "pb_voc_mark_finalized: null handle");
+    h->finalized = true;
+    return PB_OK;
+}
+
+extern "C" int64_t pb_voc_last_launches(const pb_voc* h) { return h ? h->last_launches : 0; }
+
+extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
+                              int32_t B, int32_t T, float* wav, void* stream) {
+    PB_REQUIRE(h && wav, PB_ERR_INVALID, "pb_voc_forward: null argument");
+    PB_REQUIRE(h->finalized, PB_ERR_STATE, "pb_voc_forward: weights not finalized");
+    PB_REQUIRE((x != nullptr) != (code != nullptr), PB_ERR_INVALID, "pb_voc_forward: give exactly one of x / code");
+    PB_REQUIRE(B > 0 && T > 0 && B <= 65535, PB_ERR_INVALID, "pb_voc_forward: bad shape B=%d T=%d", B, T);
+    const pb_voc_cfg& c = h->cfg;
+    if (code) {
+        PB_REQUIRE(c.num_embeddings > 0, PB_ERR_INVALID, "pb_voc_forward: handle was created without a unit dictionary");
+        PB_REQUIRE(c.num_speakers == 0 || spkr != nullptr, PB_ERR_INVALID, "pb_voc_forward: spkr ids required (multispkr)");
+        const int in_dim = c.embedding_dim * (c.num_speakers > 0 ? 2 : 1);
+        PB_REQUIRE(in_dim == c.model_in_dim, PB_ERR_INVALID, "pb_voc_forward: embedding dims (%d) != model_in_dim (%d)", in_dim, c.model_in_dim);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t launches0 = g_launch_count;
+    const int c0 = c.upsample_initial_channel;
+    const int P0 = (int)round_up(T, 4);
+
+    // ---- workspace plan: x0, h0, and 7 rotating slots sized for the largest stage
+    size_t slot_floats = 0;
+    {
+        int64_t L = T;
+        for (int i = 0; i < c.num_upsamples; ++i) {
+            L *= c.upsample_rates[i];
+            PB_REQUIRE(L < (1LL << 30), PB_ERR_INVALID, "pb_voc_forward: T=%d too long", T);
+            slot_floats = std::max(slot_floats, (size_t)B * (c0 >> (i + 1)) * (size_t)round_up(L, 4));
+        }
+    }
+    Carver plan(nullptr);
+    plan.take<float>((size_t)B * c.model_in_dim * P0);
+    plan.take<float>((size_t)B * c0 * P0);
+    for (int s = 0; s < 7; ++s) plan.take<float>(slot_floats);
+    PB_TRY(h->work.reserve(plan.off));
+    Carver cv(h->work.ptr);
+    float* x0 = cv.take<float>((size_t)B * c.model_in_dim * P0);
+    float* h0 = cv.take<float>((size_t)B * c0 * P0);
+    float* slot[7];
+    for (int s = 0; s < 7; ++s) slot[s] = cv.take<float>(slot_floats);
+
+    // ---- input features [B, model_in_dim, P0]
+    if (code) {
+        PB_TRY(launch_voc_embed(code, spkr, h->A(h->dict_off), c.num_speakers > 0 ? h->A(h->spkr_off) : nullptr, lens, B, T,
+                                c.embedding_dim, c.num_embeddings, c.num_speakers, P0, x0, st));
+    } else {
+        PB_TRY(launch_repitch(x, T, x0, P0, (int64_t)B * c.model_in_dim, T, lens, 1, c.model_in_dim, st));
+    }
+
+    // ---- conv_pre (+ the leaky_relu that precedes ups[0])
+    {
+        ConvArgs a;
+        a.x = x0; a.w = h->A(h->conv_pre.w_off); a.co_tile = h->conv_pre.co_tile; a.bias = h->A(h->conv_pre.b_off);
+        a.out = h0; a.lens = lens; a.len_mul = 1; a.B = B; a.Cin = c.model_in_dim; a.Cout = c0; a.L = T; a.pitch = P0;
+        a.K = 7; a.D = 1; a.post_slope = 0.1f;
+        PB_TRY(launch_conv1d(a, st));
+    }
+
+    const float* cur_in = h0;
+    int in_slot = -1;
+    int64_t L = T;
+    int pitch_in = P0;
+    int mul = 1;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        const int C = c0 >> (i + 1);
+        const int u = c.upsample_rates[i];
+        const int64_t Lo = L * u;
+        const int P = (int)round_up(Lo, 4);
+        mul *= u;
+        float* buf[6];
+        for (int s = 0, n = 0; s < 7 && n < 6; ++s) if (s != in_slot) buf[n++] = slot[s];
+        float *X = buf[0], *XT = buf[1], *XA = buf[2], *XB = buf[3], *XS = buf[4], *Y = buf[5];
+        int y_slot = 0;
+        for (int s = 0; s < 7; ++s) if (slot[s] == Y) y_slot = s;
+        {
+            const ConvSlot& s = h->ups[i];
+            ConvTrArgs a;
+            a.x = cur_in; a.w = h->A(s.w_off); a.co_tile = s.co_tile; a.bias = h->A(s.b_off); a.out = X;
+            a.lens = lens; a.len_mul = mul; a.B = B; a.Cin = s.Cin; a.Cout = s.Cout; a.Lin = (int)L;
+            a.pitch_in = pitch_in; a.pitch_out = P; a.K = s.K; a.U = u;
+            PB_TRY(launch_convtr1d(a, st));
+        }
+        for (int j = 0; j < c.num_kernels; ++j) {
+            const float* cur = X;
+            for (int m = 0; m < c.num_dilations; ++m) {
+                const int idx = (i * c.num_kernels + j) * c.num_dilations + m;
+                const ConvSlot& s1 = h->rb1[idx];
+                const ConvSlot& s2 = h->rb2[idx];
+                ConvArgs a;
+                a.x = cur; a.w = h->A(s1.w_off); a.co_tile = s1.co_tile; a.bias = h->A(s1.b_off); a.out = XT;
+                a.lens = lens; a.len_mul = mul; a.B = B; a.Cin = C; a.Cout = C; a.L = (int)Lo; a.pitch = P;
+                a.K = s1.K; a.D = s1.D; a.pre_slope = 0.1f; a.post_slope = 0.1f;
+                PB_TRY(launch_conv1d(a, st));
+                ConvArgs b2;
+                b2.x = XT; b2.w = h->A(s2.w_off); b2.co_tile = s2.co_tile; b2.bias = h->A(s2.b_off); b2.res = cur;
+                b2.lens = lens; b2.len_mul = mul; b2.B = B; b2.Cin = C; b2.Cout = C; b2.L = (int)Lo; b2.pitch = P;
+                b2.K = s2.K; b2.D = 1;
+                if (m + 1 < c.num_dilations) {
+                    float* dst = (cur == XA) ? XB : XA;
+                    b2.out = dst;
+                    PB_TRY(launch_conv1d(b2, st));
+                    cur = dst;
+                } else {
+                    // xs (+)= resblock output; the last kernel size also takes the mean and the next activation
+                    if (j > 0) b2.accin = XS;
+                    if (j + 1 < c.num_kernels) {
+                        b2.out = XS;
+                    } else {
+                        b2.out = Y;
+                        b2.acc_div = (float)c.num_kernels;
+                        b2.post_slope = (i + 1 < c.num_upsamples) ? 0.1f : 0.01f;
+                    }
+                    PB_TRY(launch_conv1d(b2, st));
+                }
+            }
+        }
+        cur_in = Y; in_slot = y_slot; L = Lo; pitch_in = P;
+    }
+    PB_TRY(launch_conv_post(cur_in, h->A(h->conv_post.w_off), h->A(h->conv_post.b_off), wav, lens, mul, B,
+                            h->conv_post.Cin, (int)L, pitch_in, L, 7, st));
+    h->last_launches = g_launch_count - launches0;
+    return PB_OK;
+}
+
+extern "C" int pb_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, void* stream) {
+    PB_REQUIRE(wav && pcm && n >= 0, PB_ERR_INVALID, "pb_wav_to_pcm16: bad argument");
+    return launch_wav_to_pcm16(wav, n, pcm, (cudaStream_t)stream);
+}
+
+// ---- per-op entry points (unit tests): torch-layout weights are packed on the fly ------------------
+extern "C" int pb_conv1d(const float* x, const float* w, const float* bias, const float* res, float* y, int32_t B, int32_t Cin,
+                         int32_t Cout, int32_t L, int32_t K, int32_t dilation, float pre_slope, float post_slope,
+                         void* stream) {
+    PB_REQUIRE(x && w && y, PB_ERR_INVALID, "pb_conv1d: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ct = conv_co_tile(Cout);
+    PB_REQUIRE(ct > 0, PB_ERR_INVALID, "pb_conv1d: Cout=%d must be a multiple of 16", Cout);
+    const int P = (int)round_up(L, 4);
+    float *xp = nullptr, *yp = nullptr, *rp = nullptr, *wp = nullptr;
+    PB_CUDA(cudaMalloc(&xp, (size_t)B * Cin * P * sizeof(float)));
+    PB_CUDA(cudaMalloc(&yp, (size_t)B * Cout * P * sizeof(float)));
+    PB_CUDA(cudaMalloc(&wp, (size_t)Cout * Cin * K * sizeof(float)));
+    if (res) PB_CUDA(cudaMalloc(&rp, (size_t)B * Cout * P * sizeof(float)));
+    int rc = launch_repitch(x, L, xp, P, (int64_t)B * Cin, L, nullptr, 1, Cin, st);
+    if (rc == PB_OK && res) rc = launch_repitch(res, L, rp, P, (int64_t)B * Cout, L, nullptr, 1, Cout, st);
+    if (rc == PB_OK) rc = launch_pack_conv_weight(w, (int64_t)Cin * K, K, wp, Cout, Cin, K, ct, st);
+    if (rc == PB_OK) {
+        ConvArgs a;
+        a.x = xp; a.w = wp; a.co_tile = ct; a.bias = bias; a.res = rp; a.out = yp; a.B = B; a.Cin = Cin; a.Cout = Cout;
+        a.L = L; a.pitch = P; a.K = K; a.D = dilation; a.pre_slope = pre_slope; a.post_slope = post_slope;
+        rc = launch_conv1d(a, st);
+    }
+    if (rc == PB_OK) rc = launch_repitch(yp, P, y, L, (int64_t)B * Cout, L, nullptr, 1, Cout, st);
+    cudaStreamSynchronize(st);
+    cudaFree(xp); cudaFree(yp); cudaFree(wp); if (rp) cudaFree(rp);
+    return rc;
+}
+
+extern "C" int pb_conv_transpose1d(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,
+                                   int32_t Cout, int32_t L, int32_t K, int32_t stride, float pre_slope, void* stream) {
+    PB_REQUIRE(x && w && y, PB_ERR_INVALID, "pb_conv_transpose1d: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ct = convtr_co_tile(Cout, stride);
+    PB_REQUIRE(ct > 0, PB_ERR_INVALID, "pb_conv_transpose1d: Cout=%d must be a multiple of 16", Cout);
+    const int P = (int)round_up(L, 4);
+    const int64_t Lo = (int64_t)L * stride;
+    const int Po = (int)round_up(Lo, 4);
+    float *xp = nullptr, *yp = nullptr, *wp = nullptr;
+    PB_CUDA(cudaMalloc(&xp, (size_t)B * Cin * P * sizeof(float)));
+    PB_CUDA(cudaMalloc(&yp, (size_t)B * Cout * Po * sizeof(float)));
+    PB_CUDA(cudaMalloc(&wp, (size_t)Cout * Cin * K * sizeof(float)));
+    int rc = launch_repitch(x, L, xp, P, (int64_t)B * Cin, L, nullptr, 1, Cin, st);
+    if (rc == PB_OK) rc = launch_pack_conv_weight(w, K, (int64_t)Cout * K, wp, Cout, Cin, K, ct, st);
+    if (rc == PB_OK) {
+        ConvTrArgs a;
+        a.x = xp; a.w = wp; a.co_tile = ct; a.bias = bias; a.out = yp; a.B = B; a.Cin = Cin; a.Cout = Cout; a.Lin = L;
+        a.pitch_in = P; a.pitch_out = Po; a.K = K; a.U = stride; a.pre_slope = pre_slope;
+        rc = launch_convtr1d(a, st);
+    }
+    if (rc == PB_OK) rc = launch_repitch(yp, Po, y, Lo, (int64_t)B * Cout, (int)Lo, nullptr, 1, Cout, st);
+    cudaStreamSynchronize(st);
+    cudaFree(xp); cudaFree(yp); cudaFree(wp);
+    return rc;
+}

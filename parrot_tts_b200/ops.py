@@ -1,0 +1,57 @@
+"""Single-op entry points of libparrot_b200.so on torch CUDA tensors (used by the unit tests and by the
+FFTBlock / DurationPredictor / length_regulator mirrors).  Every function runs the same sm_100a kernel
+the fused model path uses; there is no fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _f32(t):
+    return t.to(torch.float32).contiguous()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.ParrotB200Error("parrot_tts_b200.ops need CUDA tensors (no CPU path)")
+
+
+def conv1d(x, w, bias=None, dilation=1, res=None, pre_slope=1.0, post_slope=1.0):
+    """post(conv1d(pre(x), w, bias, 'same', dilation) [+ res]); x [B,Cin,L], w [Cout,Cin,K]."""
+    _need_cuda(x, w, bias, res)
+    x, w = _f32(x), _f32(w)
+    B, Cin, L = x.shape
+    Cout, _, K = w.shape
+    bias = _f32(bias) if bias is not None else None
+    res = _f32(res) if res is not None else None
+    y = torch.empty(B, Cout, L, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pb_conv1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(y),
+                                         B, Cin, Cout, L, K, dilation, pre_slope, post_slope, _lib.stream_ptr(x.device)))
+    return y
+
+
+def conv_transpose1d(x, w, bias=None, stride=1, pre_slope=1.0):
+    """conv_transpose1d(pre(x), w [Cin,Cout,K], bias, stride, padding=(K-stride)/2) -> [B,Cout,stride*L]."""
+    _need_cuda(x, w, bias)
+    x, w = _f32(x), _f32(w)
+    B, Cin, L = x.shape
+    _, Cout, K = w.shape
+    bias = _f32(bias) if bias is not None else None
+    y = torch.empty(B, Cout, L * stride, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pb_conv_transpose1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y),
+                                                   B, Cin, Cout, L, K, stride, pre_slope, _lib.stream_ptr(x.device)))
+    return y
+
+
+def wav_to_pcm16(wav):
+    """(wav * 32768) -> int16 with the reference's cast semantics (utils/vocoder/inference.py:71-73)."""
+    _need_cuda(wav)
+    wav = _f32(wav)
+    pcm = torch.empty(wav.shape, device=wav.device, dtype=torch.int16)
+    with torch.cuda.device(wav.device):
+        _lib.check(_lib.load().pb_wav_to_pcm16(_lib.ptr(wav), wav.numel(), _lib.ptr(pcm), _lib.stream_ptr(wav.device)))
+    return pcm

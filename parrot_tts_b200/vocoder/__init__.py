@@ -1,0 +1,2 @@
+from .models import CodeGenerator, Generator, ResBlock1, ResBlock2  # noqa: F401
+from .utils import AttrDict, get_padding, init_weights  # noqa: F401

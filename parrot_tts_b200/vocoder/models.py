@@ -1,0 +1,237 @@
+"""HiFi-GAN code generator with the reference's class names, constructor/forward signatures and
+state_dict layout (reference utils/vocoder/models.py:13-169), executing on libparrot_b200.so.
+
+The torch.nn conv modules below are *parameter containers only* - they give ``state_dict()`` /
+``load_state_dict()`` exactly the reference's key names and shapes (old-style weight norm:
+``weight_g`` / ``weight_v``; plain ``weight`` after ``remove_weight_norm()``).  ``forward`` never
+calls them: it hands the tensors to the sm_100a kernels through the C ABI.  There is no PyTorch
+or CPU fallback - calling ``forward`` on CPU tensors raises.
+"""
+import ctypes as C
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .utils import get_padding, init_weights
+
+LRELU_SLOPE = 0.1
+
+
+def _wn(module):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return torch.nn.utils.weight_norm(module)
+
+
+def _strip_wn(module):
+    torch.nn.utils.remove_weight_norm(module)
+
+
+class _ResBlockParams(nn.Module):
+    """Parameter container shared by ResBlock1 / ResBlock2."""
+
+    def _make(self, channels, kernel_size, dilations):
+        convs = nn.ModuleList(
+            _wn(nn.Conv1d(channels, channels, kernel_size, 1, dilation=d, padding=get_padding(kernel_size, d)))
+            for d in dilations)
+        convs.apply(init_weights)
+        return convs
+
+    def forward(self, x):
+        raise RuntimeError("resblocks execute inside Generator.forward (fused sm_100a kernels); "
+                           "use parrot_tts_b200.ops.conv1d for a single convolution")
+
+
+class ResBlock1(_ResBlockParams):
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5)):
+        super().__init__()
+        self.h = h
+        self.convs1 = self._make(channels, kernel_size, dilation)
+        self.convs2 = self._make(channels, kernel_size, [1] * len(dilation))
+
+    def remove_weight_norm(self):
+        for conv in list(self.convs1) + list(self.convs2):
+            _strip_wn(conv)
+
+
+class ResBlock2(_ResBlockParams):
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3)):
+        super().__init__()
+        self.h = h
+        self.convs = self._make(channels, kernel_size, dilation)
+
+    def remove_weight_norm(self):
+        for conv in self.convs:
+            _strip_wn(conv)
+
+
+class _Engine:
+    """Owns one pb_voc handle for (module, device); rebuilt when the parameters change."""
+
+    def __init__(self):
+        self.handle = None
+        self.stamp = None
+        self.device = None
+
+    def close(self):
+        if self.handle is not None:
+            _lib.load().pb_voc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Generator(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.h = h
+        if str(h.resblock) != "1":
+            raise NotImplementedError("only resblock type '1' (the reference config) has sm_100a kernels")
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        c0 = h.upsample_initial_channel
+        self.conv_pre = _wn(nn.Conv1d(getattr(h, "model_in_dim", 128), c0, 7, 1, padding=3))
+        self.ups = nn.ModuleList(
+            _wn(nn.ConvTranspose1d(c0 // 2 ** i, c0 // 2 ** (i + 1), k, u, padding=(k - u) // 2))
+            for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)))
+        self.resblocks = nn.ModuleList(
+            ResBlock1(h, c0 // 2 ** (i + 1), k, d)
+            for i in range(self.num_upsamples)
+            for k, d in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes))
+        self.conv_post = _wn(nn.Conv1d(c0 // 2 ** self.num_upsamples, 1, 7, 1, padding=3))
+        self.ups.apply(init_weights)
+        self.conv_post.apply(init_weights)
+        self._eng = _Engine()
+        self.hop = 1
+        for u in h.upsample_rates:
+            self.hop *= int(u)
+
+    # ------------------------------------------------------------------ engine management
+    def _has_code_path(self):
+        return False
+
+    def _cfg(self):
+        h = self.h
+        cfg = _lib.VocCfg()
+        cfg.model_in_dim = int(getattr(h, "model_in_dim", 128))
+        cfg.upsample_initial_channel = int(h.upsample_initial_channel)
+        cfg.num_upsamples = self.num_upsamples
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            cfg.upsample_rates[i] = int(u)
+            cfg.upsample_kernel_sizes[i] = int(k)
+        cfg.num_kernels = self.num_kernels
+        dil = h.resblock_dilation_sizes
+        cfg.num_dilations = len(dil[0])
+        for j, k in enumerate(h.resblock_kernel_sizes):
+            cfg.resblock_kernel_sizes[j] = int(k)
+            if len(dil[j]) != cfg.num_dilations:
+                raise ValueError("all resblocks must have the same number of dilations")
+            for m, d in enumerate(dil[j]):
+                cfg.resblock_dilation_sizes[j][m] = int(d)
+        cfg.num_embeddings = 0
+        cfg.embedding_dim = 0
+        cfg.num_speakers = 0
+        return cfg
+
+    def _stamp(self, device):
+        return (str(device),) + tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+
+    def _engine(self, device):
+        """pb_voc handle holding the folded + packed copy of the current parameters."""
+        stamp = self._stamp(device)
+        eng = self._eng
+        if eng.handle is not None and eng.stamp == stamp:
+            return eng.handle
+        lib = _lib.load()
+        eng.close()
+        with torch.cuda.device(device):
+            hnd = C.c_void_p()
+            cfg = self._cfg()
+            _lib.check(lib.pb_voc_create(C.byref(cfg), C.byref(hnd)))
+            try:
+                for key, t in self.state_dict().items():
+                    t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+                    shape = (C.c_int64 * t.dim())(*t.shape)
+                    _lib.check(lib.pb_voc_set_weight(hnd, key.encode(), _lib.ptr(t), shape, t.dim(), 0))
+                _lib.check(lib.pb_voc_finalize(hnd, _lib.stream_ptr(device)))
+            except Exception:
+                lib.pb_voc_destroy(hnd)
+                raise
+        eng.handle, eng.stamp, eng.device = hnd, stamp, device
+        return hnd
+
+    def _run(self, x=None, code=None, spkr=None, lens=None):
+        ref = x if x is not None else code
+        if not ref.is_cuda:
+            raise _lib.ParrotB200Error("Generator.forward needs CUDA tensors: the vocoder has no CPU path")
+        device = ref.device
+        lib = _lib.load()
+        hnd = self._engine(device)
+        B, T = (x.shape[0], x.shape[2]) if x is not None else code.shape
+        wav = torch.empty(B, 1, self.hop * T, device=device, dtype=torch.float32)
+        if x is not None:
+            x = x.to(torch.float32).contiguous()
+        else:
+            code = code.to(torch.int64).contiguous()
+            if spkr is not None:
+                spkr = spkr.to(device=device, dtype=torch.int64).reshape(-1).contiguous()
+                if spkr.numel() != B:
+                    raise ValueError(f"spkr must hold one id per item, got {spkr.numel()} for batch {B}")
+        if lens is not None:
+            lens = torch.as_tensor(lens).to(device=device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(device):
+            _lib.check(lib.pb_voc_forward(hnd, _lib.ptr(x), _lib.ptr(code), _lib.ptr(spkr), _lib.ptr(lens),
+                                          B, T, _lib.ptr(wav), _lib.stream_ptr(device)))
+        self.last_launches = int(lib.pb_voc_last_launches(hnd))
+        return wav
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x):
+        """f32 [B, model_in_dim, T] -> f32 [B, 1, hop*T] (reference utils/vocoder/models.py:95-111)."""
+        return self._run(x=x)
+
+    def remove_weight_norm(self):
+        for up in self.ups:
+            _strip_wn(up)
+        for rb in self.resblocks:
+            rb.remove_weight_norm()
+        _strip_wn(self.conv_pre)
+        _strip_wn(self.conv_post)
+
+
+class CodeGenerator(Generator):
+    def __init__(self, h):
+        super().__init__(h)
+        self.dict = nn.Embedding(h.num_embeddings, h.embedding_dim)
+        self.f0 = h.get("f0", None)
+        self.multispkr = h.get("multispkr", None)
+        if self.multispkr:
+            self.spkr = nn.Embedding(10, h.embedding_dim)
+
+    def _cfg(self):
+        cfg = super()._cfg()
+        cfg.num_embeddings = int(self.h.num_embeddings)
+        cfg.embedding_dim = int(self.h.embedding_dim)
+        cfg.num_speakers = int(self.spkr.num_embeddings) if self.multispkr else 0
+        return cfg
+
+    def forward(self, **kwargs):
+        """code i64 [B,T], spkr i64 [B,1] -> f32 [B,1,hop*T] (reference utils/vocoder/models.py:153-169).
+
+        ``lens`` (i32/i64 [B], optional, not in the reference) gives each item's true unit count: every
+        item then equals its own batch-of-1 result instead of the padded-rectangle result.
+        """
+        extra = [k for k in kwargs if k not in ("code", "spkr", "f0", "lens")]
+        if extra:
+            raise NotImplementedError(f"extra conditioning features {extra} are not supported: model_in_dim is "
+                                      "fully used by the unit and speaker embeddings")
+        spkr = kwargs.get("spkr") if self.multispkr else None
+        if self.multispkr and spkr is None:
+            raise KeyError("spkr")
+        return self._run(code=kwargs["code"], spkr=spkr, lens=kwargs.get("lens"))
