@@ -162,6 +162,8 @@ int pb_layernorm(const float* x, const float* gamma, const float* beta, float* y
  * x,y f32 [B,L,D]; key_valid u8 [B,L] (1 = attend) or NULL. */
 int pb_tte_fft_block(pb_tte* h, int32_t stack, int32_t layer, const float* x, const uint8_t* key_valid,
                      int32_t B, int32_t L, float* y, void* stream);
+/* DurationPredictor.forward (duration.py:41-48) and the rounding of parrot.py:82-86 on x f32 [B,S,D]; dur may be NULL. */
+int pb_tte_duration(pb_tte* h, const float* x, const uint8_t* src_mask, int32_t B, int32_t S, float* log_dur, int64_t* dur, void* stream);
 /* length_regulator (duration.py:6-24) + optional pos row add: seq f32 [B,S,D], dur i64 [B,S] ->
  * out f32 [B,T,D] (zero rows past each item's end), tgt_mask u8 [B,T]. pe_row: f32 [D] or NULL. */
 int pb_length_regulate(const float* seq, const int64_t* dur, const float* pe_row, int32_t B, int32_t S, int32_t D, int32_t T,
@@ -178,6 +180,9 @@ int pb_voc_arena_bytes(pb_voc* h, int64_t* bytes);
 void* pb_voc_arena_ptr(pb_voc* h);
 int pb_tte_arena_bytes(pb_tte* h, int64_t* bytes);
 void* pb_tte_arena_ptr(pb_tte* h);
+/* non-root ranks: declare the arena complete after it has been received */
+int pb_voc_mark_finalized(pb_voc* h);
+int pb_tte_mark_finalized(pb_tte* h);
 
 #ifdef __cplusplus
 }

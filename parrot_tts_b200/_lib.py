@@ -71,6 +71,7 @@ SIGNATURES = {
     "pb_tte_mark_finalized": (C.c_int, [_P]),
     "pb_layernorm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),
     "pb_tte_fft_block": (C.c_int, [_P, _I32, _I32, _P, _P, _I32, _I32, _P, _P]),
+    "pb_tte_duration": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P, _P]),
     "pb_length_regulate": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "pb_linear": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
 }

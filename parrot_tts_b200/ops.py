@@ -55,3 +55,28 @@ def wav_to_pcm16(wav):
     with torch.cuda.device(wav.device):
         _lib.check(_lib.load().pb_wav_to_pcm16(_lib.ptr(wav), wav.numel(), _lib.ptr(pcm), _lib.stream_ptr(wav.device)))
     return pcm
+
+
+def linear(x, w, bias=None, mode=0):
+    """nn.Linear: x [M,K] . w[N,K]^T + bias (fp32)."""
+    _need_cuda(x, w, bias)
+    x, w = _f32(x), _f32(w)
+    M, K = x.shape
+    N = w.shape[0]
+    bias = _f32(bias) if bias is not None else None
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pb_linear(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), M, N, K, mode, _lib.stream_ptr(x.device)))
+    return y
+
+
+def layernorm(x, gamma, beta):
+    """nn.LayerNorm(256), eps 1e-5, over the last dim."""
+    _need_cuda(x, gamma, beta)
+    x = _f32(x)
+    D = x.shape[-1]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pb_layernorm(_lib.ptr(x), _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)), _lib.ptr(y),
+                                            x.numel() // D, D, _lib.stream_ptr(x.device)))
+    return y

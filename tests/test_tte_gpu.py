@@ -1,0 +1,217 @@
+"""GPU parity: TTE kernels and the full Parrot path against the CPU oracle and the golden vectors recorded
+from the reference.  Integer outputs (durations, unit ids, masks) must be bit-exact; floats within fp32
+round-off (tolerances written per assert)."""
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tte_oracle
+from parrot_tts_b200 import configs, ops, synth
+from parrot_tts_b200.tte import DurationPredictor, FFTBlock, LitParrot, Parrot, SinusoidalPosEmb, length_regulator
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+VOCAB, NSPK = 150, 10
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _cfg(max_len=None):
+    d = tempfile.mkdtemp(prefix="parrot_tte_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({f"s{i}": i for i in range(NSPK)}, f)
+    return configs.default_tte_config(root_path=d, max_len=max_len)
+
+
+def _parrot(seed=0, max_len=None, **synth_kw):
+    cfg = _cfg(max_len)
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=seed, **synth_kw)
+    m = Parrot(cfg, VOCAB, 0)
+    m.load_state_dict(sd, strict=True)
+    return cfg, sd, m.eval().to(DEV)
+
+
+def _to_dev(batch):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 256, 256), (130, 768, 256), (257, 1000, 256), (64, 256, 1024), (300, 100, 36)])
+def test_linear_kernel(M, N, K):
+    g = _gen(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = x @ w.t() + b
+    got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV)).cpu()
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), float((got - ref).abs().max())
+
+
+def test_layernorm_kernel():
+    g = _gen(1)
+    x = torch.randn(37, 256, generator=g) * 3 + 1
+    w, b = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    ref = F.layer_norm(x, (256,), w, b, 1e-5)
+    got = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV)).cpu()
+    assert torch.allclose(got, ref, atol=5e-6, rtol=1e-5), float((got - ref).abs().max())
+
+
+def test_length_regulator_matches_oracle():
+    g = _gen(2)
+    seq = torch.randn(3, 11, 256, generator=g)
+    dur = torch.randint(0, 6, (3, 11), generator=g)
+    dur[2] = 0
+    dur[2, 3] = 2                       # an item much shorter than the batch maximum
+    ref, ref_mask, _ = tte_oracle.length_regulator(seq, dur)
+    got, mask = length_regulator(seq.to(DEV), dur.to(DEV))
+    assert torch.equal(got.cpu(), ref)              # pure gather: bit-exact
+    assert torch.equal(mask.cpu(), ref_mask)        # `<=` off-by-one mask (data.py:18)
+
+
+def test_pos_emb_single_row_quirk():
+    pe = SinusoidalPosEmb(64, 256).to(DEV)
+    x = torch.randn(2, 9, 256, generator=_gen(3))
+    got = pe(x.to(DEV)).cpu()
+    assert torch.equal(got, pe.pe.cpu()[9] + x)     # row index = sequence LENGTH, same row for every position
+    with pytest.raises(IndexError):
+        pe(torch.zeros(1, 64, 256, device=DEV))
+
+
+@pytest.mark.parametrize("fold", [True, False])
+@pytest.mark.parametrize("B,L", [(1, 5), (2, 37), (3, 130)])
+def test_fft_block_matches_oracle(fold, B, L):
+    cfg = _cfg()
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=5)
+    p = "decoder_layers.1"
+    blk = FFTBlock(256, 2, 1024, [9, 1], 0.1)
+    blk.load_state_dict({k[len(p) + 1:]: v for k, v in sd.items() if k.startswith(p + ".")}, strict=True)
+    blk = blk.eval().to(DEV)
+    blk.fold_projections = fold
+    g = _gen(B * 100 + L)
+    x = torch.randn(B, L, 256, generator=g)
+    pad = torch.zeros(B, L, dtype=torch.bool)
+    if B > 1:
+        pad[1, L // 2:] = True
+    with torch.no_grad():
+        ref = tte_oracle.fft_block(sd, p, x, pad, 2)
+    got = blk(x.to(DEV), key_padding_mask=pad.to(DEV)).cpu()
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4), float((got - ref).abs().max())
+
+
+def test_duration_predictor_matches_oracle():
+    cfg = _cfg()
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=6)
+    dp = DurationPredictor(256, 256, 3, 0.5)
+    dp.load_state_dict({k[len("duration_predictor."):]: v for k, v in sd.items() if k.startswith("duration_predictor.")}, strict=True)
+    dp = dp.eval().to(DEV)
+    g = _gen(7)
+    x = torch.randn(2, 23, 256, generator=g)
+    mask = torch.zeros(2, 23, dtype=torch.bool)
+    mask[1, 15:] = True
+    with torch.no_grad():
+        ref = tte_oracle.duration_predictor(sd, x, mask)
+    got = dp(x.to(DEV), mask.to(DEV)).cpu()
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), float((got - ref).abs().max())
+    assert (got[1, 15:] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged"])
+def test_parrot_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    _, _, m = _parrot(seed=int(g["seed"]))
+    batch = _to_dev({"phones": torch.from_numpy(g["phones"]), "src_mask": torch.from_numpy(g["src_mask"]),
+                     "speaker": torch.from_numpy(g["speaker"])})
+    logits, src_mask, tgt_mask, log_dur = m(batch, inference=True)
+    np.testing.assert_allclose(log_dur.cpu().numpy(), g["log_dur"], rtol=0, atol=5e-5)
+    assert np.array_equal(tgt_mask.cpu().numpy(), g["tgt_mask"])                   # implies bit-exact durations
+    ids = m.infer(batch)
+    assert [len(x) for x in ids] == g["ids_lens"].tolist()
+    flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in ids])
+    mism = np.nonzero(flat != g["ids_flat"])[0]
+    am = torch.argmax(logits, -1).cpu().numpy()
+    bad = np.argwhere(am != g["argmax"])
+    detail = [(tuple(ix), float(g["margin"][tuple(ix)])) for ix in bad[:5]]
+    assert mism.size == 0 and bad.size == 0, f"{mism.size} id mismatches; first (index, reference top-2 margin): {detail}"
+    stride = int(g["logits_row_stride"])
+    np.testing.assert_allclose(logits[:, ::stride].cpu().numpy(), g["logits_rows"], rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("fold", [True, False])
+def test_parrot_vs_oracle_random_batch(fold):
+    cfg, sd, m = _parrot(seed=21)
+    m.fold_projections = fold
+    g = _gen(8)
+    phones = torch.randint(2, VOCAB, (4, 33), generator=g)
+    phones[1, 20:] = 0
+    phones[3, 5:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([0, 9, 4, 2])}
+    ids_ref, r = tte_oracle.parrot_infer(sd, batch)
+    ids = m.infer(_to_dev(batch))
+    logits, _, tgt_mask, log_dur = m(_to_dev(batch), inference=True)
+    assert torch.equal(tgt_mask.cpu(), r["tgt_mask"])
+    assert torch.allclose(log_dur.cpu(), r["log_dur"], atol=5e-5, rtol=0)
+    top2 = torch.topk(r["logits"], 2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]
+    n_bad = 0
+    for b, (a, e) in enumerate(zip(ids, ids_ref)):
+        assert len(a) == len(e)
+        for t, (u, v) in enumerate(zip(a, e)):
+            if u != v:
+                n_bad += 1
+                assert margin[b, t] < 1e-4, f"id mismatch at a clear-cut position b={b} t={t} margin={float(margin[b, t])}"
+    assert n_bad == 0, f"{n_bad} near-tie id mismatches"
+    assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0), float((logits.cpu() - r["logits"]).abs().max())
+
+
+def test_parrot_teacher_forced_durations():
+    cfg, sd, m = _parrot(seed=22)
+    g = _gen(9)
+    phones = torch.randint(2, VOCAB, (2, 10), generator=g)
+    dur = torch.randint(0, 5, (2, 10), generator=g)
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([1, 2]), "duration": dur}
+    r = tte_oracle.parrot_forward(sd, batch, dur_override=dur)
+    logits, _, tgt_mask, _ = m(_to_dev(batch), inference=False)
+    assert torch.equal(tgt_mask.cpu(), r["tgt_mask"])
+    assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0)
+
+
+def test_parrot_rejects_overlong_like_reference():
+    _, _, m = _parrot(seed=0, max_len=40)
+    phones = torch.randint(2, VOCAB, (1, 40), generator=_gen(1))
+    with pytest.raises(IndexError):                       # source length hits the pe table (fft.py:18)
+        m({"phones": phones.to(DEV), "src_mask": (phones != 0).to(DEV), "speaker": torch.zeros(1, dtype=torch.long, device=DEV)}, inference=True)
+    phones = torch.randint(2, VOCAB, (1, 30), generator=_gen(1))
+    with pytest.raises(IndexError):                       # ~8 units per char -> unit length >= 40
+        m({"phones": phones.to(DEV), "src_mask": (phones != 0).to(DEV), "speaker": torch.zeros(1, dtype=torch.long, device=DEV)}, inference=True)
+
+
+def test_const8_duration_recipe():
+    """Throughput recipe of SURVEY.md 8d: every real char -> exactly 8 units."""
+    _, _, m = _parrot(seed=0, dur_mode="const8")
+    phones = torch.randint(2, VOCAB, (2, 64), generator=_gen(4))
+    phones[1, 40:] = 0
+    ids, n = m.infer_device({"phones": phones.to(DEV), "src_mask": (phones != 0).to(DEV), "speaker": torch.tensor([0, 1], device=DEV)})
+    assert ids.shape == (2, 512)
+    assert n.tolist() == [512, 321]       # min(len + 1, T): the `<=` mask emits one extra position for the shorter item
+
+
+def test_lit_parrot_checkpoint_roundtrip(tmp_path):
+    cfg = _cfg()
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=3)
+    lit = LitParrot(cfg, VOCAB, 0)
+    lit.parrot.load_state_dict(sd)
+    path = str(tmp_path / "epoch=0-step=1000.ckpt")
+    lit.save_checkpoint(path)
+    ck = torch.load(path, weights_only=True)
+    assert set(ck) >= {"state_dict", "hyper_parameters"} and all(k.startswith("parrot.") for k in ck["state_dict"])
+    model = LitParrot.load_from_checkpoint(path, weights_only=True).to(DEV)
+    phones = torch.randint(2, VOCAB, (1, 12), generator=_gen(5))
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([3])}
+    ids_ref, _ = tte_oracle.parrot_infer(sd, batch)
+    assert model.infer(_to_dev(batch)) == ids_ref
