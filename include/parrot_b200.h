@@ -95,6 +95,13 @@ int pb_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, void* stream);
 /* Number of this library's kernel launches issued by the last pb_voc_forward / pb_tte_* call on the handle. */
 int64_t pb_voc_last_launches(const pb_voc* h);
 
+/* Section timing for the roofline report (bench.py): when enabled, pb_voc_forward records CUDA events on the
+ * caller's stream at its section boundaries.  Sections: 0 = embedding + conv_pre; 1+2i = ups[i];
+ * 2+2i = the 3 ResBlocks of stage i; last = conv_post + tanh.  pb_voc_section_ms waits for the last event. */
+int pb_voc_set_timing(pb_voc* h, int32_t enable);
+int pb_voc_section_count(const pb_voc* h);
+int pb_voc_section_ms(pb_voc* h, float* ms_host, int32_t n);
+
 /* Per-op entry points (unit tests; each is the kernel the model path uses).
  * conv1d: y = post( conv1d(pre(x), w, bias, dilation, 'same') [+ res] ), x/y/res f32 [B, C, L] contiguous.
  *   pre_slope: leaky-relu slope applied to the input (1.0 = none); post_slope likewise on the output;

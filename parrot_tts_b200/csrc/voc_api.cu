@@ -33,6 +33,10 @@ struct pb_voc {
     size_t dict_off = 0, spkr_off = 0;
     DevBuf work;
     int64_t last_launches = 0;
+    // optional section timing (bench.py roofline): events on the caller's stream at section boundaries
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    bool ev_valid = false;
     float* A(size_t off) const { return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(arena.ptr) + off); }
 };
 
@@ -100,6 +104,7 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
 extern "C" void pb_voc_destroy(pb_voc* h) {
     if (!h) return;
     for (auto& kv : h->staged) if (kv.second.ptr) cudaFree(kv.second.ptr);
+    for (auto e : h->ev) cudaEventDestroy(e);
     h->arena.release();
     h->work.release();
     delete h;
@@ -208,6 +213,28 @@ extern "C" int pb_voc_mark_finalized(pb_voc* h) {
 
 extern "C" int64_t pb_voc_last_launches(const pb_voc* h) { return h ? h->last_launches : 0; }
 
+extern "C" int pb_voc_section_count(const pb_voc* h) { return h ? 2 + 2 * h->cfg.num_upsamples : 0; }
+
+extern "C" int pb_voc_set_timing(pb_voc* h, int32_t enable) {
+    PB_REQUIRE(h, PB_ERR_INVALID, "pb_voc_set_timing: null handle");
+    h->timing = enable != 0;
+    h->ev_valid = false;
+    if (h->timing && h->ev.empty()) {
+        h->ev.resize(pb_voc_section_count(h) + 1);
+        for (auto& e : h->ev) PB_CUDA(cudaEventCreate(&e));
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_voc_section_ms(pb_voc* h, float* ms_host, int32_t n) {
+    PB_REQUIRE(h && ms_host, PB_ERR_INVALID, "pb_voc_section_ms: null argument");
+    PB_REQUIRE(h->timing && h->ev_valid, PB_ERR_STATE, "pb_voc_section_ms: no timed forward has run");
+    PB_REQUIRE(n == pb_voc_section_count(h), PB_ERR_INVALID, "pb_voc_section_ms: expected room for %d sections", pb_voc_section_count(h));
+    PB_CUDA(cudaEventSynchronize(h->ev.back()));
+    for (int i = 0; i < n; ++i) PB_CUDA(cudaEventElapsedTime(&ms_host[i], h->ev[i], h->ev[i + 1]));
+    return PB_OK;
+}
+
 extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
                               int32_t B, int32_t T, float* wav, void* stream) {
     PB_REQUIRE(h && wav, PB_ERR_INVALID, "pb_voc_forward: null argument");
@@ -247,6 +274,10 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
     float* slot[7];
     for (int s = 0; s < 7; ++s) slot[s] = cv.take<float>(slot_floats);
 
+    int ev_i = 0;
+    h->ev_valid = false;
+#define PB_MARK() do { if (h->timing) PB_CUDA(cudaEventRecord(h->ev[ev_i++], st)); } while (0)
+    PB_MARK();
     // ---- input features [B, model_in_dim, P0]
     if (code) {
         PB_TRY(launch_voc_embed(code, spkr, h->A(h->dict_off), c.num_speakers > 0 ? h->A(h->spkr_off) : nullptr, lens, B, T,
@@ -264,6 +295,7 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
         PB_TRY(launch_conv1d(a, st));
     }
 
+    PB_MARK();
     const float* cur_in = h0;
     int in_slot = -1;
     int64_t L = T;
@@ -288,6 +320,7 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
             a.pitch_in = pitch_in; a.pitch_out = P; a.K = s.K; a.U = u;
             PB_TRY(launch_convtr1d(a, st));
         }
+        PB_MARK();
         for (int j = 0; j < c.num_kernels; ++j) {
             const float* cur = X;
             for (int m = 0; m < c.num_dilations; ++m) {
@@ -322,10 +355,14 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
                 }
             }
         }
+        PB_MARK();
         cur_in = Y; in_slot = y_slot; L = Lo; pitch_in = P;
     }
     PB_TRY(launch_conv_post(cur_in, h->A(h->conv_post.w_off), h->A(h->conv_post.b_off), wav, lens, mul, B,
                             h->conv_post.Cin, (int)L, pitch_in, L, 7, st));
+    PB_MARK();
+#undef PB_MARK
+    h->ev_valid = h->timing;
     h->last_launches = g_launch_count - launches0;
     return PB_OK;
 }

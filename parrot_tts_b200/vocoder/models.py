@@ -191,6 +191,23 @@ class Generator(nn.Module):
         self.last_launches = int(lib.pb_voc_last_launches(hnd))
         return wav
 
+    # ------------------------------------------------------------------ measurement hooks
+    def set_timing(self, enable, device="cuda:0"):
+        """Record CUDA events at the section boundaries of every forward (see pb_voc_set_timing)."""
+        _lib.check(_lib.load().pb_voc_set_timing(self._engine(torch.device(device)), int(bool(enable))))
+
+    def section_ms(self):
+        """{section name: milliseconds} of the last timed forward (waits for it to finish)."""
+        lib = _lib.load()
+        n = lib.pb_voc_section_count(self._eng.handle)
+        buf = (C.c_float * n)()
+        _lib.check(lib.pb_voc_section_ms(self._eng.handle, buf, n))
+        names = ["embed+conv_pre"]
+        for i in range(self.num_upsamples):
+            names += [f"ups{i}", f"resblocks{i}"]
+        names.append("conv_post")
+        return dict(zip(names, [float(v) for v in buf]))
+
     # ------------------------------------------------------------------ reference API
     def forward(self, x):
         """f32 [B, model_in_dim, T] -> f32 [B, 1, hop*T] (reference utils/vocoder/models.py:95-111)."""

@@ -1,0 +1,91 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/parrot_b200.h declares, the ctypes table mirrors the header one to one, and the product path
+refuses to run without CUDA (no CPU fallback).  No compute calls are made here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from parrot_tts_b200 import _lib, build, configs, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "parrot_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    return build.build()
+
+
+def test_header_declares_symbols():
+    names = _declared()
+    assert "pb_voc_forward" in names and "pb_tte_encode" in names and len(names) >= 30
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_ctypes_table_matches_header(lib_path):
+    assert sorted(_lib.SIGNATURES) == _declared()
+    lib = _lib.load()
+    assert lib.pb_version() == 1
+    assert lib.pb_last_error() is not None
+
+
+def test_struct_layouts_match_header():
+    # pb_voc_cfg: 3 + 8 + 8 + 1 + 4 + 1 + 16 + 3 int32 ; pb_tte_cfg: 16 int32
+    assert ctypes.sizeof(_lib.VocCfg) == 4 * (3 + 8 + 8 + 1 + 4 + 1 + 16 + 3)
+    assert ctypes.sizeof(_lib.TteCfg) == 4 * 16
+
+
+def test_error_paths_without_gpu(lib_path):
+    lib = _lib.load()
+    assert lib.pb_voc_forward(None, None, None, None, None, 1, 1, None, None) == _lib.PB_ERR_INVALID
+    assert b"null" in lib.pb_last_error()
+    assert lib.pb_tte_decode(None, 1, 1, 1, None, None, None, None) == _lib.PB_ERR_INVALID
+    with pytest.raises(IndexError):
+        _lib.check(_lib.PB_ERR_INDEX)
+    with pytest.raises(_lib.ParrotB200Error):
+        _lib.check(_lib.PB_ERR_CUDA)
+
+
+def test_product_has_no_cpu_path():
+    from parrot_tts_b200.vocoder import CodeGenerator
+    h = configs.default_vocoder_config()
+    gen = CodeGenerator(h)
+    gen.load_state_dict(synth.synth_vocoder_state_dict(h, seed=0), strict=True)
+    with pytest.raises(_lib.ParrotB200Error):
+        gen(code=torch.zeros(1, 4, dtype=torch.long), spkr=torch.zeros(1, 1, dtype=torch.long))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "parrot_tts_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_state_dict_layouts_match_reference_names():
+    """Key names/shapes of SURVEY.md section 8b (old-style weight norm for the vocoder; TTE keys)."""
+    from parrot_tts_b200.vocoder import CodeGenerator
+    h = configs.default_vocoder_config()
+    sd = CodeGenerator(h).state_dict()
+    assert tuple(sd["conv_pre.weight_v"].shape) == (512, 256, 7) and tuple(sd["conv_pre.weight_g"].shape) == (512, 1, 1)
+    assert tuple(sd["ups.0.weight_g"].shape) == (512, 1, 1) and tuple(sd["ups.0.weight_v"].shape) == (512, 256, 11)
+    assert tuple(sd["resblocks.14.convs2.2.weight_v"].shape) == (16, 16, 11)
+    assert tuple(sd["conv_post.weight_v"].shape) == (1, 16, 7)
+    assert tuple(sd["dict.weight"].shape) == (1000, 128) and tuple(sd["spkr.weight"].shape) == (10, 128)
+    assert set(sd) == set(synth.synth_vocoder_state_dict(h, seed=0))

@@ -1,0 +1,85 @@
+"""Multi-GPU host logic on CPU: LPT assignment, length bucketing, and the one-off weight broadcast over a
+world_size-2 gloo group (the NCCL path runs the same code on device tensors)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from parrot_tts_b200 import configs, sharding, synth
+
+
+def test_lpt_covers_everything_and_balances():
+    lens = np.random.default_rng(0).integers(256, 4097, 256).tolist()     # BASELINE config 4 lengths
+    costs = [sharding.utterance_cost(n) for n in lens]
+    bins = sharding.lpt_assign(costs, 8)
+    flat = sorted(i for b in bins for i in b)
+    assert flat == list(range(256))
+    load = [sum(costs[i] for i in b) for b in bins]
+    assert max(load) / (sum(load) / 8) < 1.02           # LPT: within 2 % of perfect balance here
+    assert bins == sharding.lpt_assign(costs, 8)        # deterministic -> no communication needed
+
+
+def test_lpt_edge_cases():
+    assert sharding.lpt_assign([], 4) == [[], [], [], []]
+    assert sharding.lpt_assign([5.0], 2) == [[0], []]
+    assert sharding.lpt_assign([1.0, 1.0, 1.0], 1) == [[0, 1, 2]]
+
+
+def test_length_buckets_bound_padding():
+    lens = np.random.default_rng(1).integers(256, 4097, 64).tolist()
+    buckets = sharding.length_buckets(list(range(64)), lens, max_batch=8, max_pad_ratio=1.25)
+    assert sorted(i for b in buckets for i in b) == list(range(64))
+    for b in buckets:
+        assert len(b) <= 8
+        assert max(lens[i] for i in b) <= 1.25 * min(lens[i] for i in b)
+
+
+def test_pack_unpack_roundtrip():
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=3)
+    flat, manifest = sharding.pack_state_dict(sd)
+    back = sharding.unpack_state_dict(flat, manifest)
+    assert set(back) == set(sd)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h = configs.default_vocoder_config()
+        sd = synth.synth_vocoder_state_dict(h, seed=5) if rank == 0 else None
+        got = sharding.broadcast_state_dict(sd, src=0)
+        ref = synth.synth_vocoder_state_dict(h, seed=5)
+        ok = set(got) == set(ref) and all(torch.equal(got[k], ref[k]) for k in ref)
+        lens = np.random.default_rng(0).integers(256, 4097, 32).tolist()
+        mine = sharding.lpt_assign([sharding.utterance_cost(n) for n in lens], world)[rank]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        q.put((rank, ok, gathered))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_broadcast_and_sharding_world_size_2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, gathered in res:
+        assert ok, f"rank {rank}: broadcast weights differ"
+        assert sorted(i for b in gathered for i in b) == list(range(32))    # shards are disjoint and complete
