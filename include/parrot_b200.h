@@ -114,6 +114,16 @@ int pb_conv_transpose1d(const float* x, const float* w, const float* bias, float
                         int32_t B, int32_t Cin, int32_t Cout, int32_t L, int32_t K, int32_t stride,
                         float pre_slope, void* stream);
 
+/* Tensor-core variants of the two ops above (tcgen05 implicit GEMM on split-bf16 operands, fp32 accumulation in TMEM;
+ * see parrot_tts_b200/csrc/pb_tc.cuh).  Same tensors and semantics; Cin in {16, 32, 64k}, Cout a multiple of 16.
+ * `debug_flags` bit 0 selects how the shifted-tile descriptor's base offset is derived (kernel bring-up knob). */
+int pb_conv1d_tc(const float* x, const float* w, const float* bias, const float* res, float* y,
+                 int32_t B, int32_t Cin, int32_t Cout, int32_t L, int32_t K, int32_t dilation,
+                 float pre_slope, float post_slope, int32_t debug_flags, void* stream);
+int pb_conv_transpose1d_tc(const float* x, const float* w, const float* bias, float* y,
+                           int32_t B, int32_t Cin, int32_t Cout, int32_t L, int32_t K, int32_t stride,
+                           float pre_slope, int32_t debug_flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * TTE  (reference modules/parrot.py, modules/fft.py, modules/duration.py)
  * ------------------------------------------------------------------------------------------ */

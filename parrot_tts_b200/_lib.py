@@ -62,6 +62,8 @@ SIGNATURES = {
     "pb_voc_mark_finalized": (C.c_int, [_P]),
     "pb_conv1d": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _F, _P]),
     "pb_conv_transpose1d": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P]),
+    "pb_conv1d_tc": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _F, _I32, _P]),
+    "pb_conv_transpose1d_tc": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _P]),
     "pb_tte_create": (C.c_int, [C.POINTER(TteCfg), C.POINTER(_P)]),
     "pb_tte_destroy": (None, [_P]),
     "pb_tte_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(_I64), _I32, _I32]),

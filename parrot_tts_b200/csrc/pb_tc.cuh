@@ -1,0 +1,53 @@
+// pb_tc.cuh - tensor-core (tcgen05 / TMEM / TMA) implicit-GEMM convolution family for sm_100a.
+//
+// Activation format ("split-bf16, channels-last"): a tensor with C channels and L positions per item is
+//   bf16 [B][L][2C], row = [hi(0..C-1) | lo(0..C-1)],  value = float(hi) + float(lo),
+// i.e. the two leading bf16 terms of the fp32 value (4 bytes per element, the same HBM footprint as fp32).
+// A product x.w is evaluated as x_hi.w_hi + x_lo.w_hi + x_hi.w_lo on the bf16 tensor pipe with fp32
+// accumulation in TMEM: relative error ~2^-16 per product instead of 2^-9 (bf16) or 2^-11 (tf32) - what the
+// 1e-3 waveform tolerance of the north star needs (hard part 2).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "pb_common.cuh"
+
+namespace pb {
+
+// One launch = one Conv1d ('same' padding, dilation D, K taps) or one polyphase ConvTranspose1d, as an implicit GEMM
+//   acc[t, n] = sum_{tap j} sum_{ci} x[t + j*D - pad, ci] * W_j[ci, n]            (M = 128 time rows per tile)
+// followed by the fused epilogue
+//   v = acc + bias[co] (+ unact(res)) (+ accin);  v *= scale;  v = lrelu(v, post_slope);  v = 0 past the valid length
+// and the store of v as split-bf16 (and/or fp32) at row t*U + n / out_C, channel n % out_C.
+struct TcConvArgs {
+    const __nv_bfloat16* x = nullptr;      // [B][L][2*Cin] split-bf16 (already activated by its producer)
+    const uint8_t* w = nullptr;            // packed by tc_pack_* (see tc_conv.cu)
+    const float* bias = nullptr;           // [out_C] or null
+    const __nv_bfloat16* res = nullptr;    // [B][U*L][2*out_C] residual or null
+    float res_unslope = 1.f;               // the residual tensor is stored leaky-relu'd with slope s: pass 1/s to undo (1 = raw)
+    const __nv_bfloat16* accin = nullptr;  // [B][U*L][2*out_C] raw running sum or null
+    __nv_bfloat16* out = nullptr;          // [B][U*L][2*out_C] split-bf16 or null
+    float* out_f32 = nullptr;              // [B][U*L][out_C] fp32 or null
+    const int32_t* lens = nullptr;         // [B] valid units per item or null
+    int len_mul = 1;                       // output rows per unit
+    int B = 0, L = 0, Cin = 0;
+    int N = 0;                             // GEMM N = U * out_C
+    int out_C = 0, U = 1;
+    int K = 1, D = 1;
+    float post_slope = 1.f, scale = 1.f;
+    int tanh_out = 0;                      // apply tanh after the activation (conv_post)
+    int bo_mode = 0;                       // debug: how the A descriptor's base_offset is set for row-shifted tiles
+};
+
+int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)
+size_t tc_packed_weight_bytes(int Cin, int N, int K);
+// torch Conv1d weight f32 [Cout][Cin][K]  -> packed split-bf16 B operand (N = Cout)
+int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st);
+// torch ConvTranspose1d weight f32 [Cin][Cout][Kt], stride U, padding (Kt-U)/2 -> 3-tap polyphase operand (N = U*Cout)
+int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st);
+int launch_tc_conv(const TcConvArgs& a, cudaStream_t st);
+
+// layout conversion (test entry points, embedding stage): f32 [B][C][L] (row stride pitch) <-> split-bf16 [B][L][2C]
+int launch_f32_to_split(const float* x, int64_t pitch, __nv_bfloat16* y, int B, int C, int L, float pre_slope, cudaStream_t st);
+int launch_split_to_f32(const __nv_bfloat16* x, float* y, int64_t pitch, int B, int C, int L, cudaStream_t st);
+
+}  // namespace pb

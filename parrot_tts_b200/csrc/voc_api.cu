@@ -427,3 +427,69 @@ extern "C" int pb_conv_transpose1d(const float* x, const float* w, const float* 
     cudaFree(xp); cudaFree(yp); cudaFree(wp);
     return rc;
 }
+
+// ---- tensor-core per-op entry points (unit tests) ---------------------------------------------------------------------
+#include "pb_tc.cuh"
+
+namespace {
+struct ScratchGuard {
+    std::vector<void*> ptrs;
+    ~ScratchGuard() { for (void* q : ptrs) cudaFree(q); }
+    template <class T> int get(T** out, size_t n) {
+        void* q = nullptr;
+        PB_CUDA(cudaMalloc(&q, n * sizeof(T) + 16));
+        ptrs.push_back(q);
+        *out = reinterpret_cast<T*>(q);
+        return PB_OK;
+    }
+};
+}  // namespace
+
+extern "C" int pb_conv1d_tc(const float* x, const float* w, const float* bias, const float* res, float* y, int32_t B, int32_t Cin,
+                            int32_t Cout, int32_t L, int32_t K, int32_t dilation, float pre_slope, float post_slope,
+                            int32_t debug_flags, void* stream) {
+    PB_REQUIRE(x && w && y, PB_ERR_INVALID, "pb_conv1d_tc: null argument");
+    PB_REQUIRE(B > 0 && L > 0 && Cin > 0 && Cout > 0 && K > 0, PB_ERR_INVALID, "pb_conv1d_tc: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    ScratchGuard g;
+    __nv_bfloat16 *xs = nullptr, *ys = nullptr, *rs = nullptr;
+    uint8_t* wp = nullptr;
+    PB_TRY(g.get(&xs, (size_t)B * L * 2 * Cin));
+    PB_TRY(g.get(&ys, (size_t)B * L * 2 * Cout));
+    PB_TRY(g.get(&wp, tc_packed_weight_bytes(Cin, Cout, K)));
+    if (res) PB_TRY(g.get(&rs, (size_t)B * L * 2 * Cout));
+    PB_TRY(launch_f32_to_split(x, L, xs, B, Cin, L, pre_slope, st));
+    if (res) PB_TRY(launch_f32_to_split(res, L, rs, B, Cout, L, 1.f, st));
+    PB_TRY(tc_pack_conv_weight(w, wp, Cout, Cin, K, st));
+    TcConvArgs a;
+    a.x = xs; a.w = wp; a.bias = bias; a.res = rs; a.out = ys; a.B = B; a.L = L; a.Cin = Cin; a.N = Cout; a.out_C = Cout;
+    a.U = 1; a.K = K; a.D = dilation; a.post_slope = post_slope; a.bo_mode = debug_flags & 1;
+    PB_TRY(launch_tc_conv(a, st));
+    PB_TRY(launch_split_to_f32(ys, y, L, B, Cout, L, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+extern "C" int pb_conv_transpose1d_tc(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,
+                                      int32_t Cout, int32_t L, int32_t K, int32_t stride, float pre_slope, int32_t debug_flags,
+                                      void* stream) {
+    PB_REQUIRE(x && w && y, PB_ERR_INVALID, "pb_conv_transpose1d_tc: null argument");
+    PB_REQUIRE(B > 0 && L > 0 && Cin > 0 && Cout > 0 && K > 0 && stride > 0, PB_ERR_INVALID, "pb_conv_transpose1d_tc: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    ScratchGuard g;
+    __nv_bfloat16 *xs = nullptr, *ys = nullptr;
+    uint8_t* wp = nullptr;
+    const int Lo = L * stride;
+    PB_TRY(g.get(&xs, (size_t)B * L * 2 * Cin));
+    PB_TRY(g.get(&ys, (size_t)B * Lo * 2 * Cout));
+    PB_TRY(g.get(&wp, tc_packed_weight_bytes(Cin, stride * Cout, 3)));
+    PB_TRY(launch_f32_to_split(x, L, xs, B, Cin, L, pre_slope, st));
+    PB_TRY(tc_pack_convtr_weight(w, wp, Cin, Cout, K, stride, st));
+    TcConvArgs a;
+    a.x = xs; a.w = wp; a.bias = bias; a.out = ys; a.B = B; a.L = L; a.Cin = Cin; a.N = stride * Cout; a.out_C = Cout;
+    a.U = stride; a.K = 3; a.D = 1; a.bo_mode = debug_flags & 1;
+    PB_TRY(launch_tc_conv(a, st));
+    PB_TRY(launch_split_to_f32(ys, y, Lo, B, Cout, Lo, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
