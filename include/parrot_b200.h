@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 
 typedef enum pb_status {
     PB_OK = 0,
@@ -61,6 +61,9 @@ typedef struct pb_voc_cfg {
     int32_t num_embeddings;            /* 1000 (0 = Generator only, no code path) */
     int32_t embedding_dim;             /* 128 */
     int32_t num_speakers;              /* 10  (0 = single speaker: no spkr table) */
+    int32_t conv_mode;                 /* 0 = fp32 SIMT sliding-window kernels; 1 = tcgen05 implicit GEMM on split-bf16
+                                          operands (3 MMAs per product, fp32-accurate: the default of the Python mirror);
+                                          2 = tcgen05 single-pass bf16 (throughput mode, ~2^-9 relative error per product) */
 } pb_voc_cfg;
 
 typedef struct pb_voc pb_voc;
@@ -116,13 +119,13 @@ int pb_conv_transpose1d(const float* x, const float* w, const float* bias, float
 
 /* Tensor-core variants of the two ops above (tcgen05 implicit GEMM on split-bf16 operands, fp32 accumulation in TMEM;
  * see parrot_tts_b200/csrc/pb_tc.cuh).  Same tensors and semantics; Cin in {16, 32, 64k}, Cout a multiple of 16.
- * `debug_flags` bit 0 selects how the shifted-tile descriptor's base offset is derived (kernel bring-up knob). */
+ * `flags` bit 0: single-pass bf16 products (throughput mode) instead of the fp32-accurate 3-pass split. */
 int pb_conv1d_tc(const float* x, const float* w, const float* bias, const float* res, float* y,
                  int32_t B, int32_t Cin, int32_t Cout, int32_t L, int32_t K, int32_t dilation,
-                 float pre_slope, float post_slope, int32_t debug_flags, void* stream);
+                 float pre_slope, float post_slope, int32_t flags, void* stream);
 int pb_conv_transpose1d_tc(const float* x, const float* w, const float* bias, float* y,
                            int32_t B, int32_t Cin, int32_t Cout, int32_t L, int32_t K, int32_t stride,
-                           float pre_slope, int32_t debug_flags, void* stream);
+                           float pre_slope, int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * TTE  (reference modules/parrot.py, modules/fft.py, modules/duration.py)

@@ -28,6 +28,7 @@ class VocCfg(C.Structure):
         ("num_embeddings", C.c_int32),
         ("embedding_dim", C.c_int32),
         ("num_speakers", C.c_int32),
+        ("conv_mode", C.c_int32),
     ]
 
 
@@ -102,7 +103,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.pb_version() != 1:
+    if lib.pb_version() != 2:
         raise ParrotB200Error(f"ABI version mismatch: library reports {lib.pb_version()}")
     _lib = lib
     return lib

@@ -35,7 +35,7 @@ struct TcConvArgs {
     int K = 1, D = 1;
     float post_slope = 1.f, scale = 1.f;
     int tanh_out = 0;                      // apply tanh after the activation (conv_post)
-    int bo_mode = 0;                       // debug: how the A descriptor's base_offset is set for row-shifted tiles
+    int single_pass = 0;                   // 1: hi.hi only (plain bf16 product, throughput mode)
 };
 
 int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)

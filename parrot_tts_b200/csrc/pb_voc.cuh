@@ -1,5 +1,7 @@
 // pb_voc.cuh - internal launch interface of the vocoder kernels (voc_kernels.cu).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "pb_common.cuh"
 
 namespace pb {
@@ -63,6 +65,14 @@ int launch_weight_norm_fold(const float* v, const float* g, float* w, int n0, in
 // src element (co, ci, j) at co*s_co + ci*s_ci + j  ->  dst[((co/CO_T)*Cin + ci)*K + j)*CO_T + co%CO_T]
 int launch_pack_conv_weight(const float* src, int64_t s_co, int64_t s_ci, float* dst, int Cout, int Cin, int K, int CO_T,
                             cudaStream_t st);
+// ---- tensor-core path (activations split-bf16 channels-last [B][L][2C], see pb_tc.cuh) ----------------------------------
+// unit + speaker embedding -> x0 [B][T][2*(E or 2E)] split-bf16 (rows past the valid length are zero)
+int launch_voc_embed_split(const int64_t* code, const int64_t* spkr, const float* dict_w, const float* spkr_w,
+                           const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, __nv_bfloat16* x0, cudaStream_t st);
+// conv_post on a split-bf16 input that already carries the final leaky-relu: tanh(conv k7 + bias) -> wav f32 [B][L]
+int launch_conv_post_split(const __nv_bfloat16* x, const float* w /*[Cin][K]*/, const float* bias, float* wav,
+                           const int32_t* lens, int len_mul, int B, int Cin, int L, int K, cudaStream_t st);
+
 int launch_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, cudaStream_t st);
 
 }  // namespace pb

@@ -47,7 +47,7 @@ struct TcParams {
     float post_slope, scale, res_unslope;
     int tanh_out;
     uint32_t idesc;
-    int bo_mode;
+    int single_pass;
     int tmem_cols;
 };
 
@@ -223,16 +223,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                         const uint32_t a_tap = a_base + (uint32_t)(j * p.D) * (uint32_t)p.a_row_bytes;
                         for (int ks = 0; ks < p.ksteps; ++ks) {
                             const uint32_t a_hi = a_tap + ks * 32u, a_lo = a_hi + (uint32_t)p.lo_off;
-                            const uint32_t bo_hi = p.bo_mode ? (a_hi >> 7) & 7u : 0u;
-                            const uint32_t bo_lo = p.bo_mode ? (a_lo >> 7) & 7u : 0u;
-                            const uint64_t da_hi = smem_desc(a_hi, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, bo_hi);
-                            const uint64_t da_lo = smem_desc(a_lo, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, bo_lo);
+                            // The swizzle is a function of the absolute shared-memory address (measured on B200: a start
+                            // address advanced by whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the
+                            // K taps are K views of one staged tile.
+                            const uint64_t da_hi = smem_desc(a_hi, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
                             const uint64_t db_hi = smem_desc(b_base + ks * kstep_b_bytes, b_lbo, 128, 0, 0);
-                            const uint64_t db_lo = smem_desc(b_base + (p.ksteps + ks) * kstep_b_bytes, b_lbo, 128, 0, 0);
                             umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                             accumulate = 1;
-                            umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
-                            umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                            if (!p.single_pass) {
+                                const uint64_t da_lo = smem_desc(a_lo, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
+                                const uint64_t db_lo = smem_desc(b_base + (p.ksteps + ks) * kstep_b_bytes, b_lbo, 128, 0, 0);
+                                umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
+                                umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                            }
                         }
                         if (!p.b_resident) { umma_commit(&empty_b[sb]); ++b_it; }
                     }
@@ -447,7 +450,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.post_slope = a.post_slope; p.scale = a.scale; p.res_unslope = a.res_unslope; p.tanh_out = a.tanh_out;
     // instruction descriptor: D f32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    p.bo_mode = a.bo_mode;
+    p.single_pass = a.single_pass;
     int cols = 32;
     while (cols < 2 * NT) cols *= 2;
     p.tmem_cols = cols;

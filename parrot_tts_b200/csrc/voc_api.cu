@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "pb_runtime.cuh"
+#include "pb_tc.cuh"
 #include "pb_voc.cuh"
 
 using namespace pb;
@@ -45,7 +46,10 @@ static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
 static void plan_slot(pb_voc* h, ConvSlot& s, const std::string& key, int Cin, int Cout, int K, int D, bool transposed,
                       int co_tile) {
     s.key = key; s.Cin = Cin; s.Cout = Cout; s.K = K; s.D = D; s.transposed = transposed; s.co_tile = co_tile;
-    s.w_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + (size_t)Cin * Cout * K * sizeof(float));
+    size_t wbytes = (size_t)Cin * Cout * K * sizeof(float);
+    if (h->cfg.conv_mode != 0 && Cout > 1)   // tensor-core operand: a transposed conv becomes U phases x 3 taps (D carries U)
+        wbytes = transposed ? tc_packed_weight_bytes(Cin, D * Cout, 3) : tc_packed_weight_bytes(Cin, Cout, K);
+    s.w_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + wbytes);
     s.b_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + (size_t)Cout * sizeof(float));
 }
 
@@ -56,6 +60,16 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
                PB_ERR_INVALID, "pb_voc_create: layer counts out of range");
     PB_REQUIRE(cfg->upsample_initial_channel % (1 << cfg->num_upsamples) == 0, PB_ERR_INVALID,
                "pb_voc_create: upsample_initial_channel=%d not divisible by 2^%d", cfg->upsample_initial_channel, cfg->num_upsamples);
+    PB_REQUIRE(cfg->conv_mode >= 0 && cfg->conv_mode <= 2, PB_ERR_INVALID, "pb_voc_create: conv_mode=%d (0, 1 or 2 expected)", cfg->conv_mode);
+    if (cfg->conv_mode != 0) {
+        // tensor-core path: every layer width must map onto the implicit-GEMM tiles
+        bool ok = cfg->model_in_dim % 64 == 0 && tc_n_tile(cfg->upsample_initial_channel) > 0 && cfg->upsample_initial_channel % 64 == 0;
+        for (int i = 0; ok && i < cfg->num_upsamples; ++i) {
+            const int cout = cfg->upsample_initial_channel >> (i + 1);
+            ok = (cout == 16 || cout == 32 || cout % 64 == 0) && tc_n_tile(cfg->upsample_rates[i] * cout) > 0;
+        }
+        PB_REQUIRE(ok, PB_ERR_INVALID, "pb_voc_create: channel widths unsupported by the tensor-core path (use conv_mode 0)");
+    }
     pb_voc* h = new pb_voc();
     h->cfg = *cfg;
     PB_CUDA(cudaGetDevice(&h->device));
@@ -71,7 +85,7 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
         const int ct = convtr_co_tile(cout, u);
         if (!ct || (k - u) % 2 || cin % 8) { delete h; set_error("pb_voc_create: unsupported upsample layer %d", i); return PB_ERR_INVALID; }
         ConvSlot s;
-        plan_slot(h, s, "ups." + std::to_string(i), cin, cout, k, 1, true, ct);
+        plan_slot(h, s, "ups." + std::to_string(i), cin, cout, k, u, true, ct);   // D field = stride of the transposed conv
         h->ups.push_back(s);
         const int cr = conv_co_tile(cout);
         if (!cr || cout % 8) { delete h; set_error("pb_voc_create: unsupported resblock width %d", cout); return PB_ERR_INVALID; }
@@ -144,6 +158,10 @@ static int finalize_conv(pb_voc* h, const ConvSlot& s, float* scratch, cudaStrea
     if (s.Cout == 1) {
         // conv_post: [1, Cin, K] is already [ci][j]
         PB_CUDA(cudaMemcpyAsync(h->A(s.w_off), scratch, (size_t)s.Cin * s.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (h->cfg.conv_mode != 0) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(h->A(s.w_off));
+        if (s.transposed) PB_TRY(tc_pack_convtr_weight(scratch, dst, s.Cin, s.Cout, s.K, s.D, st));
+        else PB_TRY(tc_pack_conv_weight(scratch, dst, s.Cout, s.Cin, s.K, st));
     } else if (s.transposed) {
         PB_TRY(launch_pack_conv_weight(scratch, s.K, (int64_t)s.Cout * s.K, h->A(s.w_off), s.Cout, s.Cin, s.K, s.co_tile, st));
     } else {
@@ -235,6 +253,123 @@ extern "C" int pb_voc_section_ms(pb_voc* h, float* ms_host, int32_t n) {
     return PB_OK;
 }
 
+// ---- tensor-core forward: every activation is split-bf16 channels-last [B][L][2C] (pb_tc.cuh) ------------------------------
+// Storage convention: a tensor that feeds a convolution is stored with the leaky-relu that precedes that convolution in
+// the reference already applied (slope 0.1, or 0.01 before conv_post); the residual read undoes it (x = a < 0 ? a/slope : a).
+static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
+                          int32_t B, int32_t T, float* wav, cudaStream_t st) {
+    const pb_voc_cfg& c = h->cfg;
+    const int64_t launches0 = g_launch_count;
+    const int c0 = c.upsample_initial_channel;
+    const int single = c.conv_mode == 2;
+    typedef __nv_bfloat16 bf;
+    size_t slot_elems = 0;
+    {
+        int64_t L = T;
+        for (int i = 0; i < c.num_upsamples; ++i) {
+            L *= c.upsample_rates[i];
+            PB_REQUIRE(L < (1LL << 30), PB_ERR_INVALID, "pb_voc_forward: T=%d too long", T);
+            slot_elems = std::max(slot_elems, (size_t)B * (size_t)L * 2 * (c0 >> (i + 1)));
+        }
+    }
+    Carver plan(nullptr);
+    plan.take<bf>((size_t)B * T * 2 * c.model_in_dim);
+    plan.take<bf>((size_t)B * T * 2 * c0);
+    for (int s = 0; s < 7; ++s) plan.take<bf>(slot_elems);
+    PB_TRY(h->work.reserve(plan.off));
+    Carver cv(h->work.ptr);
+    bf* x0 = cv.take<bf>((size_t)B * T * 2 * c.model_in_dim);
+    bf* h0 = cv.take<bf>((size_t)B * T * 2 * c0);
+    bf* slot[7];
+    for (int s = 0; s < 7; ++s) slot[s] = cv.take<bf>(slot_elems);
+
+    int ev_i = 0;
+    h->ev_valid = false;
+#define PB_MARK() do { if (h->timing) PB_CUDA(cudaEventRecord(h->ev[ev_i++], st)); } while (0)
+    PB_MARK();
+    if (code) {
+        PB_TRY(launch_voc_embed_split(code, spkr, h->A(h->dict_off), c.num_speakers > 0 ? h->A(h->spkr_off) : nullptr, lens, B, T,
+                                      c.embedding_dim, c.num_embeddings, c.num_speakers, x0, st));
+    } else {
+        PB_TRY(launch_f32_to_split(x, T, x0, B, c.model_in_dim, T, 1.f, st));
+    }
+    auto W = [&](const ConvSlot& s) { return reinterpret_cast<const uint8_t*>(h->A(s.w_off)); };
+    {   // conv_pre, stored with the leaky-relu that precedes ups[0]
+        TcConvArgs a;
+        a.x = x0; a.w = W(h->conv_pre); a.bias = h->A(h->conv_pre.b_off); a.out = h0; a.lens = lens; a.len_mul = 1;
+        a.B = B; a.L = T; a.Cin = c.model_in_dim; a.N = c0; a.out_C = c0; a.U = 1; a.K = 7; a.D = 1; a.post_slope = 0.1f;
+        a.single_pass = single;
+        PB_TRY(launch_tc_conv(a, st));
+    }
+    PB_MARK();
+    const bf* cur_in = h0;
+    int in_slot = -1;
+    int64_t L = T;
+    int mul = 1;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        const int C = c0 >> (i + 1);
+        const int u = c.upsample_rates[i];
+        const int64_t Lo = L * u;
+        mul *= u;
+        bf* buf[6];
+        for (int s = 0, n = 0; s < 7 && n < 6; ++s) if (s != in_slot) buf[n++] = slot[s];
+        bf *X = buf[0], *XT = buf[1], *XA = buf[2], *XB = buf[3], *XS = buf[4], *Y = buf[5];
+        int y_slot = 0;
+        for (int s = 0; s < 7; ++s) if (slot[s] == Y) y_slot = s;
+        {   // ups[i] as a 3-tap polyphase implicit GEMM; X is stored leaky-relu'd (the resblocks' first activation)
+            const ConvSlot& s = h->ups[i];
+            TcConvArgs a;
+            a.x = cur_in; a.w = W(s); a.bias = h->A(s.b_off); a.out = X; a.lens = lens; a.len_mul = mul;
+            a.B = B; a.L = (int)L; a.Cin = s.Cin; a.N = u * s.Cout; a.out_C = s.Cout; a.U = u; a.K = 3; a.D = 1;
+            a.post_slope = 0.1f; a.single_pass = single;
+            PB_TRY(launch_tc_conv(a, st));
+        }
+        PB_MARK();
+        for (int j = 0; j < c.num_kernels; ++j) {
+            const bf* cur = X;
+            for (int m = 0; m < c.num_dilations; ++m) {
+                const int idx = (i * c.num_kernels + j) * c.num_dilations + m;
+                const ConvSlot& s1 = h->rb1[idx];
+                const ConvSlot& s2 = h->rb2[idx];
+                TcConvArgs a;
+                a.x = cur; a.w = W(s1); a.bias = h->A(s1.b_off); a.out = XT; a.lens = lens; a.len_mul = mul;
+                a.B = B; a.L = (int)Lo; a.Cin = C; a.N = C; a.out_C = C; a.U = 1; a.K = s1.K; a.D = s1.D;
+                a.post_slope = 0.1f; a.single_pass = single;
+                PB_TRY(launch_tc_conv(a, st));
+                TcConvArgs b2;
+                b2.x = XT; b2.w = W(s2); b2.bias = h->A(s2.b_off); b2.res = cur; b2.res_unslope = 10.f;
+                b2.lens = lens; b2.len_mul = mul; b2.B = B; b2.L = (int)Lo; b2.Cin = C; b2.N = C; b2.out_C = C; b2.U = 1;
+                b2.K = s2.K; b2.D = 1; b2.single_pass = single;
+                if (m + 1 < c.num_dilations) {
+                    bf* dst = (cur == XA) ? XB : XA;
+                    b2.out = dst; b2.post_slope = 0.1f;
+                    PB_TRY(launch_tc_conv(b2, st));
+                    cur = dst;
+                } else {
+                    if (j > 0) b2.accin = XS;
+                    if (j + 1 < c.num_kernels) {
+                        b2.out = XS;                 // raw running sum over the resblocks
+                    } else {
+                        b2.out = Y;
+                        b2.scale = 1.0f / (float)c.num_kernels;
+                        b2.post_slope = (i + 1 < c.num_upsamples) ? 0.1f : 0.01f;
+                    }
+                    PB_TRY(launch_tc_conv(b2, st));
+                }
+            }
+        }
+        PB_MARK();
+        cur_in = Y; in_slot = y_slot; L = Lo;
+    }
+    PB_TRY(launch_conv_post_split(cur_in, h->A(h->conv_post.w_off), h->A(h->conv_post.b_off), wav, lens, mul, B,
+                                  h->conv_post.Cin, (int)L, 7, st));
+    PB_MARK();
+#undef PB_MARK
+    h->ev_valid = h->timing;
+    h->last_launches = g_launch_count - launches0;
+    return PB_OK;
+}
+
 extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
                               int32_t B, int32_t T, float* wav, void* stream) {
     PB_REQUIRE(h && wav, PB_ERR_INVALID, "pb_voc_forward: null argument");
@@ -249,6 +384,7 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
         PB_REQUIRE(in_dim == c.model_in_dim, PB_ERR_INVALID, "pb_voc_forward: embedding dims (%d) != model_in_dim (%d)", in_dim, c.model_in_dim);
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (c.conv_mode != 0) return voc_forward_tc(h, x, code, spkr, lens, B, T, wav, st);
     const int64_t launches0 = g_launch_count;
     const int c0 = c.upsample_initial_channel;
     const int P0 = (int)round_up(T, 4);
@@ -429,7 +565,6 @@ extern "C" int pb_conv_transpose1d(const float* x, const float* w, const float* 
 }
 
 // ---- tensor-core per-op entry points (unit tests) ---------------------------------------------------------------------
-#include "pb_tc.cuh"
 
 namespace {
 struct ScratchGuard {
@@ -463,7 +598,7 @@ extern "C" int pb_conv1d_tc(const float* x, const float* w, const float* bias, c
     PB_TRY(tc_pack_conv_weight(w, wp, Cout, Cin, K, st));
     TcConvArgs a;
     a.x = xs; a.w = wp; a.bias = bias; a.res = rs; a.out = ys; a.B = B; a.L = L; a.Cin = Cin; a.N = Cout; a.out_C = Cout;
-    a.U = 1; a.K = K; a.D = dilation; a.post_slope = post_slope; a.bo_mode = debug_flags & 1;
+    a.U = 1; a.K = K; a.D = dilation; a.post_slope = post_slope; a.single_pass = debug_flags & 1;
     PB_TRY(launch_tc_conv(a, st));
     PB_TRY(launch_split_to_f32(ys, y, L, B, Cout, L, st));
     PB_CUDA(cudaStreamSynchronize(st));
@@ -487,7 +622,7 @@ extern "C" int pb_conv_transpose1d_tc(const float* x, const float* w, const floa
     PB_TRY(tc_pack_convtr_weight(w, wp, Cin, Cout, K, stride, st));
     TcConvArgs a;
     a.x = xs; a.w = wp; a.bias = bias; a.out = ys; a.B = B; a.L = L; a.Cin = Cin; a.N = stride * Cout; a.out_C = Cout;
-    a.U = stride; a.K = 3; a.D = 1; a.bo_mode = debug_flags & 1;
+    a.U = stride; a.K = 3; a.D = 1; a.single_pass = debug_flags & 1;
     PB_TRY(launch_tc_conv(a, st));
     PB_TRY(launch_split_to_f32(ys, y, Lo, B, Cout, Lo, st));
     PB_CUDA(cudaStreamSynchronize(st));

@@ -653,6 +653,93 @@ int launch_pack_conv_weight(const float* src, int64_t s_co, int64_t s_ci, float*
     return PB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tensor-core path helpers: embedding gather into split-bf16 rows, conv_post on split-bf16 rows
+// ------------------------------------------------------------------------------------------------
+// one warp per (b, t) row; row = [hi(dict E | spkr E) | lo(dict E | spkr E)]
+__global__ void __launch_bounds__(256)
+voc_embed_split_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ spkr, const float* __restrict__ dict_w,
+                       const float* __restrict__ spkr_w, const int32_t* __restrict__ lens, int T, int E, int n_codes, int n_spk,
+                       int64_t rows, __nv_bfloat16* __restrict__ x0) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int b = (int)(row / T), t = (int)(row % T);
+    const int C = spkr_w ? 2 * E : E;
+    const int valid = lens ? min(lens[b], T) : T;
+    long long id = code[row];
+    id = id < 0 ? 0 : (id >= n_codes ? n_codes - 1 : id);
+    long long sp = spkr_w ? spkr[b] : 0;
+    sp = sp < 0 ? 0 : (sp >= n_spk ? n_spk - 1 : sp);
+    __nv_bfloat16* out = x0 + row * 2 * C;
+    for (int c = lane; c < C; c += 32) {
+        float v = 0.f;
+        if (t < valid) v = c < E ? dict_w[(size_t)id * E + c] : spkr_w[(size_t)sp * E + (c - E)];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        out[c] = hi;
+        out[C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+int launch_voc_embed_split(const int64_t* code, const int64_t* spkr, const float* dict_w, const float* spkr_w,
+                           const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, __nv_bfloat16* x0, cudaStream_t st) {
+    const int64_t rows = (int64_t)B * T;
+    voc_embed_split_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(code, spkr, dict_w, spkr_w, lens, T, E, n_codes, n_spk, rows, x0);
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// one thread per output sample: 7 rows x CIN channels (hi + lo), rows shared with the neighbours through L1
+template <int CIN, int K>
+__global__ void __launch_bounds__(256)
+conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ wav, const int32_t* __restrict__ lens, int len_mul, int L) {
+    __shared__ float ws[CIN * K];
+    for (int i = threadIdx.x; i < CIN * K; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L) return;
+    int valid = L;
+    if (lens) { const int v = lens[b] * len_mul; valid = v < valid ? v : valid; }
+    float acc = 0.f;
+    if (t < valid) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int tt = t + j - (K - 1) / 2;
+            if (tt < 0 || tt >= L) continue;
+            const uint4* row = reinterpret_cast<const uint4*>(x + ((size_t)b * L + tt) * 2 * CIN);
+#pragma unroll
+            for (int q = 0; q < CIN / 8; ++q) {
+                const uint4 h = row[q], l = row[CIN / 8 + q];
+                const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v0 = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+                    const float v1 = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+                    acc = fmaf(ws[(q * 8 + 2 * i) * K + j], v0, acc);
+                    acc = fmaf(ws[(q * 8 + 2 * i + 1) * K + j], v1, acc);
+                }
+            }
+        }
+        acc = tanhf(acc + bias[0]);
+    }
+    wav[(size_t)b * L + t] = acc;
+}
+
+int launch_conv_post_split(const __nv_bfloat16* x, const float* w, const float* bias, float* wav, const int32_t* lens, int len_mul,
+                           int B, int Cin, int L, int K, cudaStream_t st) {
+    PB_REQUIRE(K == 7, PB_ERR_INVALID, "conv_post: kernel size %d unsupported (7 expected)", K);
+    dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
+    if (Cin == 16) conv_post_split_kernel<16, 7><<<grid, 256, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
+    else if (Cin == 32) conv_post_split_kernel<32, 7><<<grid, 256, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
+    else { set_error("conv_post: Cin=%d unsupported", Cin); return PB_ERR_INVALID; }
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 // generate() tail: (wav * 32768) -> int16 with C-cast semantics (truncate toward zero, wrap modulo 2^16)
 __global__ void wav_to_pcm16_kernel(const float* __restrict__ wav, int64_t n, int16_t* __restrict__ pcm) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -47,7 +47,7 @@ def conv_transpose1d(x, w, bias=None, stride=1, pre_slope=1.0):
     return y
 
 
-def conv1d_tc(x, w, bias=None, dilation=1, res=None, pre_slope=1.0, post_slope=1.0, debug_flags=0):
+def conv1d_tc(x, w, bias=None, dilation=1, res=None, pre_slope=1.0, post_slope=1.0, single_pass=False):
     """conv1d on the tensor-core path (split-bf16 tcgen05 implicit GEMM); same contract as conv1d."""
     _need_cuda(x, w, bias, res)
     x, w = _f32(x), _f32(w)
@@ -58,12 +58,12 @@ def conv1d_tc(x, w, bias=None, dilation=1, res=None, pre_slope=1.0, post_slope=1
     y = torch.empty(B, Cout, L, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().pb_conv1d_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(y),
-                                            B, Cin, Cout, L, K, dilation, pre_slope, post_slope, debug_flags,
+                                            B, Cin, Cout, L, K, dilation, pre_slope, post_slope, int(bool(single_pass)),
                                             _lib.stream_ptr(x.device)))
     return y
 
 
-def conv_transpose1d_tc(x, w, bias=None, stride=1, pre_slope=1.0, debug_flags=0):
+def conv_transpose1d_tc(x, w, bias=None, stride=1, pre_slope=1.0, single_pass=False):
     """conv_transpose1d on the tensor-core path (3-tap polyphase implicit GEMM); same contract as conv_transpose1d."""
     _need_cuda(x, w, bias)
     x, w = _f32(x), _f32(w)
@@ -73,7 +73,7 @@ def conv_transpose1d_tc(x, w, bias=None, stride=1, pre_slope=1.0, debug_flags=0)
     y = torch.empty(B, Cout, L * stride, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().pb_conv_transpose1d_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y),
-                                                      B, Cin, Cout, L, K, stride, pre_slope, debug_flags,
+                                                      B, Cin, Cout, L, K, stride, pre_slope, int(bool(single_pass)),
                                                       _lib.stream_ptr(x.device)))
     return y
 

@@ -88,6 +88,9 @@ class _Engine:
 
 
 class Generator(nn.Module):
+    #: pb_voc_cfg.conv_mode: 0 = fp32 SIMT kernels, 1 = tcgen05 split-bf16 (fp32-accurate, default), 2 = tcgen05 bf16
+    conv_mode = 1
+
     def __init__(self, h):
         super().__init__()
         self.h = h
@@ -137,10 +140,11 @@ class Generator(nn.Module):
         cfg.num_embeddings = 0
         cfg.embedding_dim = 0
         cfg.num_speakers = 0
+        cfg.conv_mode = int(self.conv_mode)
         return cfg
 
     def _stamp(self, device):
-        return (str(device),) + tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        return (str(device), int(self.conv_mode)) + tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
 
     def _engine(self, device):
         """pb_voc handle holding the folded + packed copy of the current parameters."""

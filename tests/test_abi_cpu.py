@@ -39,13 +39,13 @@ def test_library_exports_every_declared_symbol(lib_path):
 def test_ctypes_table_matches_header(lib_path):
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.pb_version() == 1
+    assert lib.pb_version() == 2
     assert lib.pb_last_error() is not None
 
 
 def test_struct_layouts_match_header():
     # pb_voc_cfg: 3 + 8 + 8 + 1 + 4 + 1 + 16 + 3 int32 ; pb_tte_cfg: 16 int32
-    assert ctypes.sizeof(_lib.VocCfg) == 4 * (3 + 8 + 8 + 1 + 4 + 1 + 16 + 3)
+    assert ctypes.sizeof(_lib.VocCfg) == 4 * (3 + 8 + 8 + 1 + 4 + 1 + 16 + 4)
     assert ctypes.sizeof(_lib.TteCfg) == 4 * 16
 
 
