@@ -25,8 +25,9 @@ namespace {
 constexpr int TC_THREADS = 256;
 constexpr int TC_M = 128;                 // time rows per tile (UMMA M, cta_group::1)
 constexpr int TC_MAX_STAGES = 8;
-constexpr uint32_t TC_SMEM_LIMIT = 232448;  // 227 KB
-constexpr uint32_t TC_B_RESIDENT_MAX = 100 * 1024;
+constexpr int TC_MAX_ACC = 4;                // accumulator stages in TMEM
+constexpr uint32_t TC_SMEM_LIMIT = 232448;  // 227 KB: one CTA per SM
+constexpr uint32_t TC_SMEM_HALF = 115712;   // 113 KB: two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 
 struct TcParams {
     const uint8_t* w;
@@ -41,14 +42,14 @@ struct TcParams {
     int K, D, pad;
     int nchunks, ksteps, cin_t;
     int a_loads, a_row_bytes, a_tile_bytes, a_stage_bytes, lo_off, a_layout, a_sbo;
-    int n_a_stages, n_b_stages, b_block_bytes, b_resident, w_total_bytes;
-    uint32_t smem_a_off, smem_b_off;
+    int n_a_stages, n_b_stages, b_block_bytes, b_sub_bytes, kpb, b_resident, w_total_bytes;
+    uint32_t smem_a_off, smem_b_off, smem_bias_off;
     int tiles_t, total_tiles;
     float post_slope, scale, res_unslope;
     int tanh_out;
     uint32_t idesc;
     int single_pass;
-    int tmem_cols;
+    int tmem_cols, n_acc;
 };
 
 // ---- tcgen05 / TMEM wrappers -----------------------------------------------------------------------------------------
@@ -101,6 +102,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     return d;
 }
 
+// true in exactly one lane of a converged warp (the same lane every time)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+
 __device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -114,7 +122,8 @@ __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u &
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool RES, bool ACC>
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -124,9 +133,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     uint64_t* full_b = bars + 2 * TC_MAX_STAGES;
     uint64_t* empty_b = bars + 3 * TC_MAX_STAGES;
     uint64_t* acc_full = bars + 4 * TC_MAX_STAGES;
-    uint64_t* acc_empty = acc_full + 2;
-    uint64_t* b_res_full = acc_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 6);
+    uint64_t* acc_empty = acc_full + TC_MAX_ACC;
+    uint64_t* b_res_full = acc_full + 2 * TC_MAX_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2 * TC_MAX_ACC + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sm_base = smem_u32(sm);
@@ -137,10 +146,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
             mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1);
         }
-        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-        mbar_init(&acc_empty[0], 128); mbar_init(&acc_empty[1], 128);
+        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
         mbar_init(b_res_full, 1);
         fence_mbar_init();
+    }
+    {   // bias -> shared memory (zeros when the layer has none)
+        float* bias_w = reinterpret_cast<float*>(sm + p.smem_bias_off);
+        for (int i = threadIdx.x; i < p.out_C; i += TC_THREADS) bias_w[i] = p.bias ? p.bias[i] : 0.f;
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
@@ -150,192 +162,273 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
 
     const int tiles_per_b = p.tiles_t * p.n_tiles_n;
 
+    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes), so that addresses, descriptors and barrier
+    // phases live in uniform registers; only the asynchronous instructions themselves are issued by one elected lane.
+    // (Measured: running the loops inside `if (lane == 0)` costs ~25 dependent R2UR/ELECT instructions per tcgen05.mma
+    // and left the tensor pipe 57-80 % idle.)
     if (warp == 0) {
-        if (lane == 0) {
-            // =========================== producer ===========================
-            if (p.b_resident) {
+        // =========================== producer ===========================
+        if (p.b_resident) {
+            if (elect_one()) {
                 mbar_expect_tx(b_res_full, (uint32_t)p.w_total_bytes);
                 for (int off = 0; off < p.w_total_bytes; off += 32768) {
                     const int n = p.w_total_bytes - off < 32768 ? p.w_total_bytes - off : 32768;
                     bulk_load_1d(sm + p.smem_b_off + off, p.w + off, (uint32_t)n, b_res_full);
                 }
             }
-            uint32_t a_it = 0, b_it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_b;
-                const int rem = tile - b * tiles_per_b;
-                const int tt = rem / p.n_tiles_n, nt = rem - tt * p.n_tiles_n;
-                const int row0 = tt * TC_M - p.pad;
-                for (int c = 0; c < p.nchunks; ++c) {
-                    const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
-                    mbar_wait(&empty_a[s], ph ^ 1);
+            __syncwarp();
+        }
+        uint32_t a_it = 0, b_it = 0;
+        const int nsub = p.ksteps / p.kpb;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_b;
+            const int rem = tile - b * tiles_per_b;
+            const int tt = rem / p.n_tiles_n, nt = rem - tt * p.n_tiles_n;
+            const int row0 = tt * TC_M - p.pad;
+            for (int c = 0; c < p.nchunks; ++c) {
+                const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
+                mbar_wait(&empty_a[s], ph ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&full_a[s], (uint32_t)(p.a_loads * p.a_tile_bytes));
                     uint8_t* dst = sm + p.smem_a_off + s * p.a_stage_bytes;
                     tma_load_3d(dst, &xmap, c * p.cin_t, row0, b, &full_a[s]);
                     if (p.a_loads == 2) tma_load_3d(dst + p.a_tile_bytes, &xmap, p.Cin + c * p.cin_t, row0, b, &full_a[s]);
-                    ++a_it;
-                    if (!p.b_resident) {
-                        for (int j = 0; j < p.K; ++j) {
-                            const uint32_t sb = b_it % p.n_b_stages, phb = (b_it / p.n_b_stages) & 1;
-                            mbar_wait(&empty_b[sb], phb ^ 1);
-                            mbar_expect_tx(&full_b[sb], (uint32_t)p.b_block_bytes);
-                            bulk_load_1d(sm + p.smem_b_off + sb * p.b_block_bytes,
-                                         p.w + (size_t)((nt * p.nchunks + c) * p.K + j) * p.b_block_bytes, (uint32_t)p.b_block_bytes,
+                }
+                __syncwarp();
+                ++a_it;
+                if (!p.b_resident) {
+                    const uint8_t* wsrc = p.w + (size_t)((nt * p.nchunks + c) * p.K) * p.b_block_bytes;
+                    for (int jb = 0; jb < p.K * nsub; ++jb) {
+                        const uint32_t sb = b_it % p.n_b_stages, phb = (b_it / p.n_b_stages) & 1;
+                        mbar_wait(&empty_b[sb], phb ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_b[sb], (uint32_t)p.b_sub_bytes);
+                            bulk_load_1d(sm + p.smem_b_off + sb * p.b_sub_bytes, wsrc + (size_t)jb * p.b_sub_bytes, (uint32_t)p.b_sub_bytes,
                                          &full_b[sb]);
-                            ++b_it;
                         }
+                        __syncwarp();
+                        ++b_it;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // =========================== MMA issuer ===========================
-            if (p.b_resident) { mbar_wait(b_res_full, 0); tc_fence_after(); }
-            uint32_t a_it = 0, b_it = 0, tile_i = 0;
-            const uint32_t b_lbo = (uint32_t)p.NT * 16u;          // between the two 8-element K halves of a k-step
-            const uint32_t kstep_b_bytes = (uint32_t)p.NT * 32u;  // one k-step (16 channels) of one precision plane
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
-                const int rem = tile % tiles_per_b;
-                const int nt = rem % p.n_tiles_n;
-                const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
-                mbar_wait(&acc_empty[as], aph ^ 1);
+        // =========================== MMA issuer ===========================
+        if (p.b_resident) { mbar_wait(b_res_full, 0); tc_fence_after(); }
+        uint32_t a_it = 0, b_it = 0, tile_i = 0;
+        const uint32_t plane_bytes = (uint32_t)p.NT * 32u;    // one k-step (16 channels) of one precision plane of B
+        const int nsub = p.ksteps / p.kpb;
+        // descriptor halves that never change: hi word = SBO | version | layout, lo word = start address | LBO
+        const uint32_t a_desc_hi = (uint32_t)(smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0) >> 32);
+        const uint32_t a_desc_lo = (uint32_t)smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
+        const uint32_t b_desc_hi = (uint32_t)(smem_desc(0, (uint32_t)p.NT * 16u, 128, 0, 0) >> 32);
+        const uint32_t b_desc_lo = (uint32_t)smem_desc(0, (uint32_t)p.NT * 16u, 128, 0, 0);
+        auto adesc = [&](uint32_t addr) { return ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_desc_lo | ((addr >> 4) & 0x3fffu)); };
+        auto bdesc = [&](uint32_t addr) { return ((uint64_t)b_desc_hi << 32) | (uint64_t)(b_desc_lo | ((addr >> 4) & 0x3fffu)); };
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+            const int rem = tile % tiles_per_b;
+            const int nt = rem % p.n_tiles_n;
+            const uint32_t as = tile_i % (uint32_t)p.n_acc, aph = (tile_i / (uint32_t)p.n_acc) & 1;
+            mbar_wait(&acc_empty[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * (uint32_t)p.NT;
+            uint32_t accumulate = 0;
+            for (int c = 0; c < p.nchunks; ++c) {
+                const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
+                mbar_wait(&full_a[s], ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * (uint32_t)p.NT;
-                uint32_t accumulate = 0;
-                for (int c = 0; c < p.nchunks; ++c) {
-                    const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
-                    mbar_wait(&full_a[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_base = sm_base + p.smem_a_off + s * p.a_stage_bytes;
-                    for (int j = 0; j < p.K; ++j) {
-                        uint32_t b_base;
-                        uint32_t sb = 0;
+                const uint32_t a_base = sm_base + p.smem_a_off + s * p.a_stage_bytes;
+                const uint32_t b_res_base = sm_base + p.smem_b_off + (uint32_t)((nt * p.nchunks + c) * p.K) * (uint32_t)p.b_block_bytes;
+                for (int j = 0; j < p.K; ++j) {
+                    // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address
+                    // advanced by whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K
+                    // views of one staged tile.
+                    const uint32_t a_tap = a_base + (uint32_t)(j * p.D) * (uint32_t)p.a_row_bytes;
+                    for (int kb = 0; kb < nsub; ++kb) {
+                        uint32_t b_base, sb = 0;
                         if (p.b_resident) {
-                            b_base = sm_base + p.smem_b_off + (uint32_t)((nt * p.nchunks + c) * p.K + j) * (uint32_t)p.b_block_bytes;
+                            b_base = b_res_base + (uint32_t)(j * nsub + kb) * (uint32_t)p.b_sub_bytes;
                         } else {
                             sb = b_it % p.n_b_stages;
                             const uint32_t phb = (b_it / p.n_b_stages) & 1;
                             mbar_wait(&full_b[sb], phb);
                             tc_fence_after();
-                            b_base = sm_base + p.smem_b_off + sb * (uint32_t)p.b_block_bytes;
+                            b_base = sm_base + p.smem_b_off + sb * (uint32_t)p.b_sub_bytes;
                         }
-                        const uint32_t a_tap = a_base + (uint32_t)(j * p.D) * (uint32_t)p.a_row_bytes;
-                        for (int ks = 0; ks < p.ksteps; ++ks) {
-                            const uint32_t a_hi = a_tap + ks * 32u, a_lo = a_hi + (uint32_t)p.lo_off;
-                            // The swizzle is a function of the absolute shared-memory address (measured on B200: a start
-                            // address advanced by whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the
-                            // K taps are K views of one staged tile.
-                            const uint64_t da_hi = smem_desc(a_hi, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
-                            const uint64_t db_hi = smem_desc(b_base + ks * kstep_b_bytes, b_lbo, 128, 0, 0);
-                            umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-                            accumulate = 1;
-                            if (!p.single_pass) {
-                                const uint64_t da_lo = smem_desc(a_lo, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
-                                const uint64_t db_lo = smem_desc(b_base + (p.ksteps + ks) * kstep_b_bytes, b_lbo, 128, 0, 0);
-                                umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
-                                umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                        if (elect_one()) {
+                            for (int k2 = 0; k2 < p.kpb; ++k2) {
+                                const uint32_t a_hi = a_tap + (uint32_t)(kb * p.kpb + k2) * 32u;
+                                const uint64_t da_hi = adesc(a_hi);
+                                const uint64_t db_hi = bdesc(b_base + (uint32_t)(2 * k2) * plane_bytes);
+                                umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                                accumulate = 1;
+                                if (!p.single_pass) {
+                                    const uint64_t da_lo = adesc(a_hi + (uint32_t)p.lo_off);
+                                    const uint64_t db_lo = bdesc(b_base + (uint32_t)(2 * k2 + 1) * plane_bytes);
+                                    umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
+                                    umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                                }
                             }
+                            if (!p.b_resident) umma_commit(&empty_b[sb]);
                         }
-                        if (!p.b_resident) { umma_commit(&empty_b[sb]); ++b_it; }
+                        __syncwarp();
+                        accumulate = 1;
+                        if (!p.b_resident) ++b_it;
                     }
-                    umma_commit(&empty_a[s]);
-                    ++a_it;
                 }
-                umma_commit(&acc_full[as]);
+                if (elect_one()) umma_commit(&empty_a[s]);
+                __syncwarp();
+                ++a_it;
             }
+            if (elect_one()) umma_commit(&acc_full[as]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
+        // Work items are (tile, 16-column chunk) in order; the residual / running-sum rows of item k+1 are requested
+        // before the arithmetic of item k, so their HBM latency hides behind it and behind the accumulator wait.
+        // Everything that costs an integer division is done once per tile; bias comes from shared memory.
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int Lout = p.L * p.U;
         const size_t out_pitch = (size_t)2 * p.out_C;
-        uint32_t tile_i = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
-            const int b = tile / tiles_per_b;
-            const int rem = tile - b * tiles_per_b;
-            const int tt = rem / p.n_tiles_n, nt = rem - tt * p.n_tiles_n;
+        const float* bias_s = reinterpret_cast<const float*>(sm + p.smem_bias_off);
+
+        struct TileCtx { int b, nt, orow0, valid_rows; size_t row_el; bool ok, row_ok; };
+        auto locate = [&](int tile, TileCtx& c) {
+            c.ok = tile < p.total_tiles;
+            if (!c.ok) return;
+            c.b = tile / tiles_per_b;
+            const int rem = tile - c.b * tiles_per_b;
+            const int tt = rem / p.n_tiles_n;
+            c.nt = rem - tt * p.n_tiles_n;
             const int t = tt * TC_M + row;
-            const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
-            mbar_wait(&acc_full[as], aph);
-            tc_fence_after();
+            c.row_ok = t < p.L;
+            c.orow0 = t * p.U;
+            c.row_el = ((size_t)c.b * Lout + c.orow0) * out_pitch;
             int valid = Lout;
-            if (p.lens) { const int v = p.lens[b] * p.len_mul; valid = v < valid ? v : valid; }
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.NT;
-            for (int n0 = 0; n0 < p.NT; n0 += 16) {
-                float v[16];
-                tmem_ld16(taddr0 + (uint32_t)n0, v);
-                if (t >= p.L) continue;
-                const int ng = nt * p.NT + n0;
-                const int phs = ng / p.out_C, co = ng - phs * p.out_C;
-                const int orow = t * p.U + phs;
-                const size_t rowoff = ((size_t)b * Lout + orow) * out_pitch;
-                if (p.bias) {
+            if (p.lens) { const int v = p.lens[c.b] * p.len_mul; valid = v < valid ? v : valid; }
+            c.valid_rows = valid;
+        };
+        // element offset of the item's 16 hi values, its first output channel, and whether the row is inside the valid length
+        auto item = [&](const TileCtx& c, int n0, size_t& off, int& co, bool& live) {
+            const int ng = c.nt * p.NT + n0;
+            if (p.U == 1) {
+                co = ng; off = c.row_el + ng; live = c.orow0 < c.valid_rows;
+            } else {
+                const int phs = ng / p.out_C;
+                co = ng - phs * p.out_C;
+                off = c.row_el + (size_t)phs * out_pitch + co;
+                live = c.orow0 + phs < c.valid_rows;
+            }
+        };
+        auto request = [&](bool ok, size_t off, uint4 (&r)[4], uint4 (&a)[4]) {
+            if (!ok) return;
+            if (RES) {
+                const uint4* rh = reinterpret_cast<const uint4*>(p.res + off);
+                const uint4* rl = reinterpret_cast<const uint4*>(p.res + off + p.out_C);
+                r[0] = __ldg(rh); r[1] = __ldg(rh + 1); r[2] = __ldg(rl); r[3] = __ldg(rl + 1);
+            }
+            if (ACC) {   // may alias `out` of an earlier item of this same thread: plain loads
+                const uint4* ah = reinterpret_cast<const uint4*>(p.accin + off);
+                const uint4* al = reinterpret_cast<const uint4*>(p.accin + off + p.out_C);
+                a[0] = ah[0]; a[1] = ah[1]; a[2] = al[0]; a[3] = al[1];
+            }
+        };
+
+        int tile = blockIdx.x, n0 = 0;
+        uint32_t tile_i = 0;
+        TileCtx cur;
+        locate(tile, cur);
+        size_t off = 0; int co = 0; bool live = false;
+        if (cur.ok) item(cur, 0, off, co, live);
+        uint4 R[4], A[4];
+        request(cur.ok && cur.row_ok, off, R, A);
+        while (cur.ok) {
+            // next item
+            TileCtx nxt = cur;
+            int tile_n = tile, n0n = n0 + 16;
+            if (n0n >= p.NT) { n0n = 0; tile_n += gridDim.x; locate(tile_n, nxt); }
+            size_t offn = 0; int con = 0; bool liven = false;
+            if (nxt.ok) item(nxt, n0n, offn, con, liven);
+
+            const uint32_t as = tile_i % (uint32_t)p.n_acc, aph = (tile_i / (uint32_t)p.n_acc) & 1;
+            if (n0 == 0) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+            }
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.NT + (uint32_t)n0, v);
+            uint4 Rn[4], An[4];
+            request(nxt.ok && nxt.row_ok, offn, Rn, An);
+            if (n0n == 0) {                            // accumulator fully read: hand it back before the arithmetic
+                tc_fence_before();
+                mbar_arrive(&acc_empty[as]);
+            }
+            if (cur.row_ok) {
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + co);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bv = bp[i];
+                    v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
                 }
-                if (p.res) {
-                    const uint4* rh = reinterpret_cast<const uint4*>(p.res + rowoff + co);
-                    const uint4* rl = reinterpret_cast<const uint4*>(p.res + rowoff + p.out_C + co);
-                    const uint4 h0 = rh[0], h1 = rh[1], l0 = rl[0], l1 = rl[1];
-                    const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                    const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                if (RES) {
+                    const uint32_t hh[8] = {R[0].x, R[0].y, R[0].z, R[0].w, R[1].x, R[1].y, R[1].z, R[1].w};
+                    const uint32_t ll[8] = {R[2].x, R[2].y, R[2].z, R[2].w, R[3].x, R[3].y, R[3].z, R[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float r0 = bf16lo(hh[i]) + bf16lo(ll[i]);
-                        float r1 = bf16hi(hh[i]) + bf16hi(ll[i]);
-                        r0 = r0 < 0.f ? r0 * p.res_unslope : r0;
-                        r1 = r1 < 0.f ? r1 * p.res_unslope : r1;
-                        v[2 * i] += r0; v[2 * i + 1] += r1;
+                        const float r0 = bf16lo(hh[i]) + bf16lo(ll[i]);
+                        const float r1 = bf16hi(hh[i]) + bf16hi(ll[i]);
+                        v[2 * i] += fminf(r0, r0 * p.res_unslope);       // undo the stored leaky relu (1/slope >= 1)
+                        v[2 * i + 1] += fminf(r1, r1 * p.res_unslope);
                     }
                 }
-                if (p.accin) {
-                    const uint4* rh = reinterpret_cast<const uint4*>(p.accin + rowoff + co);
-                    const uint4* rl = reinterpret_cast<const uint4*>(p.accin + rowoff + p.out_C + co);
-                    const uint4 h0 = rh[0], h1 = rh[1], l0 = rl[0], l1 = rl[1];
-                    const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                    const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                if (ACC) {
+                    const uint32_t hh[8] = {A[0].x, A[0].y, A[0].z, A[0].w, A[1].x, A[1].y, A[1].z, A[1].w};
+                    const uint32_t ll[8] = {A[2].x, A[2].y, A[2].z, A[2].w, A[3].x, A[3].y, A[3].z, A[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         v[2 * i] = (bf16lo(hh[i]) + bf16lo(ll[i])) + v[2 * i];
                         v[2 * i + 1] = (bf16hi(hh[i]) + bf16hi(ll[i])) + v[2 * i + 1];
                     }
                 }
-                const bool live = orow < valid;
+                const float sc = live ? p.scale : 0.f;      // rows past the valid length are written as zeros
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float u = v[i] * p.scale;
-                    u = fmaxf(u, u * p.post_slope);     // leaky relu for slope in [0,1]; slope 1 = identity
-                    if (p.tanh_out) u = tanhf(u);
-                    v[i] = live ? u : 0.f;
+                    const float u = v[i] * sc;
+                    v[i] = fmaxf(u, u * p.post_slope);      // leaky relu for slope in [0,1]; slope 1 = identity
+                }
+                if (p.tanh_out) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
                 }
                 if (p.out) {
                     uint32_t hw[8], lw[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-                        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-                        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-                        hw[i] = pack_bf16(h0, h1);
-                        lw[i] = pack_bf16(l0, l1);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - bf16lo(hw[i]), v[2 * i + 1] - bf16hi(hw[i]));
+                        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
                     }
-                    __nv_bfloat16* oh = p.out + rowoff + co;
-                    __nv_bfloat16* ol = p.out + rowoff + p.out_C + co;
+                    __nv_bfloat16* oh = p.out + off;
+                    __nv_bfloat16* ol = oh + p.out_C;
                     st_global_v4(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]));
                     st_global_v4(oh + 8, make_uint4(hw[4], hw[5], hw[6], hw[7]));
                     st_global_v4(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]));
                     st_global_v4(ol + 8, make_uint4(lw[4], lw[5], lw[6], lw[7]));
                 }
                 if (p.out_f32) {
-                    float* of = p.out_f32 + ((size_t)b * Lout + orow) * p.out_C + co;
+                    float* of = p.out_f32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<float4*>(of + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { R[i] = Rn[i]; A[i] = An[i]; }
+            if (n0n == 0) ++tile_i;
+            cur = nxt; tile = tile_n; n0 = n0n; off = offn; co = con; live = liven;
         }
     }
 
@@ -419,30 +512,47 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.lo_off = a.Cin >= 64 ? p.a_tile_bytes : (a.Cin == 32 ? 64 : 32);
     p.a_layout = cin_t == 16 ? 4 : 2;
     p.a_sbo = 8 * p.a_row_bytes;
-    p.b_block_bytes = 2 * p.ksteps * NT * 32;
+    p.b_block_bytes = 2 * p.ksteps * NT * 32;           // one (n tile, channel chunk, tap): ksteps x {hi, lo} planes
+    p.kpb = 16384 / (2 * NT * 32);                       // k-steps per streamed sub-block (~16 KB)
+    if (p.kpb < 1) p.kpb = 1;
+    if (p.kpb > p.ksteps) p.kpb = p.ksteps;
+    while (p.ksteps % p.kpb) --p.kpb;
+    p.b_sub_bytes = p.kpb * 2 * NT * 32;
     p.w_total_bytes = p.n_tiles_n * p.nchunks * a.K * p.b_block_bytes;
-    const uint32_t budget = TC_SMEM_LIMIT - 2048;   // barriers + alignment slack
-    p.smem_a_off = 1024;
-    p.b_resident = (uint32_t)p.w_total_bytes <= TC_B_RESIDENT_MAX ? 1 : 0;
-    uint32_t b_bytes;
-    if (p.b_resident) {
-        b_bytes = (uint32_t)round_up(p.w_total_bytes, 1024);
-        p.n_b_stages = 1;
-        p.n_a_stages = (int)((budget - b_bytes) / (uint32_t)p.a_stage_bytes);
+    p.smem_bias_off = 1024;
+    p.smem_a_off = 1024 + (uint32_t)round_up((int64_t)a.out_C * 4, 1024);
+    // weights stay resident whenever they fit next to two activation stages
+    p.b_resident = (uint64_t)round_up(p.w_total_bytes, 1024) + 2ull * (uint64_t)p.a_stage_bytes + 1024ull + p.smem_a_off <= TC_SMEM_LIMIT ? 1 : 0;
+    // Shared-memory plan.  Narrow layers (weights resident, small tiles) are latency bound per tile: run two CTAs per SM
+    // when >= 3 activation stages still fit in half an SM; wide layers take the whole SM and stream the weights.
+    uint32_t b_bytes = 0;
+    int ctas_per_sm = 1;
+    auto plan = [&](uint32_t limit) {
+        const uint32_t budget = limit - 1024 - p.smem_a_off;   // barriers + bias + alignment slack
+        if (p.b_resident) {
+            b_bytes = (uint32_t)round_up(p.w_total_bytes, 1024);
+            p.n_b_stages = 1;
+            p.n_a_stages = budget > b_bytes ? (int)((budget - b_bytes) / (uint32_t)p.a_stage_bytes) : 0;
+        } else {
+            if (budget < 2u * (uint32_t)p.a_stage_bytes + (uint32_t)p.b_sub_bytes) { p.n_a_stages = 0; p.n_b_stages = 0; return; }
+            const uint32_t left = budget - 2u * (uint32_t)p.a_stage_bytes;
+            p.n_b_stages = (int)(left / (uint32_t)p.b_sub_bytes);
+            if (p.n_b_stages > TC_MAX_STAGES) p.n_b_stages = TC_MAX_STAGES;
+            b_bytes = (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
+            p.n_a_stages = (int)((budget - b_bytes) / (uint32_t)p.a_stage_bytes);   // spend the rest on activation prefetch
+        }
+        if (p.n_a_stages > TC_MAX_STAGES) p.n_a_stages = TC_MAX_STAGES;
+    };
+    plan(TC_SMEM_HALF);
+    if (p.b_resident && p.n_a_stages >= 3 && NT <= 128) {
+        ctas_per_sm = 2;
     } else {
-        p.n_a_stages = 2;
-        const uint32_t left = budget - 2u * (uint32_t)p.a_stage_bytes;
-        p.n_b_stages = (int)(left / (uint32_t)p.b_block_bytes);
-        if (p.n_b_stages > TC_MAX_STAGES) p.n_b_stages = TC_MAX_STAGES;
-        // spend what is left on deeper activation prefetch
-        b_bytes = (uint32_t)p.n_b_stages * (uint32_t)p.b_block_bytes;
-        p.n_a_stages = (int)((budget - b_bytes) / (uint32_t)p.a_stage_bytes);
+        plan(TC_SMEM_LIMIT);
     }
-    if (p.n_a_stages > TC_MAX_STAGES) p.n_a_stages = TC_MAX_STAGES;
     PB_REQUIRE(p.n_a_stages >= 1 && p.n_b_stages >= 1, PB_ERR_INVALID, "tc_conv: tile does not fit in shared memory (Cin=%d N=%d K=%d D=%d)", a.Cin, a.N, a.K, a.D);
     p.smem_b_off = p.smem_a_off + (uint32_t)p.n_a_stages * (uint32_t)p.a_stage_bytes;
     const uint32_t smem_bytes = p.smem_b_off + b_bytes + 1024;
-    PB_REQUIRE(smem_bytes <= TC_SMEM_LIMIT, PB_ERR_INVALID, "tc_conv: shared memory plan %u exceeds the limit", smem_bytes);
+    PB_REQUIRE(smem_bytes <= (ctas_per_sm == 2 ? TC_SMEM_HALF : TC_SMEM_LIMIT), PB_ERR_INVALID, "tc_conv: shared memory plan %u exceeds the limit", smem_bytes);
     p.tiles_t = (int)ceil_div(a.L, TC_M);
     const int64_t total = (int64_t)a.B * p.tiles_t * p.n_tiles_n;
     PB_REQUIRE(total < (1LL << 31), PB_ERR_INVALID, "tc_conv: too many tiles");
@@ -451,8 +561,10 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     // instruction descriptor: D f32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     p.single_pass = a.single_pass;
+    p.n_acc = (512 / ctas_per_sm) / NT;
+    if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
     int cols = 32;
-    while (cols < 2 * NT) cols *= 2;
+    while (cols < p.n_acc * NT) cols *= 2;
     p.tmem_cols = cols;
 
     CUtensorMap xmap;
@@ -464,11 +576,17 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         int dev = 0;
         PB_CUDA(cudaGetDevice(&dev));
         PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
         attr_set = true;
     }
-    const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
-    tc_conv_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
+    const int grid = p.total_tiles < n_sm * ctas_per_sm ? p.total_tiles : n_sm * ctas_per_sm;
+    if (a.res && a.accin) tc_conv_kernel<true, true><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
+    else if (a.res) tc_conv_kernel<true, false><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
+    else if (a.accin) tc_conv_kernel<false, true><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
+    else tc_conv_kernel<false, false><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -476,7 +594,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------------------------------
 // weight packing: B operand blocks in the no-swizzle K-major canonical layout (8x16-byte core matrices)
-//   packed[((nt*nchunks + c)*K + j)] = block of 2 planes (hi, lo) x ksteps x [2 K-halves][NT/8 row groups][8 rows][8 bf16]
+//   packed[((nt*nchunks + c)*K + j)] = block of ksteps x {hi, lo} planes, each [2 K-halves][NT/8 row groups][8 rows][8 bf16]
 //   element (n, k) of a k-step: byte (kc*(NT/8) + n/8)*128 + (n%8)*16 + (k%8)*2, kc = k/8
 // ------------------------------------------------------------------------------------------------------------------------
 struct PackDev {
@@ -520,8 +638,8 @@ __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
         // block base (in bf16 elements): block index * (2 planes * ksteps * NT * 16)
         const int64_t blk = ((int64_t)(nt * d.nchunks + c) * d.K + j) * (2LL * d.ksteps * d.NT * 16);
         const int64_t within = ((int64_t)(kc * (d.NT / 8) + ng) * 8 + r) * 8 + e;
-        out[blk + (int64_t)ks * d.NT * 16 + within] = hi;
-        out[blk + (int64_t)(d.ksteps + ks) * d.NT * 16 + within] = lo;
+        out[blk + (int64_t)(2 * ks) * d.NT * 16 + within] = hi;
+        out[blk + (int64_t)(2 * ks + 1) * d.NT * 16 + within] = lo;
     }
 }
 

@@ -20,7 +20,7 @@ for (C, K, D, L) in cases:
     r = torch.randn(B, C, L, generator=g)
     ref = F.leaky_relu(F.conv1d(F.leaky_relu(x, 0.1), w, b, padding=(K - 1) * D // 2, dilation=D) + r, 0.1)
     try:
-        got = ops.conv1d_tc(x.to(dev), w.to(dev), b.to(dev), dilation=D, res=r.to(dev), pre_slope=0.1, post_slope=0.1, debug_flags=bo).cpu()
+        got = ops.conv1d_tc(x.to(dev), w.to(dev), b.to(dev), dilation=D, res=r.to(dev), pre_slope=0.1, post_slope=0.1, single_pass=bool(bo)).cpu()
         err = (got - ref).abs()
         print(f"conv C={C} K={K} D={D} L={L} bo={bo}: max err {float(err.max()):.3e} mean {float(err.mean()):.3e} (ref max {float(ref.abs().max()):.2f})", flush=True)
     except Exception as e:
@@ -33,7 +33,7 @@ for (Cin, Cout, K, U, L) in [(32, 16, 4, 2, 300), (64, 32, 4, 2, 300), (128, 64,
     b = torch.randn(Cout, generator=g)
     ref = F.conv_transpose1d(F.leaky_relu(x, 0.1), w, b, stride=U, padding=(K - U) // 2)
     try:
-        got = ops.conv_transpose1d_tc(x.to(dev), w.to(dev), b.to(dev), stride=U, pre_slope=0.1, debug_flags=bo).cpu()
+        got = ops.conv_transpose1d_tc(x.to(dev), w.to(dev), b.to(dev), stride=U, pre_slope=0.1, single_pass=bool(bo)).cpu()
         err = (got - ref).abs()
         print(f"convtr Cin={Cin} Cout={Cout} K={K} U={U} bo={bo}: max err {float(err.max()):.3e} mean {float(err.mean()):.3e}", flush=True)
     except Exception as e:
