@@ -237,51 +237,81 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                 const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
                 mbar_wait(&full_a[s], ph);
                 tc_fence_after();
+                // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address
+                // advanced by whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K
+                // views of one staged tile: tap j starts j*D rows further down.
                 const uint32_t a_base = sm_base + p.smem_a_off + s * p.a_stage_bytes;
-                const uint32_t b_res_base = sm_base + p.smem_b_off + (uint32_t)((nt * p.nchunks + c) * p.K) * (uint32_t)p.b_block_bytes;
-                for (int j = 0; j < p.K; ++j) {
-                    // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address
-                    // advanced by whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K
-                    // views of one staged tile.
-                    const uint32_t a_tap = a_base + (uint32_t)(j * p.D) * (uint32_t)p.a_row_bytes;
-                    for (int kb = 0; kb < nsub; ++kb) {
-                        uint32_t b_base, sb = 0;
-                        if (p.b_resident) {
-                            b_base = b_res_base + (uint32_t)(j * nsub + kb) * (uint32_t)p.b_sub_bytes;
-                        } else {
-                            sb = b_it % p.n_b_stages;
-                            const uint32_t phb = (b_it / p.n_b_stages) & 1;
-                            mbar_wait(&full_b[sb], phb);
-                            tc_fence_after();
-                            b_base = sm_base + p.smem_b_off + sb * (uint32_t)p.b_sub_bytes;
-                        }
-                        if (elect_one()) {
-                            for (int k2 = 0; k2 < p.kpb; ++k2) {
-                                const uint32_t a_hi = a_tap + (uint32_t)(kb * p.kpb + k2) * 32u;
-                                const uint64_t da_hi = adesc(a_hi);
-                                const uint64_t db_hi = bdesc(b_base + (uint32_t)(2 * k2) * plane_bytes);
+                const uint32_t a_lo0 = a_desc_lo | ((a_base >> 4) & 0x3fffu);      // descriptor low word of (tap 0, k-step 0, hi)
+                const uint32_t tap_step = (uint32_t)(p.D * p.a_row_bytes) >> 4;   // in 16-byte units
+                const uint32_t lo_step = (uint32_t)p.lo_off >> 4;
+                const uint32_t plane_step = plane_bytes >> 4;
+                if (p.b_resident) {
+                    // whole chunk (all taps) issued by one elected lane without further synchronisation
+                    if (elect_one()) {
+                        const uint32_t b_res_base = sm_base + p.smem_b_off + (uint32_t)((nt * p.nchunks + c) * p.K) * (uint32_t)p.b_block_bytes;
+                        uint32_t b_lo = b_desc_lo | ((b_res_base >> 4) & 0x3fffu);
+                        uint32_t a_tap = a_lo0;
+                        for (int j = 0; j < p.K; ++j) {
+                            uint32_t a_k = a_tap;
+                            for (int ks = 0; ks < p.ksteps; ++ks) {
+                                const uint64_t da_hi = ((uint64_t)a_desc_hi << 32) | a_k;
+                                const uint64_t db_hi = ((uint64_t)b_desc_hi << 32) | b_lo;
                                 umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                                 accumulate = 1;
                                 if (!p.single_pass) {
-                                    const uint64_t da_lo = adesc(a_hi + (uint32_t)p.lo_off);
-                                    const uint64_t db_lo = bdesc(b_base + (uint32_t)(2 * k2 + 1) * plane_bytes);
+                                    const uint64_t da_lo = ((uint64_t)a_desc_hi << 32) | (a_k + lo_step);
+                                    const uint64_t db_lo = ((uint64_t)b_desc_hi << 32) | (b_lo + plane_step);
                                     umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
                                     umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
                                 }
+                                a_k += 2;                      // next 16 channels: +32 bytes inside the swizzled row
+                                b_lo += 2 * plane_step;
                             }
-                            if (!p.b_resident) umma_commit(&empty_b[sb]);
+                            a_tap += tap_step;
                         }
-                        __syncwarp();
-                        accumulate = 1;
-                        if (!p.b_resident) ++b_it;
+                        umma_commit(&empty_a[s]);
+                        if (c + 1 == p.nchunks) umma_commit(&acc_full[as]);
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                } else {
+                    for (int j = 0; j < p.K; ++j) {
+                        for (int kb = 0; kb < nsub; ++kb) {
+                            const uint32_t sb = b_it % p.n_b_stages, phb = (b_it / p.n_b_stages) & 1;
+                            mbar_wait(&full_b[sb], phb);
+                            tc_fence_after();
+                            const uint32_t b_base = sm_base + p.smem_b_off + sb * (uint32_t)p.b_sub_bytes;
+                            if (elect_one()) {
+                                uint32_t b_lo = b_desc_lo | ((b_base >> 4) & 0x3fffu);
+                                uint32_t a_k = a_lo0 + (uint32_t)j * tap_step + (uint32_t)(kb * p.kpb) * 2u;
+                                for (int k2 = 0; k2 < p.kpb; ++k2) {
+                                    const uint64_t da_hi = ((uint64_t)a_desc_hi << 32) | a_k;
+                                    const uint64_t db_hi = ((uint64_t)b_desc_hi << 32) | b_lo;
+                                    umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                                    accumulate = 1;
+                                    if (!p.single_pass) {
+                                        const uint64_t da_lo = ((uint64_t)a_desc_hi << 32) | (a_k + lo_step);
+                                        const uint64_t db_lo = ((uint64_t)b_desc_hi << 32) | (b_lo + plane_step);
+                                        umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
+                                        umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                                    }
+                                    a_k += 2;
+                                    b_lo += 2 * plane_step;
+                                }
+                                umma_commit(&empty_b[sb]);
+                                if (j + 1 == p.K && kb + 1 == nsub) {
+                                    umma_commit(&empty_a[s]);
+                                    if (c + 1 == p.nchunks) umma_commit(&acc_full[as]);
+                                }
+                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            ++b_it;
+                        }
                     }
                 }
-                if (elect_one()) umma_commit(&empty_a[s]);
-                __syncwarp();
                 ++a_it;
             }
-            if (elect_one()) umma_commit(&acc_full[as]);
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
