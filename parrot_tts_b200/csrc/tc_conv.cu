@@ -15,6 +15,7 @@
 // Weights of the narrow layers (<= 100 KB packed) stay resident in shared memory for the whole launch; the wide layers
 // stream one (channel chunk, tap) block at a time through a ring.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "pb_tc.cuh"
 
@@ -42,13 +43,14 @@ struct TcParams {
     int K, D, pad;
     int nchunks, ksteps, cin_t;
     int a_loads, a_row_bytes, a_tile_bytes, a_stage_bytes, lo_off, a_layout, a_sbo;
-    int n_a_stages, n_b_stages, b_block_bytes, b_sub_bytes, kpb, b_resident, w_total_bytes;
-    uint32_t smem_a_off, smem_b_off, smem_bias_off;
+    int n_a_stages, n_b_stages, b_block_bytes, b_sub_bytes, kpb, w_total_bytes;
+    int res_blocks, total_blocks;          // weight blocks [nt][chunk][tap] below res_blocks stay resident in shared memory
+    uint32_t smem_a_off, smem_b_off, smem_ring_off, smem_bias_off;
     int tiles_t, total_tiles;
     float post_slope, scale, res_unslope;
     int tanh_out;
-    uint32_t idesc;
-    int single_pass;
+    uint32_t idesc, idesc_stack;
+    int single_pass, stack, acc_cols;
     int tmem_cols, n_acc;
 };
 
@@ -90,6 +92,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 16-column blocks of the same lanes, summed (the hi.hi + lo.hi block and the hi.lo block of a stacked accumulator)
+__device__ __forceinline__ void tmem_ld16x2_sum(uint32_t t0, uint32_t t1, float* v) {
+    uint32_t r[16], u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(t0)
+        : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(t1)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(u[i]);
+}
+
 // shared-memory matrix descriptor (sm_100 "version 1"): start address, leading / stride byte offsets in 16-byte units
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout, uint32_t base_offset) {
     uint64_t d = 0;
@@ -120,6 +142,145 @@ __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u <
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------------
+// MMA issuer (warp 1).  The loops run warp-uniformly; one elected lane issues.  KSTEPS (16-channel k-steps per chunk) and MODE
+// are compile-time so that one tap is a straight line of tcgen05.mma with immediate descriptor offsets (measured: with runtime
+// loop bounds the ~270 cycles of constant-bank loads and branches per tap, not the tensor pipe, bounded the narrow layers).
+//   MODE 2 (NT <= 128):  D[0,2NT) += A_hi.[B_hi;B_lo]^T ;  D[0,NT) += A_lo.B_hi^T      (2 MMAs per k-step, epilogue adds the halves)
+//   MODE 1 (NT = 256):   D += A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T                   (3 MMAs)
+//   MODE 0:              D += A_hi.B_hi^T                                               (plain bf16)
+// ------------------------------------------------------------------------------------------------------------------------
+struct MmaCtx {
+    uint64_t *full_a, *empty_a, *full_b, *empty_b, *acc_full, *acc_empty, *b_res_full;
+    uint32_t sm_base, tmem_base;
+};
+
+template <int MODE>
+__device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi_word, uint32_t b_hi_word, uint32_t a_k, uint32_t b_k,
+                                            uint32_t lo_step, uint32_t lo_rows_step, uint32_t idesc, uint32_t idesc_stack,
+                                            uint32_t accumulate) {
+    const uint64_t da_hi = ((uint64_t)a_hi_word << 32) | a_k;
+    const uint64_t db_hi = ((uint64_t)b_hi_word << 32) | b_k;
+    if (MODE == 2) {
+        umma_bf16(d_tmem, da_hi, db_hi, idesc_stack, accumulate);
+        umma_bf16(d_tmem, ((uint64_t)a_hi_word << 32) | (a_k + lo_step), db_hi, idesc, 1);
+    } else {
+        umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
+        if (MODE == 1) {
+            umma_bf16(d_tmem, ((uint64_t)a_hi_word << 32) | (a_k + lo_step), db_hi, idesc, 1);
+            umma_bf16(d_tmem, da_hi, ((uint64_t)b_hi_word << 32) | (b_k + lo_rows_step), idesc, 1);
+        }
+    }
+}
+
+template <int KSTEPS, int MODE>
+__device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) {
+    if (p.res_blocks > 0) { mbar_wait(mc.b_res_full, 0); tc_fence_after(); }
+    uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, acc_s = 0, acc_ph = 0;
+    // everything the inner loops need, read from the parameter block once
+    const int K = p.K, nchunks = p.nchunks, n_tiles_n = p.n_tiles_n, res_blocks = p.res_blocks, kpb = p.kpb;
+    const int nsub = KSTEPS / kpb;
+    const uint32_t n_a_stages = (uint32_t)p.n_a_stages, n_b_stages = (uint32_t)p.n_b_stages, n_acc = (uint32_t)p.n_acc;
+    const uint32_t acc_cols = (uint32_t)p.acc_cols, a_stage_bytes = (uint32_t)p.a_stage_bytes, b_sub_bytes = (uint32_t)p.b_sub_bytes;
+    const uint32_t idesc = p.idesc, idesc_stack = p.idesc_stack;
+    // descriptor halves that never change: hi word = SBO | version | layout, lo word = start address | LBO
+    const uint32_t a_desc_hi = (uint32_t)(smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0) >> 32);
+    const uint32_t a_desc_lo = (uint32_t)smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
+    // B k-step = [K half 0: hi rows, lo rows][K half 1: hi rows, lo rows]: LBO (K-half stride) = 2*NT*16 bytes, the lo rows
+    // start NT*16 bytes after the hi rows, so [hi; lo] is also ONE operand of 2*NT rows
+    const uint32_t b_desc_hi = (uint32_t)(smem_desc(0, (uint32_t)p.NT * 32u, 128, 0, 0) >> 32);
+    const uint32_t b_desc_lo = (uint32_t)smem_desc(0, (uint32_t)p.NT * 32u, 128, 0, 0);
+    const uint32_t tap_step = (uint32_t)(p.D * p.a_row_bytes) >> 4;   // in 16-byte units
+    const uint32_t lo_step = (uint32_t)p.lo_off >> 4;
+    const uint32_t lo_rows_step = (uint32_t)p.NT;                    // NT*16 bytes
+    const uint32_t kstep_step = (uint32_t)p.NT * 4u;                 // 2 planes x 2 K halves x NT x 16 bytes
+    const uint32_t block_step = kstep_step * KSTEPS;
+    const uint32_t a_base0 = mc.sm_base + p.smem_a_off, b_res0 = mc.sm_base + p.smem_b_off, b_ring0 = mc.sm_base + p.smem_ring_off;
+    int nt = blockIdx.x % n_tiles_n;
+    const int nt_adv = (int)(gridDim.x % (unsigned)n_tiles_n);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&mc.acc_empty[acc_s], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = mc.tmem_base + acc_s * acc_cols;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&mc.full_a[a_s], a_ph);
+            tc_fence_after();
+            // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address advanced by
+            // whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K views of one staged
+            // tile: tap j starts j*D rows further down.
+            const uint32_t a_lo0 = a_desc_lo | (((a_base0 + a_s * a_stage_bytes) >> 4) & 0x3fffu);   // (tap 0, k-step 0, hi)
+            const int blk0 = (nt * nchunks + c) * K;
+            int j0 = res_blocks - blk0;                 // taps below j0 are resident
+            j0 = j0 < 0 ? 0 : (j0 > K ? K : j0);
+            const bool last_c = c + 1 == nchunks;
+            if (j0 > 0) {
+                // resident taps: one elected lane, no further synchronisation
+                if (elect_one()) {
+                    uint32_t b_tap = b_desc_lo | (((b_res0 + (uint32_t)blk0 * (block_step << 4)) >> 4) & 0x3fffu);
+                    uint32_t a_tap = a_lo0;
+                    uint32_t acc = accumulate;
+#pragma unroll 1
+                    for (int j = 0; j < j0; ++j) {
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_tap + 2u * ks, b_tap + kstep_step * ks, lo_step, lo_rows_step,
+                                              idesc, idesc_stack, acc);
+                            acc = 1;
+                        }
+                        a_tap += tap_step;
+                        b_tap += block_step;
+                    }
+                    if (j0 == K) {
+                        umma_commit(&mc.empty_a[a_s]);
+                        if (last_c) umma_commit(&mc.acc_full[acc_s]);
+                    }
+                }
+                __syncwarp();
+                accumulate = 1;
+            }
+            for (int j = j0; j < K; ++j) {
+                for (int kb = 0; kb < nsub; ++kb) {
+                    mbar_wait(&mc.full_b[b_s], b_ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        uint32_t b_k = b_desc_lo | (((b_ring0 + b_s * b_sub_bytes) >> 4) & 0x3fffu);
+                        uint32_t a_k = a_lo0 + (uint32_t)j * tap_step + (uint32_t)(kb * kpb) * 2u;
+                        uint32_t acc = accumulate;
+                        if (kpb == KSTEPS) {
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks) {
+                                issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_k + 2u * ks, b_k + kstep_step * ks, lo_step, lo_rows_step,
+                                                  idesc, idesc_stack, acc);
+                                acc = 1;
+                            }
+                        } else {
+                            for (int ks = 0; ks < kpb; ++ks) {
+                                issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_k, b_k, lo_step, lo_rows_step, idesc, idesc_stack, acc);
+                                acc = 1;
+                                a_k += 2u;
+                                b_k += kstep_step;
+                            }
+                        }
+                        umma_commit(&mc.empty_b[b_s]);
+                        if (j + 1 == K && kb + 1 == nsub) {
+                            umma_commit(&mc.empty_a[a_s]);
+                            if (last_c) umma_commit(&mc.acc_full[acc_s]);
+                        }
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++b_s == n_b_stages) { b_s = 0; b_ph ^= 1; }
+                }
+            }
+            if (++a_s == n_a_stages) { a_s = 0; a_ph ^= 1; }
+        }
+        if (++acc_s == n_acc) { acc_s = 0; acc_ph ^= 1; }
+        nt += nt_adv;
+        if (nt >= n_tiles_n) nt -= n_tiles_n;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------------------------------
 template <bool RES, bool ACC>
@@ -168,17 +329,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     // and left the tensor pipe 57-80 % idle.)
     if (warp == 0) {
         // =========================== producer ===========================
-        if (p.b_resident) {
+        if (p.res_blocks > 0) {
             if (elect_one()) {
-                mbar_expect_tx(b_res_full, (uint32_t)p.w_total_bytes);
-                for (int off = 0; off < p.w_total_bytes; off += 32768) {
-                    const int n = p.w_total_bytes - off < 32768 ? p.w_total_bytes - off : 32768;
+                const int rbytes = p.res_blocks * p.b_block_bytes;
+                mbar_expect_tx(b_res_full, (uint32_t)rbytes);
+                for (int off = 0; off < rbytes; off += 32768) {
+                    const int n = rbytes - off < 32768 ? rbytes - off : 32768;
                     bulk_load_1d(sm + p.smem_b_off + off, p.w + off, (uint32_t)n, b_res_full);
                 }
             }
             __syncwarp();
         }
-        uint32_t a_it = 0, b_it = 0;
+        uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;      // ring slot + phase counters (no divisions in the loops)
         const int nsub = p.ksteps / p.kpb;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int b = tile / tiles_per_b;
@@ -186,132 +348,42 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             const int tt = rem / p.n_tiles_n, nt = rem - tt * p.n_tiles_n;
             const int row0 = tt * TC_M - p.pad;
             for (int c = 0; c < p.nchunks; ++c) {
-                const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
-                mbar_wait(&empty_a[s], ph ^ 1);
+                mbar_wait(&empty_a[a_s], a_ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&full_a[s], (uint32_t)(p.a_loads * p.a_tile_bytes));
-                    uint8_t* dst = sm + p.smem_a_off + s * p.a_stage_bytes;
-                    tma_load_3d(dst, &xmap, c * p.cin_t, row0, b, &full_a[s]);
-                    if (p.a_loads == 2) tma_load_3d(dst + p.a_tile_bytes, &xmap, p.Cin + c * p.cin_t, row0, b, &full_a[s]);
+                    mbar_expect_tx(&full_a[a_s], (uint32_t)(p.a_loads * p.a_tile_bytes));
+                    uint8_t* dst = sm + p.smem_a_off + a_s * p.a_stage_bytes;
+                    tma_load_3d(dst, &xmap, c * p.cin_t, row0, b, &full_a[a_s]);
+                    if (p.a_loads == 2) tma_load_3d(dst + p.a_tile_bytes, &xmap, p.Cin + c * p.cin_t, row0, b, &full_a[a_s]);
                 }
                 __syncwarp();
-                ++a_it;
-                if (!p.b_resident) {
-                    const uint8_t* wsrc = p.w + (size_t)((nt * p.nchunks + c) * p.K) * p.b_block_bytes;
-                    for (int jb = 0; jb < p.K * nsub; ++jb) {
-                        const uint32_t sb = b_it % p.n_b_stages, phb = (b_it / p.n_b_stages) & 1;
-                        mbar_wait(&empty_b[sb], phb ^ 1);
-                        if (elect_one()) {
-                            mbar_expect_tx(&full_b[sb], (uint32_t)p.b_sub_bytes);
-                            bulk_load_1d(sm + p.smem_b_off + sb * p.b_sub_bytes, wsrc + (size_t)jb * p.b_sub_bytes, (uint32_t)p.b_sub_bytes,
-                                         &full_b[sb]);
-                        }
-                        __syncwarp();
-                        ++b_it;
+                if (++a_s == (uint32_t)p.n_a_stages) { a_s = 0; a_ph ^= 1; }
+                const int blk0 = (nt * p.nchunks + c) * p.K;
+                int j0 = p.res_blocks - blk0;                 // taps below j0 are resident
+                j0 = j0 < 0 ? 0 : (j0 > p.K ? p.K : j0);
+                const uint8_t* wsrc = p.w + (size_t)(blk0 + j0) * p.b_block_bytes;
+                for (int jb = 0; jb < (p.K - j0) * nsub; ++jb) {
+                    mbar_wait(&empty_b[b_s], b_ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_b[b_s], (uint32_t)p.b_sub_bytes);
+                        bulk_load_1d(sm + p.smem_ring_off + b_s * p.b_sub_bytes, wsrc + (size_t)jb * p.b_sub_bytes, (uint32_t)p.b_sub_bytes,
+                                     &full_b[b_s]);
                     }
+                    __syncwarp();
+                    if (++b_s == (uint32_t)p.n_b_stages) { b_s = 0; b_ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (p.b_resident) { mbar_wait(b_res_full, 0); tc_fence_after(); }
-        uint32_t a_it = 0, b_it = 0, tile_i = 0;
-        const uint32_t plane_bytes = (uint32_t)p.NT * 32u;    // one k-step (16 channels) of one precision plane of B
-        const int nsub = p.ksteps / p.kpb;
-        // descriptor halves that never change: hi word = SBO | version | layout, lo word = start address | LBO
-        const uint32_t a_desc_hi = (uint32_t)(smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0) >> 32);
-        const uint32_t a_desc_lo = (uint32_t)smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
-        const uint32_t b_desc_hi = (uint32_t)(smem_desc(0, (uint32_t)p.NT * 16u, 128, 0, 0) >> 32);
-        const uint32_t b_desc_lo = (uint32_t)smem_desc(0, (uint32_t)p.NT * 16u, 128, 0, 0);
-        auto adesc = [&](uint32_t addr) { return ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_desc_lo | ((addr >> 4) & 0x3fffu)); };
-        auto bdesc = [&](uint32_t addr) { return ((uint64_t)b_desc_hi << 32) | (uint64_t)(b_desc_lo | ((addr >> 4) & 0x3fffu)); };
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
-            const int rem = tile % tiles_per_b;
-            const int nt = rem % p.n_tiles_n;
-            const uint32_t as = tile_i % (uint32_t)p.n_acc, aph = (tile_i / (uint32_t)p.n_acc) & 1;
-            mbar_wait(&acc_empty[as], aph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * (uint32_t)p.NT;
-            uint32_t accumulate = 0;
-            for (int c = 0; c < p.nchunks; ++c) {
-                const uint32_t s = a_it % p.n_a_stages, ph = (a_it / p.n_a_stages) & 1;
-                mbar_wait(&full_a[s], ph);
-                tc_fence_after();
-                // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address
-                // advanced by whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K
-                // views of one staged tile: tap j starts j*D rows further down.
-                const uint32_t a_base = sm_base + p.smem_a_off + s * p.a_stage_bytes;
-                const uint32_t a_lo0 = a_desc_lo | ((a_base >> 4) & 0x3fffu);      // descriptor low word of (tap 0, k-step 0, hi)
-                const uint32_t tap_step = (uint32_t)(p.D * p.a_row_bytes) >> 4;   // in 16-byte units
-                const uint32_t lo_step = (uint32_t)p.lo_off >> 4;
-                const uint32_t plane_step = plane_bytes >> 4;
-                if (p.b_resident) {
-                    // whole chunk (all taps) issued by one elected lane without further synchronisation
-                    if (elect_one()) {
-                        const uint32_t b_res_base = sm_base + p.smem_b_off + (uint32_t)((nt * p.nchunks + c) * p.K) * (uint32_t)p.b_block_bytes;
-                        uint32_t b_lo = b_desc_lo | ((b_res_base >> 4) & 0x3fffu);
-                        uint32_t a_tap = a_lo0;
-                        for (int j = 0; j < p.K; ++j) {
-                            uint32_t a_k = a_tap;
-                            for (int ks = 0; ks < p.ksteps; ++ks) {
-                                const uint64_t da_hi = ((uint64_t)a_desc_hi << 32) | a_k;
-                                const uint64_t db_hi = ((uint64_t)b_desc_hi << 32) | b_lo;
-                                umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-                                accumulate = 1;
-                                if (!p.single_pass) {
-                                    const uint64_t da_lo = ((uint64_t)a_desc_hi << 32) | (a_k + lo_step);
-                                    const uint64_t db_lo = ((uint64_t)b_desc_hi << 32) | (b_lo + plane_step);
-                                    umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
-                                    umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
-                                }
-                                a_k += 2;                      // next 16 channels: +32 bytes inside the swizzled row
-                                b_lo += 2 * plane_step;
-                            }
-                            a_tap += tap_step;
-                        }
-                        umma_commit(&empty_a[s]);
-                        if (c + 1 == p.nchunks) umma_commit(&acc_full[as]);
-                    }
-                    __syncwarp();
-                    accumulate = 1;
-                } else {
-                    for (int j = 0; j < p.K; ++j) {
-                        for (int kb = 0; kb < nsub; ++kb) {
-                            const uint32_t sb = b_it % p.n_b_stages, phb = (b_it / p.n_b_stages) & 1;
-                            mbar_wait(&full_b[sb], phb);
-                            tc_fence_after();
-                            const uint32_t b_base = sm_base + p.smem_b_off + sb * (uint32_t)p.b_sub_bytes;
-                            if (elect_one()) {
-                                uint32_t b_lo = b_desc_lo | ((b_base >> 4) & 0x3fffu);
-                                uint32_t a_k = a_lo0 + (uint32_t)j * tap_step + (uint32_t)(kb * p.kpb) * 2u;
-                                for (int k2 = 0; k2 < p.kpb; ++k2) {
-                                    const uint64_t da_hi = ((uint64_t)a_desc_hi << 32) | a_k;
-                                    const uint64_t db_hi = ((uint64_t)b_desc_hi << 32) | b_lo;
-                                    umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-                                    accumulate = 1;
-                                    if (!p.single_pass) {
-                                        const uint64_t da_lo = ((uint64_t)a_desc_hi << 32) | (a_k + lo_step);
-                                        const uint64_t db_lo = ((uint64_t)b_desc_hi << 32) | (b_lo + plane_step);
-                                        umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1);
-                                        umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1);
-                                    }
-                                    a_k += 2;
-                                    b_lo += 2 * plane_step;
-                                }
-                                umma_commit(&empty_b[sb]);
-                                if (j + 1 == p.K && kb + 1 == nsub) {
-                                    umma_commit(&empty_a[s]);
-                                    if (c + 1 == p.nchunks) umma_commit(&acc_full[as]);
-                                }
-                            }
-                            __syncwarp();
-                            accumulate = 1;
-                            ++b_it;
-                        }
-                    }
-                }
-                ++a_it;
-            }
+        MmaCtx mc{full_a, empty_a, full_b, empty_b, acc_full, acc_empty, b_res_full, sm_base, tmem_base};
+        switch (p.ksteps * 4 + (p.single_pass ? 0 : (p.stack ? 2 : 1))) {
+            case 1 * 4 + 2: mma_issuer<1, 2>(p, mc); break;
+            case 2 * 4 + 2: mma_issuer<2, 2>(p, mc); break;
+            case 4 * 4 + 2: mma_issuer<4, 2>(p, mc); break;
+            case 4 * 4 + 1: mma_issuer<4, 1>(p, mc); break;
+            case 1 * 4 + 0: mma_issuer<1, 0>(p, mc); break;
+            case 2 * 4 + 0: mma_issuer<2, 0>(p, mc); break;
+            default: mma_issuer<4, 0>(p, mc); break;
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
@@ -367,7 +439,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         };
 
         int tile = blockIdx.x, n0 = 0;
-        uint32_t tile_i = 0;
+        uint32_t acc_s = 0, acc_ph = 0;
         TileCtx cur;
         locate(tile, cur);
         size_t off = 0; int co = 0; bool live = false;
@@ -382,13 +454,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             size_t offn = 0; int con = 0; bool liven = false;
             if (nxt.ok) item(nxt, n0n, offn, con, liven);
 
-            const uint32_t as = tile_i % (uint32_t)p.n_acc, aph = (tile_i / (uint32_t)p.n_acc) & 1;
+            const uint32_t as = acc_s;
             if (n0 == 0) {
-                mbar_wait(&acc_full[as], aph);
+                mbar_wait(&acc_full[as], acc_ph);
                 tc_fence_after();
             }
             float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.NT + (uint32_t)n0, v);
+            {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_cols + (uint32_t)n0;
+                if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
+                else tmem_ld16(taddr, v);
+            }
             uint4 Rn[4], An[4];
             request(nxt.ok && nxt.row_ok, offn, Rn, An);
             if (n0n == 0) {                            // accumulator fully read: hand it back before the arithmetic
@@ -457,7 +533,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) { R[i] = Rn[i]; A[i] = An[i]; }
-            if (n0n == 0) ++tile_i;
+            if (n0n == 0 && ++acc_s == (uint32_t)p.n_acc) { acc_s = 0; acc_ph ^= 1; }
             cur = nxt; tile = tile_n; n0 = n0n; off = offn; co = con; live = liven;
         }
     }
@@ -543,45 +619,59 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.a_layout = cin_t == 16 ? 4 : 2;
     p.a_sbo = 8 * p.a_row_bytes;
     p.b_block_bytes = 2 * p.ksteps * NT * 32;           // one (n tile, channel chunk, tap): ksteps x {hi, lo} planes
-    p.kpb = 16384 / (2 * NT * 32);                       // k-steps per streamed sub-block (~16 KB)
+    p.kpb = 32768 / (2 * NT * 32);                       // k-steps per streamed sub-block (<= 32 KB: 6+ MMAs per barrier round trip)
     if (p.kpb < 1) p.kpb = 1;
     if (p.kpb > p.ksteps) p.kpb = p.ksteps;
     while (p.ksteps % p.kpb) --p.kpb;
     p.b_sub_bytes = p.kpb * 2 * NT * 32;
-    p.w_total_bytes = p.n_tiles_n * p.nchunks * a.K * p.b_block_bytes;
+    p.total_blocks = p.n_tiles_n * p.nchunks * a.K;
+    p.w_total_bytes = p.total_blocks * p.b_block_bytes;
     p.smem_bias_off = 1024;
     p.smem_a_off = 1024 + (uint32_t)round_up((int64_t)a.out_C * 4, 1024);
-    // weights stay resident whenever they fit next to two activation stages
-    p.b_resident = (uint64_t)round_up(p.w_total_bytes, 1024) + 2ull * (uint64_t)p.a_stage_bytes + 1024ull + p.smem_a_off <= TC_SMEM_LIMIT ? 1 : 0;
-    // Shared-memory plan.  Narrow layers (weights resident, small tiles) are latency bound per tile: run two CTAs per SM
-    // when >= 3 activation stages still fit in half an SM; wide layers take the whole SM and stream the weights.
-    uint32_t b_bytes = 0;
+    // Shared-memory plan.  Weight blocks are [n tile][chunk][tap] in the packed operand; the first `res_blocks` of them
+    // stay resident for the whole launch, the rest stream through a ring of sub-blocks once per tile.
+    //  - everything resident + >= 3 activation stages in HALF an SM: two CTAs per SM (narrow layers are latency bound per tile)
+    //  - everything resident + >= 2 stages in a whole SM: one CTA per SM
+    //  - otherwise 2 activation stages, a 4-deep ring, and as many resident blocks as still fit - kept only when they
+    //    cover at least a quarter of the operand (else the space buys more pipeline depth instead)
     int ctas_per_sm = 1;
-    auto plan = [&](uint32_t limit) {
-        const uint32_t budget = limit - 1024 - p.smem_a_off;   // barriers + bias + alignment slack
-        if (p.b_resident) {
-            b_bytes = (uint32_t)round_up(p.w_total_bytes, 1024);
-            p.n_b_stages = 1;
-            p.n_a_stages = budget > b_bytes ? (int)((budget - b_bytes) / (uint32_t)p.a_stage_bytes) : 0;
-        } else {
-            if (budget < 2u * (uint32_t)p.a_stage_bytes + (uint32_t)p.b_sub_bytes) { p.n_a_stages = 0; p.n_b_stages = 0; return; }
-            const uint32_t left = budget - 2u * (uint32_t)p.a_stage_bytes;
+    uint32_t b_res_bytes = 0, ring_bytes = 0;
+    const uint32_t w_all = (uint32_t)round_up(p.w_total_bytes, 1024);
+    auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off; };   // barriers + bias + alignment slack
+    if (NT <= 128 && budget(TC_SMEM_HALF) >= w_all + 3u * (uint32_t)p.a_stage_bytes) {
+        ctas_per_sm = 2;
+        p.res_blocks = p.total_blocks; b_res_bytes = w_all;
+        p.n_a_stages = (int)((budget(TC_SMEM_HALF) - w_all) / (uint32_t)p.a_stage_bytes);
+        p.n_b_stages = 0;
+    } else if (budget(TC_SMEM_LIMIT) >= w_all + 2u * (uint32_t)p.a_stage_bytes) {
+        p.res_blocks = p.total_blocks; b_res_bytes = w_all;
+        p.n_a_stages = (int)((budget(TC_SMEM_LIMIT) - w_all) / (uint32_t)p.a_stage_bytes);
+        p.n_b_stages = 0;
+    } else {
+        const uint32_t bud = budget(TC_SMEM_LIMIT);
+        PB_REQUIRE(bud >= 2u * (uint32_t)p.a_stage_bytes + 2u * (uint32_t)p.b_sub_bytes, PB_ERR_INVALID,
+                   "tc_conv: tile does not fit in shared memory (Cin=%d N=%d K=%d D=%d)", a.Cin, a.N, a.K, a.D);
+        p.n_a_stages = 2;
+        uint32_t left = bud - 2u * (uint32_t)p.a_stage_bytes;
+        p.n_b_stages = (int)(left / (uint32_t)p.b_sub_bytes);
+        if (p.n_b_stages > 4) p.n_b_stages = 4;
+        left -= (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
+        p.res_blocks = (int)(left / (uint32_t)p.b_block_bytes);
+        if (p.res_blocks * 4 < p.total_blocks) {
+            p.res_blocks = 0;
+            left = bud - 2u * (uint32_t)p.a_stage_bytes;
             p.n_b_stages = (int)(left / (uint32_t)p.b_sub_bytes);
             if (p.n_b_stages > TC_MAX_STAGES) p.n_b_stages = TC_MAX_STAGES;
-            b_bytes = (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
-            p.n_a_stages = (int)((budget - b_bytes) / (uint32_t)p.a_stage_bytes);   // spend the rest on activation prefetch
+            left -= (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
+            p.n_a_stages += (int)(left / (uint32_t)p.a_stage_bytes);
         }
-        if (p.n_a_stages > TC_MAX_STAGES) p.n_a_stages = TC_MAX_STAGES;
-    };
-    plan(TC_SMEM_HALF);
-    if (p.b_resident && p.n_a_stages >= 3 && NT <= 128) {
-        ctas_per_sm = 2;
-    } else {
-        plan(TC_SMEM_LIMIT);
+        b_res_bytes = (uint32_t)round_up((int64_t)p.res_blocks * p.b_block_bytes, 1024);
     }
-    PB_REQUIRE(p.n_a_stages >= 1 && p.n_b_stages >= 1, PB_ERR_INVALID, "tc_conv: tile does not fit in shared memory (Cin=%d N=%d K=%d D=%d)", a.Cin, a.N, a.K, a.D);
+    if (p.n_a_stages > TC_MAX_STAGES) p.n_a_stages = TC_MAX_STAGES;
+    ring_bytes = (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
     p.smem_b_off = p.smem_a_off + (uint32_t)p.n_a_stages * (uint32_t)p.a_stage_bytes;
-    const uint32_t smem_bytes = p.smem_b_off + b_bytes + 1024;
+    p.smem_ring_off = p.smem_b_off + b_res_bytes;
+    const uint32_t smem_bytes = p.smem_ring_off + ring_bytes + 1024;
     PB_REQUIRE(smem_bytes <= (ctas_per_sm == 2 ? TC_SMEM_HALF : TC_SMEM_LIMIT), PB_ERR_INVALID, "tc_conv: shared memory plan %u exceeds the limit", smem_bytes);
     p.tiles_t = (int)ceil_div(a.L, TC_M);
     const int64_t total = (int64_t)a.B * p.tiles_t * p.n_tiles_n;
@@ -590,11 +680,14 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.post_slope = a.post_slope; p.scale = a.scale; p.res_unslope = a.res_unslope; p.tanh_out = a.tanh_out;
     // instruction descriptor: D f32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    p.idesc_stack = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     p.single_pass = a.single_pass;
-    p.n_acc = (512 / ctas_per_sm) / NT;
+    p.stack = (!a.single_pass && NT <= 128) ? 1 : 0;
+    p.acc_cols = p.stack ? 2 * NT : NT;
+    p.n_acc = (512 / ctas_per_sm) / p.acc_cols;
     if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
     int cols = 32;
-    while (cols < p.n_acc * NT) cols *= 2;
+    while (cols < p.n_acc * p.acc_cols) cols *= 2;
     p.tmem_cols = cols;
 
     CUtensorMap xmap;
@@ -613,6 +706,13 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     const int grid = p.total_tiles < n_sm * ctas_per_sm ? p.total_tiles : n_sm * ctas_per_sm;
+    {
+        static const bool dbg = getenv("PB_TC_DEBUG") != nullptr;
+        if (dbg)
+            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d\n",
+                    a.Cin, a.N, NT, a.K, a.D, a.L, a.B, p.total_tiles, grid, ctas_per_sm, smem_bytes, p.n_a_stages, p.a_stage_bytes, p.res_blocks,
+                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc);
+    }
     if (a.res && a.accin) tc_conv_kernel<true, true><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
     else if (a.res) tc_conv_kernel<true, false><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
     else if (a.accin) tc_conv_kernel<false, true><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
@@ -624,8 +724,8 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------------------------------
 // weight packing: B operand blocks in the no-swizzle K-major canonical layout (8x16-byte core matrices)
-//   packed[((nt*nchunks + c)*K + j)] = block of ksteps x {hi, lo} planes, each [2 K-halves][NT/8 row groups][8 rows][8 bf16]
-//   element (n, k) of a k-step: byte (kc*(NT/8) + n/8)*128 + (n%8)*16 + (k%8)*2, kc = k/8
+//   packed[((nt*nchunks + c)*K + j)] = block of ksteps x [2 K-halves][hi, lo][NT/8 row groups][8 rows][8 bf16]
+//   element (n, k) of plane pl of a k-step: byte ((kc*2 + pl)*(NT/8) + n/8)*128 + (n%8)*16 + (k%8)*2, kc = k/8
 // ------------------------------------------------------------------------------------------------------------------------
 struct PackDev {
     const float* w;
@@ -665,11 +765,13 @@ __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        // block base (in bf16 elements): block index * (2 planes * ksteps * NT * 16)
+        // block base (in bf16 elements): block index * (2 planes * ksteps * NT * 16); inside a k-step the K half is outermost,
+        // then the plane, so that rows [0, NT) = hi and [NT, 2NT) = lo of ONE 2NT-row operand with LBO = 2*NT*16 bytes
         const int64_t blk = ((int64_t)(nt * d.nchunks + c) * d.K + j) * (2LL * d.ksteps * d.NT * 16);
-        const int64_t within = ((int64_t)(kc * (d.NT / 8) + ng) * 8 + r) * 8 + e;
-        out[blk + (int64_t)(2 * ks) * d.NT * 16 + within] = hi;
-        out[blk + (int64_t)(2 * ks + 1) * d.NT * 16 + within] = lo;
+        const int64_t kstep = blk + (int64_t)ks * (2LL * d.NT * 16);
+        const int64_t within = ((int64_t)ng * 8 + r) * 8 + e;
+        out[kstep + (int64_t)(kc * 2 + 0) * d.NT * 8 + within] = hi;
+        out[kstep + (int64_t)(kc * 2 + 1) * d.NT * 8 + within] = lo;
     }
 }
 
