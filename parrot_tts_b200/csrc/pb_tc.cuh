@@ -36,6 +36,7 @@ struct TcConvArgs {
     float post_slope = 1.f, scale = 1.f;
     int tanh_out = 0;                      // apply tanh after the activation (conv_post)
     int single_pass = 0;                   // 1: hi.hi only (plain bf16 product, throughput mode)
+    int n_groups = 0;                      // epilogue warpgroups per CTA (0 = choose)
 };
 
 int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)

@@ -23,10 +23,10 @@ namespace pb {
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_MAX_THREADS = 512;         // 4 service warps + up to 3 epilogue groups of 4 warps (128 registers per thread)
 constexpr int TC_M = 128;                 // time rows per tile (UMMA M, cta_group::1)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_MAX_ACC = 4;                // accumulator stages in TMEM
+constexpr int TC_MAX_ACC = 8;                // accumulator stages in TMEM
 constexpr uint32_t TC_SMEM_LIMIT = 232448;  // 227 KB: one CTA per SM
 constexpr uint32_t TC_SMEM_HALF = 115712;   // 113 KB: two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 
@@ -51,7 +51,8 @@ struct TcParams {
     int tanh_out;
     uint32_t idesc, idesc_stack;
     int single_pass, stack, acc_cols;
-    int tmem_cols, n_acc;
+    int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
+    int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads
 };
 
 // ---- tcgen05 / TMEM wrappers -----------------------------------------------------------------------------------------
@@ -184,6 +185,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
     const uint32_t n_a_stages = (uint32_t)p.n_a_stages, n_b_stages = (uint32_t)p.n_b_stages, n_acc = (uint32_t)p.n_acc;
     const uint32_t acc_cols = (uint32_t)p.acc_cols, a_stage_bytes = (uint32_t)p.a_stage_bytes, b_sub_bytes = (uint32_t)p.b_sub_bytes;
     const uint32_t idesc = p.idesc, idesc_stack = p.idesc_stack;
+    const bool skip_mma = (p.ablate & 1) != 0;
     // descriptor halves that never change: hi word = SBO | version | layout, lo word = start address | LBO
     const uint32_t a_desc_hi = (uint32_t)(smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0) >> 32);
     const uint32_t a_desc_lo = (uint32_t)smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
@@ -222,7 +224,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
                     uint32_t a_tap = a_lo0;
                     uint32_t acc = accumulate;
 #pragma unroll 1
-                    for (int j = 0; j < j0; ++j) {
+                    for (int j = 0; j < (skip_mma ? 0 : j0); ++j) {
 #pragma unroll
                         for (int ks = 0; ks < KSTEPS; ++ks) {
                             issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_tap + 2u * ks, b_tap + kstep_step * ks, lo_step, lo_rows_step,
@@ -284,7 +286,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
 
 // ------------------------------------------------------------------------------------------------------------------------
 template <bool RES, bool ACC>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -307,13 +309,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
             mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1);
         }
-        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         mbar_init(b_res_full, 1);
         fence_mbar_init();
     }
     {   // bias -> shared memory (zeros when the layer has none)
         float* bias_w = reinterpret_cast<float*>(sm + p.smem_bias_off);
-        for (int i = threadIdx.x; i < p.out_C; i += TC_THREADS) bias_w[i] = p.bias ? p.bias[i] : 0.f;
+        for (int i = threadIdx.x; i < p.out_C; i += blockDim.x) bias_w[i] = p.bias ? p.bias[i] : 0.f;
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
@@ -342,18 +344,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         }
         uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;      // ring slot + phase counters (no divisions in the loops)
         const int nsub = p.ksteps / p.kpb;
+        int b = blockIdx.x / tiles_per_b, rem = blockIdx.x - b * tiles_per_b;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int b = tile / tiles_per_b;
-            const int rem = tile - b * tiles_per_b;
-            const int tt = rem / p.n_tiles_n, nt = rem - tt * p.n_tiles_n;
+            int tt = rem, nt = 0;
+            if (p.n_tiles_n != 1) { tt = rem / p.n_tiles_n; nt = rem - tt * p.n_tiles_n; }
             const int row0 = tt * TC_M - p.pad;
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&empty_a[a_s], a_ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&full_a[a_s], (uint32_t)(p.a_loads * p.a_tile_bytes));
-                    uint8_t* dst = sm + p.smem_a_off + a_s * p.a_stage_bytes;
-                    tma_load_3d(dst, &xmap, c * p.cin_t, row0, b, &full_a[a_s]);
-                    if (p.a_loads == 2) tma_load_3d(dst + p.a_tile_bytes, &xmap, p.Cin + c * p.cin_t, row0, b, &full_a[a_s]);
+                    if (p.ablate & 8) {
+                        mbar_arrive(&full_a[a_s]);
+                    } else {
+                        mbar_expect_tx(&full_a[a_s], (uint32_t)(p.a_loads * p.a_tile_bytes));
+                        uint8_t* dst = sm + p.smem_a_off + a_s * p.a_stage_bytes;
+                        tma_load_3d(dst, &xmap, c * p.cin_t, row0, b, &full_a[a_s]);
+                        if (p.a_loads == 2) tma_load_3d(dst + p.a_tile_bytes, &xmap, p.Cin + c * p.cin_t, row0, b, &full_a[a_s]);
+                    }
                 }
                 __syncwarp();
                 if (++a_s == (uint32_t)p.n_a_stages) { a_s = 0; a_ph ^= 1; }
@@ -372,6 +378,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                     if (++b_s == (uint32_t)p.n_b_stages) { b_s = 0; b_ph ^= 1; }
                 }
             }
+            rem += (int)gridDim.x;
+            while (rem >= tiles_per_b) { rem -= tiles_per_b; ++b; }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
@@ -391,26 +399,48 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         // before the arithmetic of item k, so their HBM latency hides behind it and behind the accumulator wait.
         // Everything that costs an integer division is done once per tile; bias comes from shared memory.
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int grp = (warp - 4) >> 2;              // epilogue group: takes this CTA's tiles grp, grp + n_groups, ...
+        const int tile_stride = (int)gridDim.x * p.n_groups;
         const int row = q * 32 + lane;
         const int Lout = p.L * p.U;
         const size_t out_pitch = (size_t)2 * p.out_C;
         const float* bias_s = reinterpret_cast<const float*>(sm + p.smem_bias_off);
 
-        struct TileCtx { int b, nt, orow0, valid_rows; size_t row_el; bool ok, row_ok; };
-        auto locate = [&](int tile, TileCtx& c) {
-            c.ok = tile < p.total_tiles;
-            if (!c.ok) return;
-            c.b = tile / tiles_per_b;
-            const int rem = tile - c.b * tiles_per_b;
-            const int tt = rem / p.n_tiles_n;
-            c.nt = rem - tt * p.n_tiles_n;
+        // Tile coordinates advance incrementally by gridDim.x tiles (no division per tile); the valid length of a batch
+        // item is read from global memory only when the item changes.
+        struct TileCtx { int b, rem, nt, orow0, valid_rows; size_t row_el; bool ok, row_ok; };
+        const int n_tiles_n = p.n_tiles_n;
+        auto valid_of = [&](int b) {
+            int valid = Lout;
+            if (p.lens) { const int v = __ldg(p.lens + b) * p.len_mul; valid = v < valid ? v : valid; }
+            return valid;
+        };
+        auto place = [&](TileCtx& c) {       // (b, rem) -> row coordinates
+            int tt = c.rem;
+            c.nt = 0;
+            if (n_tiles_n != 1) { tt = c.rem / n_tiles_n; c.nt = c.rem - tt * n_tiles_n; }
             const int t = tt * TC_M + row;
             c.row_ok = t < p.L;
             c.orow0 = t * p.U;
             c.row_el = ((size_t)c.b * Lout + c.orow0) * out_pitch;
-            int valid = Lout;
-            if (p.lens) { const int v = p.lens[c.b] * p.len_mul; valid = v < valid ? v : valid; }
-            c.valid_rows = valid;
+        };
+        auto locate_first = [&](int tile, TileCtx& c) {
+            c.ok = tile < p.total_tiles;
+            if (!c.ok) return;
+            c.b = tile / tiles_per_b;
+            c.rem = tile - c.b * tiles_per_b;
+            c.valid_rows = valid_of(c.b);
+            place(c);
+        };
+        auto locate_next = [&](int tile, TileCtx& c) {      // c holds the previous tile of this CTA
+            c.ok = tile < p.total_tiles;
+            if (!c.ok) return;
+            c.rem += tile_stride;
+            if (c.rem >= tiles_per_b) {
+                do { c.rem -= tiles_per_b; ++c.b; } while (c.rem >= tiles_per_b);
+                c.valid_rows = valid_of(c.b);
+            }
+            place(c);
         };
         // element offset of the item's 16 hi values, its first output channel, and whether the row is inside the valid length
         auto item = [&](const TileCtx& c, int n0, size_t& off, int& co, bool& live) {
@@ -425,7 +455,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             }
         };
         auto request = [&](bool ok, size_t off, uint4 (&r)[4], uint4 (&a)[4]) {
-            if (!ok) return;
+            if (!ok || (p.ablate & 4)) return;
             if (RES) {
                 const uint4* rh = reinterpret_cast<const uint4*>(p.res + off);
                 const uint4* rl = reinterpret_cast<const uint4*>(p.res + off + p.out_C);
@@ -438,10 +468,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             }
         };
 
-        int tile = blockIdx.x, n0 = 0;
-        uint32_t acc_s = 0, acc_ph = 0;
+        int tile = blockIdx.x + grp * (int)gridDim.x, n0 = 0;
+        uint32_t acc_i = (uint32_t)grp;                   // local tile counter: this group sees i = grp + k*n_groups
+        const uint32_t acc_mask = (uint32_t)p.n_acc - 1u, acc_shift = (uint32_t)__ffs(p.n_acc) - 1u;   // n_acc is a power of two
         TileCtx cur;
-        locate(tile, cur);
+        locate_first(tile, cur);
         size_t off = 0; int co = 0; bool live = false;
         if (cur.ok) item(cur, 0, off, co, live);
         uint4 R[4], A[4];
@@ -450,28 +481,32 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             // next item
             TileCtx nxt = cur;
             int tile_n = tile, n0n = n0 + 16;
-            if (n0n >= p.NT) { n0n = 0; tile_n += gridDim.x; locate(tile_n, nxt); }
+            if (n0n >= p.NT) { n0n = 0; tile_n += tile_stride; locate_next(tile_n, nxt); }
             size_t offn = 0; int con = 0; bool liven = false;
             if (nxt.ok) item(nxt, n0n, offn, con, liven);
 
-            const uint32_t as = acc_s;
+            const uint32_t as = acc_i & acc_mask;
             if (n0 == 0) {
-                mbar_wait(&acc_full[as], acc_ph);
+                mbar_wait(&acc_full[as], (acc_i >> acc_shift) & 1u);
                 tc_fence_after();
             }
             float v[16];
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_cols + (uint32_t)n0;
-                if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
+                if (p.ablate & 16) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                } else if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
                 else tmem_ld16(taddr, v);
             }
             uint4 Rn[4], An[4];
             request(nxt.ok && nxt.row_ok, offn, Rn, An);
             if (n0n == 0) {                            // accumulator fully read: hand it back before the arithmetic
                 tc_fence_before();
-                mbar_arrive(&acc_empty[as]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);   // one arrival per epilogue warp
             }
-            if (cur.row_ok) {
+            if (cur.row_ok && !(p.ablate & 32)) {
                 const float4* bp = reinterpret_cast<const float4*>(bias_s + co);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -508,7 +543,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
                 }
-                if (p.out) {
+                if (p.out && !(p.ablate & 2)) {
                     uint32_t hw[8], lw[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -533,7 +568,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) { R[i] = Rn[i]; A[i] = An[i]; }
-            if (n0n == 0 && ++acc_s == (uint32_t)p.n_acc) { acc_s = 0; acc_ph ^= 1; }
+            if (n0n == 0) acc_i += (uint32_t)p.n_groups;
             cur = nxt; tile = tile_n; n0 = n0n; off = offn; co = con; live = liven;
         }
     }
@@ -638,7 +673,11 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     uint32_t b_res_bytes = 0, ring_bytes = 0;
     const uint32_t w_all = (uint32_t)round_up(p.w_total_bytes, 1024);
     auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off; };   // barriers + bias + alignment slack
-    if (NT <= 128 && budget(TC_SMEM_HALF) >= w_all + 3u * (uint32_t)p.a_stage_bytes) {
+    // two CTAs per SM (two producers, two MMA issuers, one epilogue group each) measured best for the 16-channel layers;
+    // wider layers run one CTA per SM with up to 3 epilogue groups (PB_TC_2CTA=0/1 forces either, dev switch)
+    static const int force_2cta = getenv("PB_TC_2CTA") ? atoi(getenv("PB_TC_2CTA")) : -1;
+    const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
+    if (want_2cta && budget(TC_SMEM_HALF) >= w_all + 3u * (uint32_t)p.a_stage_bytes) {
         ctas_per_sm = 2;
         p.res_blocks = p.total_blocks; b_res_bytes = w_all;
         p.n_a_stages = (int)((budget(TC_SMEM_HALF) - w_all) / (uint32_t)p.a_stage_bytes);
@@ -686,6 +725,14 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.acc_cols = p.stack ? 2 * NT : NT;
     p.n_acc = (512 / ctas_per_sm) / p.acc_cols;
     if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
+    while (p.n_acc & (p.n_acc - 1)) --p.n_acc;        // power of two
+    // The epilogue of a narrow tile is a short latency-bound chain (accumulator wait, TMEM load, arithmetic, stores):
+    // several warpgroups take alternate tiles so that those chains overlap.
+    static const int env_groups = getenv("PB_TC_GROUPS") ? atoi(getenv("PB_TC_GROUPS")) : 0;
+    p.n_groups = a.n_groups > 0 ? a.n_groups : (env_groups > 0 ? env_groups : (ctas_per_sm == 2 ? 1 : 3));
+    if (p.n_groups > p.n_acc) p.n_groups = p.n_acc;
+    if (p.n_groups > 3) p.n_groups = 3;
+    const int threads = 128 + 128 * p.n_groups;
     int cols = 32;
     while (cols < p.n_acc * p.acc_cols) cols *= 2;
     p.tmem_cols = cols;
@@ -693,6 +740,10 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     CUtensorMap xmap;
     PB_TRY(make_tmap_act(&xmap, a.x, a.Cin, a.L, a.B, cin_t == 16 ? 32 : 64, a_rows, cin_t != 16));
 
+    {
+        static const int abl = getenv("PB_TC_ABLATE") ? atoi(getenv("PB_TC_ABLATE")) : 0;
+        p.ablate = abl;
+    }
     static int n_sm = 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -709,14 +760,14 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     {
         static const bool dbg = getenv("PB_TC_DEBUG") != nullptr;
         if (dbg)
-            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d\n",
+            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d groups=%d\n",
                     a.Cin, a.N, NT, a.K, a.D, a.L, a.B, p.total_tiles, grid, ctas_per_sm, smem_bytes, p.n_a_stages, p.a_stage_bytes, p.res_blocks,
-                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc);
+                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc, p.n_groups);
     }
-    if (a.res && a.accin) tc_conv_kernel<true, true><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
-    else if (a.res) tc_conv_kernel<true, false><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
-    else if (a.accin) tc_conv_kernel<false, true><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
-    else tc_conv_kernel<false, false><<<grid, TC_THREADS, smem_bytes, st>>>(xmap, p);
+    if (a.res && a.accin) tc_conv_kernel<true, true><<<grid, threads, smem_bytes, st>>>(xmap, p);
+    else if (a.res) tc_conv_kernel<true, false><<<grid, threads, smem_bytes, st>>>(xmap, p);
+    else if (a.accin) tc_conv_kernel<false, true><<<grid, threads, smem_bytes, st>>>(xmap, p);
+    else tc_conv_kernel<false, false><<<grid, threads, smem_bytes, st>>>(xmap, p);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
