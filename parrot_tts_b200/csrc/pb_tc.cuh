@@ -37,14 +37,16 @@ struct TcConvArgs {
     int tanh_out = 0;                      // apply tanh after the activation (conv_post)
     int single_pass = 0;                   // 1: hi.hi only (plain bf16 product, throughput mode)
     int n_groups = 0;                      // epilogue warpgroups per CTA (0 = choose)
+    int fmt = 0;                           // split storage + MMA operand type of x / w / res / accin / out: 0 = bf16, 1 = fp16
+    const float* res_f32 = nullptr;        // [B][U*L][out_C] fp32 residual (added like res, no activation to undo) or null
 };
 
 int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)
 size_t tc_packed_weight_bytes(int Cin, int N, int K);
 // torch Conv1d weight f32 [Cout][Cin][K]  -> packed split-bf16 B operand (N = Cout)
-int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st);
+int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt = 0);
 // torch ConvTranspose1d weight f32 [Cin][Cout][Kt], stride U, padding (Kt-U)/2 -> 3-tap polyphase operand (N = U*Cout)
-int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st);
+int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st, int fmt = 0);
 int launch_tc_conv(const TcConvArgs& a, cudaStream_t st);
 
 // layout conversion (test entry points, embedding stage): f32 [B][C][L] (row stride pitch) <-> split-bf16 [B][L][2C]

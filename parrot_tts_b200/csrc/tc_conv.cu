@@ -15,6 +15,7 @@
 // Weights of the narrow layers (<= 100 KB packed) stay resident in shared memory for the whole launch; the wide layers
 // stream one (channel chunk, tap) block at a time through a ring.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "pb_tc.cuh"
@@ -34,6 +35,7 @@ struct TcParams {
     const uint8_t* w;
     const float* bias;
     const __nv_bfloat16* res;
+    const float* res_f32;
     const __nv_bfloat16* accin;
     __nv_bfloat16* out;
     float* out_f32;
@@ -51,6 +53,7 @@ struct TcParams {
     int tanh_out;
     uint32_t idesc, idesc_stack;
     int single_pass, stack, acc_cols;
+    int fmt;                             // split storage / MMA operand type: 0 bf16, 1 fp16
     int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
     int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads
 };
@@ -141,6 +144,42 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 }
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// ---- split 16-bit storage: value = hi + lo, both bf16 (fmt 0) or both fp16 (fmt 1; ~2^-22 relative for |v| in [2^-3, 65504]) ----
+__device__ __forceinline__ void split2(float a, float b, int fmt, uint32_t& hw, uint32_t& lw) {
+    if (fmt == 0) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+        hw = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - bf16lo(hw), b - bf16hi(hw));
+        lw = *reinterpret_cast<const uint32_t*>(&l2);
+    } else {
+        a = fminf(fmaxf(a, -65504.f), 65504.f);      // saturate instead of overflowing to inf
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        const __half2 h2 = __floats2half2_rn(a, b);
+        hw = *reinterpret_cast<const uint32_t*>(&h2);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+        lw = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+}
+__device__ __forceinline__ float2 join2(uint32_t hw, uint32_t lw, int fmt) {
+    if (fmt == 0) return make_float2(bf16lo(hw) + bf16lo(lw), bf16hi(hw) + bf16hi(lw));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lw));
+    return make_float2(h.x + l.x, h.y + l.y);
+}
+__device__ __forceinline__ void split1(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+    if (fmt == 0) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    } else {
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(v);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    }
+}
 
 }  // namespace
 
@@ -518,10 +557,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                     const uint32_t ll[8] = {R[2].x, R[2].y, R[2].z, R[2].w, R[3].x, R[3].y, R[3].z, R[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float r0 = bf16lo(hh[i]) + bf16lo(ll[i]);
-                        const float r1 = bf16hi(hh[i]) + bf16hi(ll[i]);
-                        v[2 * i] += fminf(r0, r0 * p.res_unslope);       // undo the stored leaky relu (1/slope >= 1)
-                        v[2 * i + 1] += fminf(r1, r1 * p.res_unslope);
+                        const float2 r = join2(hh[i], ll[i], p.fmt);
+                        v[2 * i] += fminf(r.x, r.x * p.res_unslope);       // undo the stored leaky relu (1/slope >= 1)
+                        v[2 * i + 1] += fminf(r.y, r.y * p.res_unslope);
                     }
                 }
                 if (ACC) {
@@ -529,8 +567,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                     const uint32_t ll[8] = {A[2].x, A[2].y, A[2].z, A[2].w, A[3].x, A[3].y, A[3].z, A[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        v[2 * i] = (bf16lo(hh[i]) + bf16lo(ll[i])) + v[2 * i];
-                        v[2 * i + 1] = (bf16hi(hh[i]) + bf16hi(ll[i])) + v[2 * i + 1];
+                        const float2 r = join2(hh[i], ll[i], p.fmt);
+                        v[2 * i] = r.x + v[2 * i];
+                        v[2 * i + 1] = r.y + v[2 * i + 1];
+                    }
+                }
+                if (p.res_f32) {      // fp32 residual stream [B][Lout][out_C] (TTE)
+                    const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + (off - (size_t)co) / 2 + co);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 rv = __ldg(rp + i);
+                        v[4 * i] += rv.x; v[4 * i + 1] += rv.y; v[4 * i + 2] += rv.z; v[4 * i + 3] += rv.w;
                     }
                 }
                 const float sc = live ? p.scale : 0.f;      // rows past the valid length are written as zeros
@@ -546,12 +593,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                 if (p.out && !(p.ablate & 2)) {
                     uint32_t hw[8], lw[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - bf16lo(hw[i]), v[2 * i + 1] - bf16hi(hw[i]));
-                        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
-                    }
+                    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], p.fmt, hw[i], lw[i]);
                     __nv_bfloat16* oh = p.out + off;
                     __nv_bfloat16* ol = oh + p.out_C;
                     st_global_v4(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]));
@@ -614,7 +656,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 3-D map over split-bf16 activations [B][L][2C]: dims (2C, L, B), box (box_c, rows, 1), 128B / 64B swizzle, zero OOB fill
-static int make_tmap_act(CUtensorMap* map, const __nv_bfloat16* base, int C, int L, int B, int box_c, int rows, bool sw128) {
+static int make_tmap_act(CUtensorMap* map, const __nv_bfloat16* base, int C, int L, int B, int box_c, int rows, bool sw128) {   // 16-bit elements; the copy is type-agnostic
     EncodeTiledFn fn = encode_fn();
     PB_REQUIRE(fn != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     PB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, PB_ERR_INVALID, "tc_conv: activation base must be 16-byte aligned");
@@ -639,7 +681,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     PB_REQUIRE(a.out_C > 0 && a.out_C % 16 == 0 && a.N == a.U * a.out_C, PB_ERR_INVALID, "tc_conv: N=%d != U=%d * out_C=%d", a.N, a.U, a.out_C);
     PB_REQUIRE((a.K - 1) * a.D % 2 == 0, PB_ERR_INVALID, "tc_conv: (K-1)*D must be even ('same' padding)");
     TcParams p{};
-    p.w = a.w; p.bias = a.bias; p.res = a.res; p.accin = a.accin; p.out = a.out; p.out_f32 = a.out_f32; p.lens = a.lens;
+    p.w = a.w; p.bias = a.bias; p.res = a.res; p.res_f32 = a.res_f32; p.accin = a.accin; p.out = a.out; p.out_f32 = a.out_f32; p.lens = a.lens;
     p.len_mul = a.len_mul;
     p.B = a.B; p.L = a.L; p.Cin = a.Cin; p.N = a.N; p.NT = NT; p.n_tiles_n = a.N / NT; p.out_C = a.out_C; p.U = a.U;
     p.K = a.K; p.D = a.D; p.pad = (a.K - 1) * a.D / 2;
@@ -717,9 +759,11 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     PB_REQUIRE(total < (1LL << 31), PB_ERR_INVALID, "tc_conv: too many tiles");
     p.total_tiles = (int)total;
     p.post_slope = a.post_slope; p.scale = a.scale; p.res_unslope = a.res_unslope; p.tanh_out = a.tanh_out;
-    // instruction descriptor: D f32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    p.idesc_stack = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    // instruction descriptor: D f32 (bit 4), A / B format at bits 7 / 10 (0 = f16, 1 = bf16), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t ab_fmt = a.fmt == 0 ? ((1u << 7) | (1u << 10)) : 0u;
+    p.idesc = (1u << 4) | ab_fmt | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    p.idesc_stack = (1u << 4) | ab_fmt | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    p.fmt = a.fmt;
     p.single_pass = a.single_pass;
     p.stack = (!a.single_pass && NT <= 128) ? 1 : 0;
     p.acc_cols = p.stack ? 2 * NT : NT;
@@ -784,11 +828,12 @@ struct PackDev {
     int Cin, N, K, NT, cin_t, ksteps, nchunks;
     // transposed conv: N = U*Cout, 3 taps; source tap index for (phase, tap) or -1
     int convtr, Cout, Kt, U;
+    int fmt;
 };
 
 __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
     const int64_t total = (int64_t)d.Cin * d.N * d.K;
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(packed);
+    uint16_t* out = reinterpret_cast<uint16_t*>(packed);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         // decode destination-major index: [nt][c][j][ks][kc][ng][r][e]  (per plane)
         int64_t r_ = i;
@@ -814,9 +859,9 @@ __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
             const int jj = r0 + m * d.U;
             v = (m >= 0 && jj < d.Kt) ? d.w[((int64_t)ci * d.Cout + co) * d.Kt + jj] : 0.f;
         }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        // block base (in bf16 elements): block index * (2 planes * ksteps * NT * 16); inside a k-step the K half is outermost,
+        uint16_t hi, lo;
+        split1(v, d.fmt, hi, lo);
+        // block base (in 16-bit elements): block index * (2 planes * ksteps * NT * 16); inside a k-step the K half is outermost,
         // then the plane, so that rows [0, NT) = hi and [NT, 2NT) = lo of ONE 2NT-row operand with LBO = 2*NT*16 bytes
         const int64_t blk = ((int64_t)(nt * d.nchunks + c) * d.K + j) * (2LL * d.ksteps * d.NT * 16);
         const int64_t kstep = blk + (int64_t)ks * (2LL * d.NT * 16);
@@ -840,13 +885,14 @@ static int pack_common(PackDev d, uint8_t* packed, cudaStream_t st) {
     return PB_OK;
 }
 
-int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st) {
+int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt) {
     PackDev d{};
+    d.fmt = fmt;
     d.w = w; d.s_n = (int64_t)Cin * K; d.s_ci = K; d.s_j = 1; d.Cin = Cin; d.N = Cout; d.K = K;
     return pack_common(d, packed, st);
 }
 
-int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st) {
+int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st, int fmt) {
     PB_REQUIRE((Kt - U) % 2 == 0 && Kt <= 3 * U, PB_ERR_INVALID, "tc_pack_convtr: kernel %d / stride %d unsupported", Kt, U);
     // every phase must only reach x[q-1], x[q], x[q+1]
     for (int ph = 0; ph < U; ++ph) {
@@ -855,6 +901,7 @@ int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, in
             PB_REQUIRE(a - m >= -1 && a - m <= 1, PB_ERR_INVALID, "tc_pack_convtr: kernel %d / stride %d needs more than 3 input taps", Kt, U);
     }
     PackDev d{};
+    d.fmt = fmt;
     d.w = w; d.Cin = Cin; d.N = U * Cout; d.K = 3; d.convtr = 1; d.Cout = Cout; d.Kt = Kt; d.U = U;
     return pack_common(d, packed, st);
 }

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "pb_runtime.cuh"
+#include "pb_tc.cuh"
 #include "pb_tte.cuh"
 
 using namespace pb;
@@ -55,6 +56,12 @@ extern "C" int pb_tte_create(const pb_tte_cfg* cfg, pb_tte** out) {
     PB_REQUIRE(cfg->conv_k1 % 2 == 1 && cfg->conv_k2 % 2 == 1, PB_ERR_INVALID, "pb_tte_create: FFN kernel sizes must be odd");
     PB_REQUIRE(cfg->dp_n_filter == 256 && cfg->dp_kernel == 3, PB_ERR_INVALID, "pb_tte_create: duration predictor must be 256 filters, kernel 3");
     PB_REQUIRE(cfg->conv_n_filter % 4 == 0 && cfg->n_codes > 0 && cfg->max_len > 1 && cfg->src_vocab_size > 0, PB_ERR_INVALID, "pb_tte_create: bad sizes");
+    PB_REQUIRE(cfg->gemm_mode == 0 || cfg->gemm_mode == 1, PB_ERR_INVALID, "pb_tte_create: gemm_mode=%d (0 = fp32 SIMT, 1 = tcgen05 split-fp16)", cfg->gemm_mode);
+    if (cfg->gemm_mode == 1) {
+        PB_REQUIRE(cfg->fold_projections, PB_ERR_INVALID, "pb_tte_create: gemm_mode 1 needs fold_projections = 1 (the unfolded reference mode runs on the fp32 SIMT path)");
+        PB_REQUIRE(cfg->conv_n_filter % 256 == 0 && cfg->conv_k2 == 1 && (cfg->conv_k1 - 1) <= 128, PB_ERR_INVALID,
+                   "pb_tte_create: gemm_mode 1 needs conv_n_filter %% 256 == 0 and conv_kernel_sizes [k, 1]");
+    }
     pb_tte* h = new pb_tte();
     h->cfg = *cfg;
     cudaGetDevice(&h->device);
@@ -94,10 +101,22 @@ extern "C" int pb_tte_create(const pb_tte_cfg* cfg, pb_tte** out) {
             add_slot(h, p + ".attention.wo_eff", {D, D}, false);
             add_slot(h, p + ".convlayer.conv1.packed", {F, cfg->conv_k1 * D}, false);
             add_slot(h, p + ".convlayer.conv2.packed", {D, cfg->conv_k2 * F}, false);
+            if (cfg->gemm_mode == 1) {   // tcgen05 operands (split-fp16, packed by tc_pack_conv_weight): same element count in bytes/4
+                add_slot(h, p + ".attention.qkv_eff.tc", {3 * D, D}, false);
+                add_slot(h, p + ".attention.wo_eff.tc", {D, D}, false);
+                add_slot(h, p + ".convlayer.conv1.tc", {F, cfg->conv_k1 * D}, false);
+                add_slot(h, p + ".convlayer.conv2.tc", {D, cfg->conv_k2 * F}, false);
+            }
         }
     }
     add_slot(h, "head.weight", {cfg->n_codes, D}, true);
     add_slot(h, "head.bias", {cfg->n_codes}, true);
+    if (cfg->gemm_mode == 1) {
+        const int np = (int)round_up(cfg->n_codes, 256);
+        add_slot(h, "head.weight.pad", {np, D}, false);      // zero rows past n_codes
+        add_slot(h, "head.weight.tc", {np, D}, false);
+        add_slot(h, "head.bias.pad", {np}, false);
+    }
     int st = h->arena.reserve(h->arena_bytes);
     if (st != PB_OK) { delete h; return st; }
     *out = h;
@@ -165,11 +184,26 @@ extern "C" int pb_tte_finalize(pb_tte* h, void* stream) {
             }
             PB_TRY(launch_permute_conv_weight(h->P(p + ".convlayer.conv1.weight"), h->P(p + ".convlayer.conv1.packed"), F, D, c.conv_k1, st));
             PB_TRY(launch_permute_conv_weight(h->P(p + ".convlayer.conv2.weight"), h->P(p + ".convlayer.conv2.packed"), D, F, c.conv_k2, st));
+            if (c.gemm_mode == 1) {
+                auto TC = [&](const std::string& k) { return reinterpret_cast<uint8_t*>(h->P(k)); };
+                PB_TRY(tc_pack_conv_weight(h->P(p + ".attention.qkv_eff"), TC(p + ".attention.qkv_eff.tc"), 3 * D, D, 1, st, 1));
+                PB_TRY(tc_pack_conv_weight(h->P(p + ".attention.wo_eff"), TC(p + ".attention.wo_eff.tc"), D, D, 1, st, 1));
+                PB_TRY(tc_pack_conv_weight(h->P(p + ".convlayer.conv1.weight"), TC(p + ".convlayer.conv1.tc"), F, D, c.conv_k1, st, 1));
+                PB_TRY(tc_pack_conv_weight(h->P(p + ".convlayer.conv2.weight"), TC(p + ".convlayer.conv2.tc"), D, F, c.conv_k2, st, 1));
+            }
         }
     }
     if (h->slots["duration_predictor.layers.0.conv.weight"].loaded && h->slots["duration_predictor.layers.4.conv.weight"].loaded) {
         PB_TRY(launch_permute_conv_weight(h->P("duration_predictor.layers.0.conv.weight"), h->P("duration_predictor.layers.0.conv.packed"), 256, D, 3, st));
         PB_TRY(launch_permute_conv_weight(h->P("duration_predictor.layers.4.conv.weight"), h->P("duration_predictor.layers.4.conv.packed"), 256, 256, 3, st));
+    }
+    if (c.gemm_mode == 1 && h->slots["head.weight"].loaded && h->slots["head.bias"].loaded) {
+        const int np = (int)round_up(c.n_codes, 256);
+        PB_CUDA(cudaMemsetAsync(h->P("head.weight.pad"), 0, (size_t)np * D * sizeof(float), st));
+        PB_CUDA(cudaMemcpyAsync(h->P("head.weight.pad"), h->P("head.weight"), (size_t)c.n_codes * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PB_CUDA(cudaMemsetAsync(h->P("head.bias.pad"), 0, (size_t)np * sizeof(float), st));
+        PB_CUDA(cudaMemcpyAsync(h->P("head.bias.pad"), h->P("head.bias"), (size_t)c.n_codes * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PB_TRY(tc_pack_conv_weight(h->P("head.weight.pad"), reinterpret_cast<uint8_t*>(h->P("head.weight.tc")), np, D, 1, st, 1));
     }
     PB_CUDA(cudaStreamSynchronize(st));
     h->finalized = true;
@@ -193,8 +227,9 @@ extern "C" int64_t pb_tte_last_launches(const pb_tte* h) { return h ? h->last_la
 // ---- one FFT block: y = FFTBlock(x)  (fft.py:94-100) ------------------------------------------------
 struct BlockWork {
     float *xn, *qkv, *qkv1, *S, *o, *y1, *hbuf, *f;
+    uint16_t *xn_s, *o_s, *f_s;     // gemm_mode 1: split-fp16 GEMM operands [M][2C]
 };
-static size_t block_work_plan(Carver& cv, BlockWork& w, int B, int L, int D, int F, int H, bool unfolded) {
+static size_t block_work_plan(Carver& cv, BlockWork& w, int B, int L, int D, int F, int H, bool unfolded, bool tc = false) {
     const size_t M = (size_t)B * L;
     const size_t Lp = (size_t)round_up(L, 4);
     w.xn = cv.take<float>(M * D);
@@ -204,8 +239,66 @@ static size_t block_work_plan(Carver& cv, BlockWork& w, int B, int L, int D, int
     w.o = cv.take<float>(M * D);
     w.y1 = unfolded ? cv.take<float>(M * D) : nullptr;
     w.hbuf = cv.take<float>(M * D);
-    w.f = cv.take<float>(M * F);
+    w.f = tc ? nullptr : cv.take<float>(M * F);
+    w.xn_s = tc ? cv.take<uint16_t>(M * 2 * D) : nullptr;
+    w.o_s = tc ? cv.take<uint16_t>(M * 2 * D) : nullptr;
+    w.f_s = tc ? cv.take<uint16_t>(M * 2 * F) : nullptr;
     return cv.off;
+}
+
+// One GEMM / Conv1d of the TTE on the tensor-core kernel of the vocoder (tc_conv.cu): x split-fp16 [B][L][2*Cin] ->
+// out split-fp16 [B][L][2*N] and/or out_f32 [B][L][N];  acc = conv(x, w) + bias (+ res_f32), then ReLU when relu != 0.
+static int tte_tc_gemm(const uint16_t* x, const uint8_t* w, const float* bias, const float* res_f32, uint16_t* out, float* out_f32,
+                       int B, int L, int Cin, int N, int K, int relu, cudaStream_t st) {
+    TcConvArgs a;
+    a.x = reinterpret_cast<const __nv_bfloat16*>(x); a.w = w; a.bias = bias; a.res_f32 = res_f32;
+    a.out = reinterpret_cast<__nv_bfloat16*>(out); a.out_f32 = out_f32;
+    a.B = B; a.L = L; a.Cin = Cin; a.N = N; a.out_C = N; a.U = 1; a.K = K; a.D = 1;
+    a.post_slope = relu ? 0.f : 1.f;       // max(u, 0*u) = ReLU
+    a.fmt = 1;
+    return launch_tc_conv(a, st);
+}
+
+// FFTBlock.forward (fft.py:94-100) with the projections and the FFN convolutions on tcgen05 (split-fp16 operands, fp32
+// accumulation in TMEM, 3 passes per product); the residual stream, LayerNorm statistics and softmax stay fp32.
+static int run_fft_block_tc(pb_tte* h, const std::string& p, const float* x, const uint8_t* key_valid, int B, int L,
+                            const BlockWork& w, float* y, cudaStream_t st) {
+    const pb_tte_cfg& c = h->cfg;
+    const int D = c.d_model, F = c.conv_n_filter, H = c.n_head, dh = D / H;
+    const int M = B * L;
+    const int Lp = (int)round_up(L, 4);
+    auto TC = [&](const std::string& k) { return reinterpret_cast<const uint8_t*>(h->P(k)); };
+    PB_TRY(launch_layernorm_split(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn_s, M, D, st));
+    // q | k | v = LN(x) . Wqkv_eff^T   (rows flattened: a 1-tap GEMM has no sequence edges)
+    PB_TRY(tte_tc_gemm(w.xn_s, TC(p + ".attention.qkv_eff.tc"), nullptr, nullptr, nullptr, w.qkv, 1, M, D, 3 * D, 1, 0, st));
+    const float* qkv = w.qkv;
+    {   // S = Q.K^T per (batch, head)
+        GemmArgs g;
+        g.A = qkv; g.lda = 3 * D; g.sAb = (int64_t)L * 3 * D; g.sAh = dh;
+        g.B = qkv + D; g.ldb = 3 * D; g.sBb = (int64_t)L * 3 * D; g.sBh = dh;
+        g.C = w.S; g.ldc = Lp; g.sCb = (int64_t)H * L * Lp; g.sCh = (int64_t)L * Lp;
+        g.M = L; g.N = L; g.K = dh; g.nbatch = B * H; g.H = H;
+        PB_TRY(launch_sgemm(g, st));
+    }
+    PB_TRY(launch_softmax(w.S, key_valid, B * H, H, L, Lp, sqrtf(1.0f / (float)dh), st));
+    {   // O = P.V
+        GemmArgs g;
+        g.A = w.S; g.lda = Lp; g.sAb = (int64_t)H * L * Lp; g.sAh = (int64_t)L * Lp;
+        g.B = qkv + 2 * D; g.ldb = 3 * D; g.b_kn = 1; g.sBb = (int64_t)L * 3 * D; g.sBh = dh;
+        g.C = w.o; g.ldc = D; g.sCb = (int64_t)L * D; g.sCh = dh;
+        g.M = L; g.N = dh; g.K = L; g.nbatch = B * H; g.H = H;
+        PB_TRY(launch_sgemm(g, st));
+    }
+    PB_TRY(launch_rows_to_split(w.o, D, w.o_s, M, D, st));
+    // h = x + attn . Wo_eff^T
+    PB_TRY(tte_tc_gemm(w.o_s, TC(p + ".attention.wo_eff.tc"), nullptr, x, nullptr, w.hbuf, 1, M, D, D, 1, 0, st));
+    PB_TRY(launch_layernorm_split(w.hbuf, h->P(p + ".conv_norm.weight"), h->P(p + ".conv_norm.bias"), w.xn_s, M, D, st));
+    // f = relu(conv1(LN(h)))  - per item ('same' zero padding at each sequence's own ends, fft.py:65-70)
+    PB_TRY(tte_tc_gemm(w.xn_s, TC(p + ".convlayer.conv1.tc"), h->P(p + ".convlayer.conv1.bias"), nullptr, w.f_s, nullptr, B, L, D, F,
+                       c.conv_k1, 1, st));
+    // y = h + conv2(f)
+    PB_TRY(tte_tc_gemm(w.f_s, TC(p + ".convlayer.conv2.tc"), h->P(p + ".convlayer.conv2.bias"), w.hbuf, nullptr, y, 1, M, F, D, 1, 0, st));
+    return PB_OK;
 }
 
 static int run_fft_block(pb_tte* h, const std::string& p, const float* x, const uint8_t* key_valid, int B, int L,
@@ -215,6 +308,7 @@ static int run_fft_block(pb_tte* h, const std::string& p, const float* x, const 
     const int M = B * L;
     const int Lp = (int)round_up(L, 4);
     const bool unfolded = !c.fold_projections;
+    if (c.gemm_mode == 1) return run_fft_block_tc(h, p, x, key_valid, B, L, w, y, st);
     PB_TRY(launch_layernorm(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn, M, D, st));
     const float* qkv = w.qkv;
     {
@@ -318,11 +412,11 @@ extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* sr
     {
         Carver plan(nullptr);
         plan.take<float>((size_t)M * D); plan.take<float>((size_t)M * D);
-        block_work_plan(plan, w, B, S, D, F, H, !c.fold_projections);
+        block_work_plan(plan, w, B, S, D, F, H, !c.fold_projections, c.gemm_mode == 1);
         PB_TRY(h->work.reserve(plan.off));
         Carver cv(h->work.ptr);
         xa = cv.take<float>((size_t)M * D); xb = cv.take<float>((size_t)M * D);
-        block_work_plan(cv, w, B, S, D, F, H, !c.fold_projections);
+        block_work_plan(cv, w, B, S, D, F, H, !c.fold_projections, c.gemm_mode == 1);
     }
     PB_TRY(launch_embed_pos(phones, h->P("tok_emb.weight"), h->P("pos_emb.pe") + (size_t)S * D, c.src_vocab_size, M, D, xa, h->err_flag, st));
     float* cur = xa;
@@ -387,17 +481,19 @@ extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, float* 
     PB_REQUIRE(M64 < (1LL << 30), PB_ERR_INVALID, "pb_tte_decode: batch too large");
     const int M = (int)M64;
     BlockWork w;
-    float *xa, *xb, *lg; uint8_t* mask;
+    float *xa, *xb, *lg = nullptr, *lgp = nullptr; uint8_t* mask;
     {
         Carver plan(nullptr);
         plan.take<float>((size_t)M * D); plan.take<float>((size_t)M * D); plan.take<uint8_t>(M);
-        if (!logits) plan.take<float>((size_t)M * c.n_codes);
-        block_work_plan(plan, w, B, T, D, F, H, !c.fold_projections);
+        if (c.gemm_mode == 1) plan.take<float>((size_t)M * round_up(c.n_codes, 256));
+        else if (!logits) plan.take<float>((size_t)M * c.n_codes);
+        block_work_plan(plan, w, B, T, D, F, H, !c.fold_projections, c.gemm_mode == 1);
         PB_TRY(h->work.reserve(plan.off));
         Carver cv(h->work.ptr);
         xa = cv.take<float>((size_t)M * D); xb = cv.take<float>((size_t)M * D); mask = cv.take<uint8_t>(M);
-        lg = logits ? logits : cv.take<float>((size_t)M * c.n_codes);
-        block_work_plan(cv, w, B, T, D, F, H, !c.fold_projections);
+        if (c.gemm_mode == 1) { lgp = cv.take<float>((size_t)M * round_up(c.n_codes, 256)); lg = nullptr; }
+        else lg = logits ? logits : cv.take<float>((size_t)M * c.n_codes);
+        block_work_plan(cv, w, B, T, D, F, H, !c.fold_projections, c.gemm_mode == 1);
     }
     uint8_t* mk = tgt_mask ? tgt_mask : mask;
     PB_TRY(launch_length_regulate(h->enc_out, h->cum, h->P("pos_emb.pe") + (size_t)T * D, B, S, D, T, xa, mk, st));
@@ -406,13 +502,22 @@ extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, float* 
         PB_TRY(run_fft_block(h, layer_prefix(1, i), cur, mk, B, T, w, nxt, st));
         std::swap(cur, nxt);
     }
-    {
+    if (c.gemm_mode == 1) {
+        // head on tcgen05: N padded to a multiple of 256 (zero rows), logits land in a padded scratch
+        const int np = (int)round_up(c.n_codes, 256);
+        PB_TRY(launch_rows_to_split(cur, D, w.xn_s, M, D, st));
+        PB_TRY(tte_tc_gemm(w.xn_s, reinterpret_cast<const uint8_t*>(h->P("head.weight.tc")), h->P("head.bias.pad"), nullptr, nullptr, lgp,
+                           1, M, D, np, 1, 0, st));
+        if (ids) PB_TRY(launch_argmax(lgp, M, c.n_codes, np, ids, st));
+        if (logits) PB_CUDA(cudaMemcpy2DAsync(logits, (size_t)c.n_codes * sizeof(float), lgp, (size_t)np * sizeof(float),
+                                              (size_t)c.n_codes * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
+    } else {
         GemmArgs g;
         g.A = cur; g.lda = D; g.B = h->P("head.weight"); g.ldb = D; g.C = lg; g.ldc = c.n_codes; g.bias = h->P("head.bias");
         g.M = M; g.N = c.n_codes; g.K = D;
         PB_TRY(launch_sgemm(g, st));
+        if (ids) PB_TRY(launch_argmax(lg, M, c.n_codes, c.n_codes, ids, st));
     }
-    if (ids) PB_TRY(launch_argmax(lg, M, c.n_codes, c.n_codes, ids, st));
     h->last_launches = g_launch_count - launches0;
     return PB_OK;
 }
@@ -425,7 +530,22 @@ extern "C" int pb_layernorm(const float* x, const float* gamma, const float* bet
 
 extern "C" int pb_linear(const float* x, const float* w, const float* bias, float* y, int32_t M, int32_t N, int32_t K, int32_t mode, void* stream) {
     PB_REQUIRE(x && w && y, PB_ERR_INVALID, "pb_linear: null argument");
-    PB_REQUIRE(mode == 0, PB_ERR_INVALID, "pb_linear: gemm mode %d is not built", mode);
+    PB_REQUIRE(mode == 0 || mode == 1, PB_ERR_INVALID, "pb_linear: gemm mode %d is not built", mode);
+    if (mode == 1) {
+        // tcgen05 split-fp16 GEMM (unit-test entry: operands are converted / packed on the fly)
+        PB_REQUIRE(M > 0 && (K == 16 || K == 32 || K % 64 == 0) && tc_n_tile(N) > 0, PB_ERR_INVALID,
+                   "pb_linear(mode 1): K=%d must be 16, 32 or a multiple of 64 and N=%d a multiple of 16 (<= 256, or a multiple of 128)", K, N);
+        cudaStream_t st = (cudaStream_t)stream;
+        uint16_t* xs = nullptr; uint8_t* wp = nullptr;
+        PB_CUDA(cudaMalloc(&xs, (size_t)M * 2 * K * sizeof(uint16_t)));
+        if (cudaMalloc(&wp, tc_packed_weight_bytes(K, N, 1)) != cudaSuccess) { cudaFree(xs); set_error("pb_linear: out of memory"); return PB_ERR_CUDA; }
+        int rc = launch_rows_to_split(x, K, xs, M, K, st);
+        if (rc == PB_OK) rc = tc_pack_conv_weight(w, wp, N, K, 1, st, 1);
+        if (rc == PB_OK) rc = tte_tc_gemm(xs, wp, bias, nullptr, nullptr, y, 1, M, K, N, 1, 0, st);
+        cudaStreamSynchronize(st);
+        cudaFree(xs); cudaFree(wp);
+        return rc;
+    }
     GemmArgs g;
     g.A = x; g.lda = K; g.B = w; g.ldb = K; g.C = y; g.ldc = N; g.bias = bias; g.M = M; g.N = N; g.K = K;
     return launch_sgemm(g, (cudaStream_t)stream);
@@ -440,10 +560,10 @@ extern "C" int pb_tte_fft_block(pb_tte* h, int32_t stack, int32_t layer, const f
     PB_REQUIRE(B > 0 && L > 0, PB_ERR_INVALID, "pb_tte_fft_block: bad shape");
     BlockWork w;
     Carver plan(nullptr);
-    block_work_plan(plan, w, B, L, c.d_model, c.conv_n_filter, c.n_head, !c.fold_projections);
+    block_work_plan(plan, w, B, L, c.d_model, c.conv_n_filter, c.n_head, !c.fold_projections, c.gemm_mode == 1);
     PB_TRY(h->work.reserve(plan.off));
     Carver cv(h->work.ptr);
-    block_work_plan(cv, w, B, L, c.d_model, c.conv_n_filter, c.n_head, !c.fold_projections);
+    block_work_plan(cv, w, B, L, c.d_model, c.conv_n_filter, c.n_head, !c.fold_projections, c.gemm_mode == 1);
     const int64_t launches0 = g_launch_count;
     int rc = run_fft_block(h, layer_prefix(stack, layer), x, key_valid, B, L, w, y, (cudaStream_t)stream);
     h->last_launches = g_launch_count - launches0;

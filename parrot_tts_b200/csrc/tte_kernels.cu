@@ -8,6 +8,8 @@
 //   proj + masked_fill + exp/round      modules/duration.py:45-48; parrot.py:82-86      -> duration_head_kernel
 //   length_regulator + mask             modules/duration.py:6-24; data.py:8-20          -> duration_scan / length_regulate kernels
 //   argmax                              modules/parrot.py:115                           -> argmax_kernel
+#include <cuda_fp16.h>
+
 #include "pb_tte.cuh"
 
 namespace pb {
@@ -288,6 +290,78 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
     PB_REQUIRE(D == 256, PB_ERR_INVALID, "layernorm: width %d unsupported (256 expected)", D);
     PB_REQUIRE(M > 0, PB_ERR_INVALID, "layernorm: empty input");
     layernorm_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, y, M);
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// ---- tensor-core path: rows in split-fp16 format [M][2C] = [hi(0..C-1) | lo(0..C-1)], value = hi + lo (pb_tc.cuh) --------
+__device__ __forceinline__ void split_h4(const float4 v, uint2& hi, uint2& lo) {
+    const float a = fminf(fmaxf(v.x, -65504.f), 65504.f), b = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    const float c = fminf(fmaxf(v.z, -65504.f), 65504.f), d = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(a - f0.x, b - f0.y), l1 = __floats2half2_rn(c - f1.x, d - f1.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+// LayerNorm(256) with the result written in split-fp16 rows (the A operand of the following tensor-core GEMM)
+__global__ void __launch_bounds__(256)
+layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       uint16_t* __restrict__ y, int M) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * 256);
+    const float4 v0 = src[lane], v1 = src[lane + 32];
+    float mean, rstd;
+    ln_row_256(v0, v1, mean, rstd);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    const float4 g0 = g4[lane], g1 = g4[lane + 32], c0 = b4[lane], c1 = b4[lane + 32];
+    const float4 o0 = make_float4((v0.x - mean) * rstd * g0.x + c0.x, (v0.y - mean) * rstd * g0.y + c0.y,
+                                  (v0.z - mean) * rstd * g0.z + c0.z, (v0.w - mean) * rstd * g0.w + c0.w);
+    const float4 o1 = make_float4((v1.x - mean) * rstd * g1.x + c1.x, (v1.y - mean) * rstd * g1.y + c1.y,
+                                  (v1.z - mean) * rstd * g1.z + c1.z, (v1.w - mean) * rstd * g1.w + c1.w);
+    uint2 h0, l0, h1, l1;
+    split_h4(o0, h0, l0);
+    split_h4(o1, h1, l1);
+    uint2* dst = reinterpret_cast<uint2*>(y + (size_t)row * 512);     // 4 halves = 8 bytes per lane
+    dst[lane] = h0; dst[lane + 32] = h1;                              // hi: channels 4*lane.., 128 + 4*lane..
+    dst[64 + lane] = l0; dst[96 + lane] = l1;                         // lo plane starts at element 256
+}
+
+int launch_layernorm_split(const float* x, const float* gamma, const float* beta, uint16_t* y, int M, int D, cudaStream_t st) {
+    PB_REQUIRE(D == 256, PB_ERR_INVALID, "layernorm: width %d unsupported (256 expected)", D);
+    PB_REQUIRE(M > 0, PB_ERR_INVALID, "layernorm: empty input");
+    layernorm_split_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, y, M);
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// x f32 [M][C] (row stride ldx) -> split-fp16 rows [M][2C]; C % 4 == 0
+__global__ void __launch_bounds__(256)
+rows_to_split_kernel(const float* __restrict__ x, int64_t ldx, uint16_t* __restrict__ y, int64_t M, int C) {
+    const int per_row = C / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M * per_row; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / per_row;
+        const int c4 = (int)(i - row * per_row);
+        const float4 v = *reinterpret_cast<const float4*>(x + row * ldx + 4 * c4);
+        uint2 h, l;
+        split_h4(v, h, l);
+        uint2* dst = reinterpret_cast<uint2*>(y + row * 2 * C);
+        dst[c4] = h;
+        dst[per_row + c4] = l;
+    }
+}
+
+int launch_rows_to_split(const float* x, int64_t ldx, uint16_t* y, int64_t M, int C, cudaStream_t st) {
+    PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0, PB_ERR_INVALID, "rows_to_split: width %d / stride %lld must be multiples of 4", C, (long long)ldx);
+    const int64_t n = M * (C / 4);
+    const int blocks = (int)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+    rows_to_split_kernel<<<blocks, 256, 0, st>>>(x, ldx, y, M, C);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;

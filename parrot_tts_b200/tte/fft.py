@@ -86,6 +86,7 @@ class FFTBlock(nn.Module):
         self.conv_norm = nn.LayerNorm(d_model)
         self._eng = TteEngine()
         self.fold_projections = True
+        self.gemm_mode = 0          # pb_tte_cfg.gemm_mode: 0 = fp32 SIMT, 1 = tcgen05 split-fp16
 
     def forward(self, x, key_padding_mask=None, attn_mask=None):
         """h = x + Attn(LN(x)); out = h + Conv(LN(h))  (reference fft.py:94-100).
@@ -98,7 +99,7 @@ class FFTBlock(nn.Module):
         dev = x.device
         cfg = dict(src_vocab_size=1, src_pad_idx=0, n_speaker=0, d_model=self.d_model, n_head=self.n_head, n_enc_layer=1,
                    n_dec_layer=0, conv_n_filter=self.n_filter, conv_k1=self.kernel_sizes[0], conv_k2=self.kernel_sizes[1],
-                   dp_n_filter=256, dp_kernel=3, n_codes=1, max_len=2, fold_projections=int(self.fold_projections), gemm_mode=0)
+                   dp_n_filter=256, dp_kernel=3, n_codes=1, max_len=2, fold_projections=int(self.fold_projections), gemm_mode=int(self.gemm_mode))
         tensors = {"encoder_layers.0." + k: v for k, v in self.state_dict(keep_vars=True).items()}
         hnd = self._eng.get(cfg, tensors, dev)
         B, L, _ = x.shape

@@ -53,6 +53,20 @@ def test_linear_kernel(M, N, K):
     assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), float((got - ref).abs().max())
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 256, 256), (130, 768, 256), (257, 1024, 256), (64, 256, 1024), (300, 112, 64), (129, 16, 32)])
+def test_linear_kernel_tensor_core(M, N, K):
+    """tcgen05 GEMM on split-fp16 operands (3 passes, fp32 accumulation): fp32-class accuracy."""
+    g = _gen(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = (x.double() @ w.double().t() + b.double()).float()
+    got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), mode=1).cpu()
+    ref32 = x @ w.t() + b
+    err, err32 = float((got - ref).abs().max()), float((ref32 - ref).abs().max())
+    assert err < 2e-5 and err < 20 * max(err32, 1e-7), (err, err32)
+
+
 def test_layernorm_kernel():
     g = _gen(1)
     x = torch.randn(37, 256, generator=g) * 3 + 1
@@ -83,9 +97,9 @@ def test_pos_emb_single_row_quirk():
         pe(torch.zeros(1, 64, 256, device=DEV))
 
 
-@pytest.mark.parametrize("fold", [True, False])
+@pytest.mark.parametrize("fold,mode", [(True, 0), (False, 0), (True, 1)])
 @pytest.mark.parametrize("B,L", [(1, 5), (2, 37), (3, 130)])
-def test_fft_block_matches_oracle(fold, B, L):
+def test_fft_block_matches_oracle(fold, mode, B, L):
     cfg = _cfg()
     sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=5)
     p = "decoder_layers.1"
@@ -93,6 +107,7 @@ def test_fft_block_matches_oracle(fold, B, L):
     blk.load_state_dict({k[len(p) + 1:]: v for k, v in sd.items() if k.startswith(p + ".")}, strict=True)
     blk = blk.eval().to(DEV)
     blk.fold_projections = fold
+    blk.gemm_mode = mode
     g = _gen(B * 100 + L)
     x = torch.randn(B, L, 256, generator=g)
     pad = torch.zeros(B, L, dtype=torch.bool)
@@ -121,10 +136,12 @@ def test_duration_predictor_matches_oracle():
     assert (got[1, 15:] == 0).all()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged"])
-def test_parrot_matches_reference_golden(golden_dir, name):
+def test_parrot_matches_reference_golden(golden_dir, name, mode):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     _, _, m = _parrot(seed=int(g["seed"]))
+    m.gemm_mode = mode
     batch = _to_dev({"phones": torch.from_numpy(g["phones"]), "src_mask": torch.from_numpy(g["src_mask"]),
                      "speaker": torch.from_numpy(g["speaker"])})
     logits, src_mask, tgt_mask, log_dur = m(batch, inference=True)
@@ -142,10 +159,11 @@ def test_parrot_matches_reference_golden(golden_dir, name):
     np.testing.assert_allclose(logits[:, ::stride].cpu().numpy(), g["logits_rows"], rtol=0, atol=2e-3)
 
 
-@pytest.mark.parametrize("fold", [True, False])
-def test_parrot_vs_oracle_random_batch(fold):
+@pytest.mark.parametrize("fold,mode", [(True, 0), (False, 0), (True, 1)])
+def test_parrot_vs_oracle_random_batch(fold, mode):
     cfg, sd, m = _parrot(seed=21)
     m.fold_projections = fold
+    m.gemm_mode = mode
     g = _gen(8)
     phones = torch.randint(2, VOCAB, (4, 33), generator=g)
     phones[1, 20:] = 0
