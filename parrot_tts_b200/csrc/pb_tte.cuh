@@ -34,6 +34,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
 // tensor-core path: LayerNorm / plain rows written as split-fp16 rows [M][2C] = [hi | lo] (pb_tc.cuh, fmt 1)
 int launch_layernorm_split(const float* x, const float* gamma, const float* beta, uint16_t* y, int M, int D, cudaStream_t st);
 int launch_rows_to_split(const float* x, int64_t ldx, uint16_t* y, int64_t M, int C, cudaStream_t st);
+// fused attention on tcgen05 (attn_tc.cu): qkv split-fp16 rows [B*L][2*3D] ([q|k|v] hi, then lo), key_valid u8 [B][L] or null ->
+// out split-fp16 rows [B*L][2*D] (head h at columns h*128); head width must be 128
+int launch_attention_tc(const uint16_t* qkv, const uint8_t* key_valid, uint16_t* out, int B, int L, int H, int D, cudaStream_t st);
 // x[b,l,:] += row[idx[b],:]   (speaker embedding, parrot.py:98-99)
 int launch_add_indexed_row(float* x, const float* table, const int64_t* idx, int n_rows, int B, int L, int D, int* err_flag, cudaStream_t st);
 // in-place masked softmax over the last dim of S [Z, L, Lp]: softmax(scale * s + (valid ? 0 : -inf)), pad columns -> 0

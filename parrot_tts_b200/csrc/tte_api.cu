@@ -227,16 +227,17 @@ extern "C" int64_t pb_tte_last_launches(const pb_tte* h) { return h ? h->last_la
 // ---- one FFT block: y = FFTBlock(x)  (fft.py:94-100) ------------------------------------------------
 struct BlockWork {
     float *xn, *qkv, *qkv1, *S, *o, *y1, *hbuf, *f;
-    uint16_t *xn_s, *o_s, *f_s;     // gemm_mode 1: split-fp16 GEMM operands [M][2C]
+    uint16_t *xn_s, *o_s, *f_s, *qkv_s;     // gemm_mode 1: split-fp16 GEMM operands [M][2C]
 };
 static size_t block_work_plan(Carver& cv, BlockWork& w, int B, int L, int D, int F, int H, bool unfolded, bool tc = false) {
     const size_t M = (size_t)B * L;
     const size_t Lp = (size_t)round_up(L, 4);
     w.xn = cv.take<float>(M * D);
-    w.qkv = cv.take<float>(M * 3 * D);
+    w.qkv = tc ? nullptr : cv.take<float>(M * 3 * D);
     w.qkv1 = unfolded ? cv.take<float>(M * 3 * D) : nullptr;
-    w.S = cv.take<float>((size_t)B * H * L * Lp);
+    w.S = tc ? nullptr : cv.take<float>((size_t)B * H * L * Lp);      // the tensor-core attention never materialises the scores
     w.o = cv.take<float>(M * D);
+    w.qkv_s = tc ? cv.take<uint16_t>(M * 6 * D) : nullptr;
     w.y1 = unfolded ? cv.take<float>(M * D) : nullptr;
     w.hbuf = cv.take<float>(M * D);
     w.f = tc ? nullptr : cv.take<float>(M * F);
@@ -264,32 +265,14 @@ static int tte_tc_gemm(const uint16_t* x, const uint8_t* w, const float* bias, c
 static int run_fft_block_tc(pb_tte* h, const std::string& p, const float* x, const uint8_t* key_valid, int B, int L,
                             const BlockWork& w, float* y, cudaStream_t st) {
     const pb_tte_cfg& c = h->cfg;
-    const int D = c.d_model, F = c.conv_n_filter, H = c.n_head, dh = D / H;
+    const int D = c.d_model, F = c.conv_n_filter, H = c.n_head;
     const int M = B * L;
-    const int Lp = (int)round_up(L, 4);
     auto TC = [&](const std::string& k) { return reinterpret_cast<const uint8_t*>(h->P(k)); };
     PB_TRY(launch_layernorm_split(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn_s, M, D, st));
-    // q | k | v = LN(x) . Wqkv_eff^T   (rows flattened: a 1-tap GEMM has no sequence edges)
-    PB_TRY(tte_tc_gemm(w.xn_s, TC(p + ".attention.qkv_eff.tc"), nullptr, nullptr, nullptr, w.qkv, 1, M, D, 3 * D, 1, 0, st));
-    const float* qkv = w.qkv;
-    {   // S = Q.K^T per (batch, head)
-        GemmArgs g;
-        g.A = qkv; g.lda = 3 * D; g.sAb = (int64_t)L * 3 * D; g.sAh = dh;
-        g.B = qkv + D; g.ldb = 3 * D; g.sBb = (int64_t)L * 3 * D; g.sBh = dh;
-        g.C = w.S; g.ldc = Lp; g.sCb = (int64_t)H * L * Lp; g.sCh = (int64_t)L * Lp;
-        g.M = L; g.N = L; g.K = dh; g.nbatch = B * H; g.H = H;
-        PB_TRY(launch_sgemm(g, st));
-    }
-    PB_TRY(launch_softmax(w.S, key_valid, B * H, H, L, Lp, sqrtf(1.0f / (float)dh), st));
-    {   // O = P.V
-        GemmArgs g;
-        g.A = w.S; g.lda = Lp; g.sAb = (int64_t)H * L * Lp; g.sAh = (int64_t)L * Lp;
-        g.B = qkv + 2 * D; g.ldb = 3 * D; g.b_kn = 1; g.sBb = (int64_t)L * 3 * D; g.sBh = dh;
-        g.C = w.o; g.ldc = D; g.sCb = (int64_t)L * D; g.sCh = dh;
-        g.M = L; g.N = dh; g.K = L; g.nbatch = B * H; g.H = H;
-        PB_TRY(launch_sgemm(g, st));
-    }
-    PB_TRY(launch_rows_to_split(w.o, D, w.o_s, M, D, st));
+    // q | k | v = LN(x) . Wqkv_eff^T   (rows flattened: a 1-tap GEMM has no sequence edges), kept as split-fp16 rows
+    PB_TRY(tte_tc_gemm(w.xn_s, TC(p + ".attention.qkv_eff.tc"), nullptr, nullptr, w.qkv_s, nullptr, 1, M, D, 3 * D, 1, 0, st));
+    // softmax(q.k^T / sqrt(dh) + mask) . v per (batch, head), fused on tcgen05 (attn_tc.cu): scores stay in tensor memory
+    PB_TRY(launch_attention_tc(w.qkv_s, key_valid, w.o_s, B, L, H, D, st));
     // h = x + attn . Wo_eff^T
     PB_TRY(tte_tc_gemm(w.o_s, TC(p + ".attention.wo_eff.tc"), nullptr, x, nullptr, w.hbuf, 1, M, D, D, 1, 0, st));
     PB_TRY(launch_layernorm_split(w.hbuf, h->P(p + ".conv_norm.weight"), h->P(p + ".conv_norm.bias"), w.xn_s, M, D, st));

@@ -14,8 +14,10 @@ from .fft import FFTBlock, SinusoidalPosEmb
 
 
 class Parrot(nn.Module):
-    #: 0 = fp32 SIMT GEMMs (parity mode).  See pb_tte_cfg.gemm_mode.
-    gemm_mode = 0
+    #: pb_tte_cfg.gemm_mode: 1 = tcgen05 (projections, FFN convolutions, head and the fused attention on split-fp16 operands with
+    #: fp32 accumulation - fp32-class accuracy, bit-exact ids / durations on every golden vector; the default),
+    #: 0 = fp32 SIMT kernels (also used for the unfolded-projection reference mode).
+    gemm_mode = 1
     #: fold mha.in_proj . qkv and wo . out_proj at load (exact in real arithmetic; 6 GEMMs -> 2 per block)
     fold_projections = True
 
@@ -61,7 +63,7 @@ class Parrot(nn.Module):
                    n_dec_layer=len(self.decoder_layers), conv_n_filter=tr["conv_n_filter"], conv_k1=tr["conv_kernel_sizes"][0],
                    conv_k2=tr["conv_kernel_sizes"][1], dp_n_filter=dp["n_filter"], dp_kernel=dp["kernel_size"],
                    n_codes=self.n_codes, max_len=self.max_len, fold_projections=int(self.fold_projections),
-                   gemm_mode=int(self.gemm_mode))
+                   gemm_mode=int(self.gemm_mode) if self.fold_projections else 0)   # the unfolded reference mode is fp32 SIMT
         return self._eng.get(cfg, dict(self.state_dict(keep_vars=True)), device)
 
     def _encode(self, batch, dur_in=None):
