@@ -3,11 +3,12 @@
 //   softmax(q.k^T / sqrt(d_head) + key_padding_mask) . v        modules/fft.py:53-59; torch F.multi_head_attention_forward
 // (the projections around it are GEMMs of tc_conv.cu).  Scores are never written to HBM.
 //
-// One CTA = one (batch item, head, 128-query tile), 192 threads:
+// One CTA = one (batch item, head, 128-query tile), 320 threads:
 //   warp 0      producer: TMA loads of the Q tile and of 64-key K / V tiles (128-byte swizzle) from the split-fp16 qkv rows
 //   warp 1      MMA issuer + TMEM owner:  S = Q.K^T  (operands from shared memory),  O += P.V  (P from TENSOR MEMORY, V from
 //               shared memory as an MN-major operand - no transpose of V anywhere)
-//   warps 2..5  softmax / epilogue: thread = query row = TMEM lane
+//   warps 2..9  softmax / epilogue: thread = (query row = TMEM lane, half of a tile's keys); scores and probabilities are
+//               double-buffered in tensor memory so the tensor pipe and the exponentials overlap
 // Products are evaluated on split-fp16 operands (x = hi + lo): a.b ~ a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, with [b_hi; b_lo]
 // stacked along N so that a k-step costs two MMAs; accumulation is fp32 in TMEM.
 // Softmax is exact two-pass (pass 1: row maximum and denominator; pass 2: normalised probabilities -> P.V), which keeps the
@@ -21,20 +22,20 @@ namespace pb {
 
 namespace {
 
-constexpr int AT_THREADS = 192;
-constexpr int AT_MQ = 128;      // queries per CTA
-constexpr int AT_NK = 64;       // keys per tile
-constexpr int AT_DH = 128;      // head width (d_model 256 / 2 heads)
-constexpr int AT_STAGES = 2;
+constexpr int AT_THREADS = 320;  // producer warp, MMA warp, 8 softmax warps
+constexpr int AT_MQ = 128;       // queries per CTA
+constexpr int AT_NK = 64;        // keys per tile
+constexpr int AT_DH = 128;       // head width (d_model 256 / 2 heads)
+constexpr int AT_KST = 3;        // K ring (needed one tile ahead of V: S(t+1) is issued while P(t) is being computed)
+constexpr int AT_VST = 2;        // V ring
 constexpr uint32_t AT_Q_BYTES = 4 * AT_MQ * 128;          // [hi c0][hi c1][lo c0][lo c1], each 128 rows x 128 bytes
 constexpr uint32_t AT_K_BYTES = 4 * AT_NK * 128;          // per channel half: [hi rows][lo rows]
 constexpr uint32_t AT_V_BYTES = 4 * AT_NK * 128;          // [Vhi d0][Vhi d1][Vlo d0][Vlo d1], each 64 keys x 128 bytes
-constexpr uint32_t AT_STAGE_BYTES = AT_K_BYTES + AT_V_BYTES;
-constexpr uint32_t AT_SMEM = 1024 + AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 1024;
-// tensor memory columns
-constexpr uint32_t TM_S = 0;      // 128: [0,64) hi.hi + lo.hi, [64,128) hi.lo
-constexpr uint32_t TM_P = 128;    // 64:  [128,160) P_hi (64 keys, 2 per column), [160,192) P_lo
-constexpr uint32_t TM_O = 256;    // 256: [256,384) P.V_hi, [384,512) P_hi.V_lo
+constexpr uint32_t AT_SMEM = 2048 + AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES + 1024;   // = 232448, the 227 KB per-CTA limit
+// tensor memory columns (512): two score buffers, two probability buffers, the output accumulator
+constexpr uint32_t TM_S = 0;      // 2 x 128: [0,64) q_hi.k_hi + q_lo.k_hi, [64,128) q_hi.k_lo
+constexpr uint32_t TM_P = 256;    // 2 x 64:  [0,32) P_hi (64 keys, 2 per column), [32,64) P_lo
+constexpr uint32_t TM_O = 384;    // 128
 
 struct AttnParams {
     const uint8_t* key_valid;     // [B][L] 1 = attend, or null
@@ -56,16 +57,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                  // [AT_STAGES]
-    uint64_t* kv_empty = kv_full + AT_STAGES;      // [AT_STAGES]
-    uint64_t* s_full = kv_empty + AT_STAGES;
-    uint64_t* s_free = s_full + 1;
-    uint64_t* p_ready = s_free + 1;
-    uint64_t* p_free = p_ready + 1;
-    uint64_t* o_full = p_free + 1;
+    uint64_t* k_full = bars + 1;                   // [AT_KST]
+    uint64_t* k_empty = k_full + AT_KST;
+    uint64_t* v_full = k_empty + AT_KST;           // [AT_VST]
+    uint64_t* v_empty = v_full + AT_VST;
+    uint64_t* s_full = v_empty + AT_VST;           // [2] score buffers
+    uint64_t* s_free = s_full + 2;
+    uint64_t* p_ready = s_free + 2;                // [2] probability buffers
+    uint64_t* p_free = p_ready + 2;
+    uint64_t* o_full = p_free + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-    uint8_t* q_s = sm + 1024;
-    uint8_t* kv_s = q_s + AT_Q_BYTES;
+    float2* stat_x = reinterpret_cast<float2*>(sm + 512);     // [128] (m, l) of the upper key half, for the merge after pass 1
+    uint8_t* q_s = sm + 1024 + 1024;
+    uint8_t* k_s = q_s + AT_Q_BYTES;
+    uint8_t* v_s = k_s + AT_KST * AT_K_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -77,8 +82,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         prefetch_tmap(&qmap);
         prefetch_tmap(&kvmap);
         mbar_init(q_full, 1);
-        for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_ready, 4); mbar_init(p_free, 1); mbar_init(o_full, 1);
+        for (int s = 0; s < AT_KST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+        for (int s = 0; s < AT_VST; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 8); mbar_init(&p_ready[s], 8); mbar_init(&p_free[s], 1); }
+        mbar_init(o_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -96,36 +103,42 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
                     tma_load_3d(q_s + (pl * 2 + c) * (AT_MQ * 128), &qmap, pl * C3 + h * AT_DH + c * 64, q0, b, q_full);
         }
         __syncwarp();
-        uint32_t st = 0, ph = 0;
+        uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
         for (int pass = 0; pass < 2; ++pass) {
             for (int t = 0; t < n_tiles; ++t) {
-                mbar_wait(&kv_empty[st], ph ^ 1);
+                const int k0 = t * AT_NK;
+                mbar_wait(&k_empty[ks], kph ^ 1);
                 if (elect_one()) {
-                    uint8_t* ks = kv_s + st * AT_STAGE_BYTES;
-                    uint8_t* vs = ks + AT_K_BYTES;
-                    mbar_expect_tx(&kv_full[st], pass == 0 ? AT_K_BYTES : AT_STAGE_BYTES);
-                    const int k0 = t * AT_NK;
+                    uint8_t* dst = k_s + ks * AT_K_BYTES;
+                    mbar_expect_tx(&k_full[ks], AT_K_BYTES);
                     for (int c = 0; c < 2; ++c)
                         for (int pl = 0; pl < 2; ++pl)   // per channel half: hi rows then lo rows (one stacked 128-row operand)
-                            tma_load_3d(ks + (c * 2 + pl) * (AT_NK * 128), &kvmap, pl * C3 + p.D + h * AT_DH + c * 64, k0, b, &kv_full[st]);
-                    if (pass == 1)
-                        for (int pl = 0; pl < 2; ++pl)
-                            for (int c = 0; c < 2; ++c)  // [Vhi d0][Vhi d1][Vlo d0][Vlo d1]: four 64-wide MN groups
-                                tma_load_3d(vs + (pl * 2 + c) * (AT_NK * 128), &kvmap, pl * C3 + 2 * p.D + h * AT_DH + c * 64, k0, b, &kv_full[st]);
+                            tma_load_3d(dst + (c * 2 + pl) * (AT_NK * 128), &kvmap, pl * C3 + p.D + h * AT_DH + c * 64, k0, b, &k_full[ks]);
                 }
                 __syncwarp();
-                if (++st == AT_STAGES) { st = 0; ph ^= 1; }
+                if (++ks == AT_KST) { ks = 0; kph ^= 1; }
+                if (pass == 1) {
+                    mbar_wait(&v_empty[vs], vph ^ 1);
+                    if (elect_one()) {
+                        uint8_t* dst = v_s + vs * AT_V_BYTES;
+                        mbar_expect_tx(&v_full[vs], AT_V_BYTES);
+                        for (int pl = 0; pl < 2; ++pl)
+                            for (int c = 0; c < 2; ++c)  // [Vhi d0][Vhi d1][Vlo d0][Vlo d1]: 64-wide MN groups
+                                tma_load_3d(dst + (pl * 2 + c) * (AT_NK * 128), &kvmap, pl * C3 + 2 * p.D + h * AT_DH + c * 64, k0, b, &v_full[vs]);
+                    }
+                    __syncwarp();
+                    if (++vs == AT_VST) { vs = 0; vph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        // instruction descriptors: D f32, A/B f16; S: N = 128 (stacked) / 64, K-major B; O: N = 256 (stacked) / 128, MN-major B
+        // instruction descriptors: D f32, A/B f16; S: N = 128 (stacked) / 64, K-major B; O: N = 128, MN-major B
         const uint32_t id_base = (1u << 4) | ((uint32_t)(AT_MQ >> 4) << 24);
         const uint32_t id_s2 = id_base | ((uint32_t)((2 * AT_NK) >> 3) << 17);
         const uint32_t id_s1 = id_base | ((uint32_t)(AT_NK >> 3) << 17);
-        const uint32_t id_o2 = id_base | (1u << 16) | ((uint32_t)((2 * AT_DH) >> 3) << 17);
-        const uint32_t id_o1 = id_base | (1u << 16) | ((uint32_t)(AT_DH >> 3) << 17);
-        const uint32_t q_base = smem_u32(q_s), kv_base = smem_u32(kv_s);
+        const uint32_t id_o = id_base | (1u << 16) | ((uint32_t)(AT_DH >> 3) << 17);
+        const uint32_t q_base = smem_u32(q_s), k_base = smem_u32(k_s), v_base = smem_u32(v_s);
         // K-major, 128-byte swizzle: rows 128 bytes apart, 8-row groups 1024 bytes apart
         const uint64_t kdesc0 = smem_desc(0, 16, 1024, 2, 0);
         // MN-major, 128-byte swizzle: 64-element MN groups LBO = one 64-key box apart, 8-key groups 1024 bytes apart
@@ -133,182 +146,166 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         auto addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3fffu); };
         mbar_wait(q_full, 0);
         tc_fence_after();
-        uint32_t st = 0, ph = 0;
-        auto issue_qk = [&](uint32_t stage) {
-            const uint32_t kb = kv_base + stage * AT_STAGE_BYTES;
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t a_hi = addr(kdesc0, q_base + (0 * 2 + c) * (AT_MQ * 128) + ks * 32);
-                    const uint64_t a_lo = addr(kdesc0, q_base + (1 * 2 + c) * (AT_MQ * 128) + ks * 32);
-                    const uint64_t bd = addr(kdesc0, kb + c * (2 * AT_NK * 128) + ks * 32);
-                    umma_bf16(tmem + TM_S, a_hi, bd, id_s2, acc);     // q_hi . [k_hi; k_lo]
-                    umma_bf16(tmem + TM_S, a_lo, bd, id_s1, 1);       // q_lo . k_hi
-                    acc = 1;
-                }
-        };
-        uint32_t sfree_ph = 0, pready_ph = 0;
-        // ---- pass 1: scores only (row maximum / denominator)
-        for (int t = 0; t < n_tiles; ++t) {
-            mbar_wait(&kv_full[st], ph);
-            if (t > 0) { mbar_wait(s_free, sfree_ph); sfree_ph ^= 1; }
+        uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+        // S(g) -> score buffer g & 1 (g counts tiles over both passes); its previous use must have been read
+        auto qk_tile = [&](int g) {
+            const uint32_t sb = (uint32_t)g & 1u, n = (uint32_t)g >> 1;
+            mbar_wait(&k_full[ks], kph);
+            if (n > 0) mbar_wait(&s_free[sb], (n - 1) & 1u);
             tc_fence_after();
             if (elect_one()) {
-                issue_qk(st);
-                umma_commit(s_full);
-                umma_commit(&kv_empty[st]);
+                const uint32_t kb = k_base + ks * AT_K_BYTES;
+                const uint32_t d = tmem + TM_S + sb * 128u;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t a_hi = addr(kdesc0, q_base + (0 * 2 + c) * (AT_MQ * 128) + k4 * 32);
+                        const uint64_t a_lo = addr(kdesc0, q_base + (1 * 2 + c) * (AT_MQ * 128) + k4 * 32);
+                        const uint64_t bd = addr(kdesc0, kb + c * (2 * AT_NK * 128) + k4 * 32);
+                        umma_bf16(d, a_hi, bd, id_s2, acc);     // q_hi . [k_hi; k_lo]
+                        umma_bf16(d, a_lo, bd, id_s1, 1);       // q_lo . k_hi
+                        acc = 1;
+                    }
+                umma_commit(&s_full[sb]);
+                umma_commit(&k_empty[ks]);
             }
             __syncwarp();
-            if (++st == AT_STAGES) { st = 0; ph ^= 1; }
-        }
-        // ---- pass 2: S(t+1) is issued as soon as the softmax warps have read S(t); P(t).V(t) follows when P(t) is in TMEM
-        mbar_wait(&kv_full[st], ph);
-        mbar_wait(s_free, sfree_ph); sfree_ph ^= 1;         // last tile of pass 1 consumed
-        tc_fence_after();
-        if (elect_one()) { issue_qk(st); umma_commit(s_full); }
-        __syncwarp();
+            if (++ks == AT_KST) { ks = 0; kph ^= 1; }
+        };
+        // ---- pass 1: scores only (row maximum / denominator); the two score buffers keep the tensor pipe ahead of the softmax warps
+        for (int t = 0; t < n_tiles; ++t) qk_tile(t);
+        // ---- pass 2: S(t+1) is issued before P(t).V(t), so it runs while the softmax warps turn S(t) into P(t)
+        qk_tile(n_tiles);
         for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t cur = st;
-            uint32_t nst = st + 1, nph = ph;
-            if (nst == AT_STAGES) { nst = 0; nph ^= 1; }
-            if (t + 1 < n_tiles) {
-                mbar_wait(&kv_full[nst], nph);
-                mbar_wait(s_free, sfree_ph); sfree_ph ^= 1;
-                tc_fence_after();
-                if (elect_one()) { issue_qk(nst); umma_commit(s_full); }
-                __syncwarp();
-            }
-            mbar_wait(p_ready, pready_ph); pready_ph ^= 1;
+            if (t + 1 < n_tiles) qk_tile(n_tiles + t + 1);
+            const uint32_t pb = (uint32_t)t & 1u, n = (uint32_t)t >> 1;
+            mbar_wait(&v_full[vs], vph);
+            mbar_wait(&p_ready[pb], n & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t vb = kv_base + cur * AT_STAGE_BYTES + AT_K_BYTES;
+                const uint32_t vb = v_base + vs * AT_V_BYTES;
+                const uint32_t pa = tmem + TM_P + pb * 64u;
 #pragma unroll
-                for (int ks = 0; ks < AT_NK / 16; ++ks) {
-                    const uint64_t bd = addr(vdesc0, vb + ks * (16 * 128));
-                    umma_f16_ts(tmem + TM_O, tmem + TM_P + ks * 8, bd, id_o2, (t > 0 || ks > 0) ? 1u : 0u);   // p_hi . [v_hi; v_lo]
-                    umma_f16_ts(tmem + TM_O, tmem + TM_P + 32 + ks * 8, bd, id_o1, 1);                          // p_lo . v_hi
+                for (int k4 = 0; k4 < AT_NK / 16; ++k4) {
+                    const uint64_t b_hi = addr(vdesc0, vb + k4 * (16 * 128));
+                    const uint64_t b_lo = addr(vdesc0, vb + 2 * (AT_NK * 128) + k4 * (16 * 128));
+                    umma_f16_ts(tmem + TM_O, pa + k4 * 8, b_hi, id_o, (t > 0 || k4 > 0) ? 1u : 0u);   // p_hi . v_hi
+                    umma_f16_ts(tmem + TM_O, pa + 32 + k4 * 8, b_hi, id_o, 1);                        // p_lo . v_hi
+                    umma_f16_ts(tmem + TM_O, pa + k4 * 8, b_lo, id_o, 1);                             // p_hi . v_lo
                 }
-                umma_commit(&kv_empty[cur]);
-                umma_commit(p_free);
+                umma_commit(&v_empty[vs]);
+                umma_commit(&p_free[pb]);
                 if (t + 1 == n_tiles) umma_commit(o_full);
             }
             __syncwarp();
-            st = nst; ph = nph;
+            if (++vs == AT_VST) { vs = 0; vph ^= 1; }
         }
     } else {
-        // =========================== softmax / epilogue (thread = query row) ===========================
+        // =========================== softmax / epilogue ===========================
+        // thread = (query row, key half): two warps per TMEM lane quarter, each taking 32 of a tile's 64 keys
         const int q = warp & 3;                              // TMEM lane quarter of this warp
+        const int half = (warp - 2) >> 2;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int row = q * 32 + lane;
         const int qrow = q0 + row;
         const uint8_t* kval = p.key_valid ? p.key_valid + (size_t)b * p.L : nullptr;
         const float c2 = p.scale_log2e;
         float m = -INFINITY, l = 0.f;
-        uint32_t sfull_ph = 0, pfree_ph = 0;
-        // 64-bit validity mask of the tile's keys, identical in every lane
-        auto tile_mask = [&](int t, uint32_t& lo32, uint32_t& hi32) {
-            const int k0 = t * AT_NK;
-            const int ka = k0 + lane, kb2 = k0 + 32 + lane;
-            const bool va = ka < p.L && (!kval || kval[ka] != 0);
-            const bool vb = kb2 < p.L && (!kval || kval[kb2] != 0);
-            lo32 = __ballot_sync(0xffffffffu, va);
-            hi32 = __ballot_sync(0xffffffffu, vb);
+        // validity mask of this thread's 32 keys of tile t, identical in every lane
+        auto tile_mask = [&](int t) {
+            const int k = t * AT_NK + half * 32 + lane;
+            return __ballot_sync(0xffffffffu, k < p.L && (!kval || kval[k] != 0));
         };
-        // ---- pass 1
-        for (int t = 0; t < n_tiles; ++t) {
-            uint32_t mk[2];
-            tile_mask(t, mk[0], mk[1]);
-            mbar_wait(s_full, sfull_ph); sfull_ph ^= 1;
+        auto load_scores = [&](int g, float* s) {
+            const uint32_t sb = (uint32_t)g & 1u, n = (uint32_t)g >> 1;
+            mbar_wait(&s_full[sb], n & 1u);
             tc_fence_after();
-            float s[AT_NK];
+            uint32_t a[32], c[32];
+            const uint32_t base = tmem + lane_off + TM_S + sb * 128u + (uint32_t)half * 32u;
+            tmem_ld32_nowait(base, a);
+            tmem_ld32_nowait(base + AT_NK, c);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t a[32], c[32];
-                tmem_ld32_nowait(tmem + lane_off + TM_S + half * 32, a);
-                tmem_ld32_nowait(tmem + lane_off + TM_S + AT_NK + half * 32, c);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) s[half * 32 + i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
-            }
+            for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_free);
+            if (lane == 0) mbar_arrive(&s_free[sb]);         // the buffer may take the scores of tile g + 2
+        };
+        // ---- pass 1: running maximum and denominator over this thread's keys
+        for (int t = 0; t < n_tiles; ++t) {
+            const uint32_t mk = tile_mask(t);
+            float s[32];
+            load_scores(t, s);
             float tm = m;
 #pragma unroll
-            for (int i = 0; i < AT_NK; ++i)
-                if ((mk[i >> 5] >> (i & 31)) & 1u) tm = fmaxf(tm, s[i]);
+            for (int i = 0; i < 32; ++i)
+                if ((mk >> i) & 1u) tm = fmaxf(tm, s[i]);
             if (tm > -INFINITY) {
                 float sum = 0.f;
 #pragma unroll
-                for (int i = 0; i < AT_NK; ++i)
-                    if ((mk[i >> 5] >> (i & 31)) & 1u) sum += exp2f((s[i] - tm) * c2);
-                l = l * exp2f((m - tm) * c2) + sum;     // m = -inf on the first valid tile: exp2(-inf) = 0
+                for (int i = 0; i < 32; ++i)
+                    if ((mk >> i) & 1u) sum += exp2f((s[i] - tm) * c2);
+                l = l * exp2f((m - tm) * c2) + sum;     // m = -inf before the first valid key: exp2(-inf) = 0
                 m = tm;
             }
         }
+        // merge the two key halves of every row
+        if (half == 1) stat_x[row] = make_float2(m, l);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+            const float2 o = stat_x[row];
+            const float mm = fmaxf(m, o.x);
+            const float la = m > -INFINITY ? l * exp2f((m - mm) * c2) : 0.f;
+            const float lb = o.x > -INFINITY ? o.y * exp2f((o.x - mm) * c2) : 0.f;
+            m = mm; l = la + lb;
+            stat_x[row] = make_float2(m, l);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 1) { const float2 o = stat_x[row]; m = o.x; l = o.y; }
         const float inv_l = 1.0f / l;
-        // ---- pass 2
+        // ---- pass 2: normalised probabilities -> tensor memory (fp16 hi + lo)
         for (int t = 0; t < n_tiles; ++t) {
-            uint32_t mk[2];
-            tile_mask(t, mk[0], mk[1]);
-            mbar_wait(s_full, sfull_ph); sfull_ph ^= 1;
-            tc_fence_after();
-            float s[AT_NK];
+            const uint32_t mk = tile_mask(t);
+            float s[32];
+            load_scores(n_tiles + t, s);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t a[32], c[32];
-                tmem_ld32_nowait(tmem + lane_off + TM_S + half * 32, a);
-                tmem_ld32_nowait(tmem + lane_off + TM_S + AT_NK + half * 32, c);
-                tmem_ld_wait();
+            for (int i = 0; i < 32; ++i) s[i] = ((mk >> i) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f;
+            uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s[half * 32 + i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
+            for (int i = 0; i < 16; ++i) {
+                const float a = s[2 * i], c = s[2 * i + 1];
+                const __half2 hh = __floats2half2_rn(a, c);
+                const float2 hf = __half22float2(hh);
+                hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo[i] = pack_h2(a - hf.x, c - hf.y);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free);          // S may be overwritten by the next tile's Q.K^T
-#pragma unroll
-            for (int i = 0; i < AT_NK; ++i)
-                s[i] = ((mk[i >> 5] >> (i & 31)) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f;
-            // P(t-1) must have been consumed by its MMAs before it is overwritten
-            if (t > 0) { mbar_wait(p_free, pfree_ph); pfree_ph ^= 1; }
+            const uint32_t pb = (uint32_t)t & 1u, n = (uint32_t)t >> 1;
+            if (n > 0) mbar_wait(&p_free[pb], (n - 1) & 1u);   // P(t-2) consumed by its MMAs
             tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < AT_NK / 32; ++g) {
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a = s[g * 32 + 2 * i], c = s[g * 32 + 2 * i + 1];
-                    const __half2 hh = __floats2half2_rn(a, c);
-                    const float2 hf = __half22float2(hh);
-                    hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
-                    lo[i] = pack_h2(a - hf.x, c - hf.y);
-                }
-                tmem_st16(tmem + lane_off + TM_P + g * 16, hi);
-                tmem_st16(tmem + lane_off + TM_P + 32 + g * 16, lo);
-            }
+            const uint32_t pbase = tmem + lane_off + TM_P + pb * 64u + (uint32_t)half * 16u;
+            tmem_st16(pbase, hi);
+            tmem_st16(pbase + 32, lo);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
+            if (lane == 0) mbar_arrive(&p_ready[pb]);
         }
-        // ---- epilogue: O = P.V_hi + P_hi.V_lo -> split-fp16 row [hi(128) | lo(128)] of head h
+        // ---- epilogue: O -> split-fp16 row [hi(128) | lo(128)] of head h; each key-half group stores 64 of the 128 columns
         mbar_wait(o_full, 0);
         tc_fence_after();
         uint16_t* orow = p.out + ((size_t)b * p.L + qrow) * 2 * p.D + h * AT_DH;
 #pragma unroll 1
-        for (int g = 0; g < AT_DH / 32; ++g) {
-            uint32_t a[32], c[32];
+        for (int g = half * 2; g < half * 2 + 2; ++g) {
+            uint32_t a[32];
             tmem_ld32_nowait(tmem + lane_off + TM_O + g * 32, a);
-            tmem_ld32_nowait(tmem + lane_off + TM_O + AT_DH + g * 32, c);
             tmem_ld_wait();
             if (qrow < p.L) {
                 uint32_t hw[16], lw[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float x0 = __uint_as_float(a[2 * i]) + __uint_as_float(c[2 * i]);
-                    const float x1 = __uint_as_float(a[2 * i + 1]) + __uint_as_float(c[2 * i + 1]);
+                    const float x0 = __uint_as_float(a[2 * i]), x1 = __uint_as_float(a[2 * i + 1]);
                     const __half2 hh = __floats2half2_rn(x0, x1);
                     const float2 hf = __half22float2(hh);
                     hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
