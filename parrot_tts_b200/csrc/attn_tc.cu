@@ -22,7 +22,10 @@ namespace pb {
 
 namespace {
 
-constexpr int AT_THREADS = 320;  // producer warp, MMA warp, 8 softmax warps
+constexpr int AT_PARTS = 4;      // softmax warps per TMEM lane quarter: each takes 64 / AT_PARTS keys of a tile
+constexpr int AT_KP = 64 / AT_PARTS;
+constexpr int AT_SW = 4 * AT_PARTS;  // softmax warps
+constexpr int AT_THREADS = 64 + 32 * AT_SW;  // producer warp, MMA warp, softmax warps
 constexpr int AT_MQ = 128;       // queries per CTA
 constexpr int AT_NK = 64;        // keys per tile
 constexpr int AT_DH = 128;       // head width (d_model 256 / 2 heads)
@@ -67,8 +70,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
     uint64_t* p_free = p_ready + 2;
     uint64_t* o_full = p_free + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-    float2* stat_x = reinterpret_cast<float2*>(sm + 512);     // [128] (m, l) of the upper key half, for the merge after pass 1
-    uint8_t* q_s = sm + 1024 + 1024;
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(sm + 512);   // [n_tiles][2] validity bits of each tile's keys (L <= 4096)
+    float2* stat_x = reinterpret_cast<float2*>(sm + 1024);     // [128] (m, l) exchange buffer for the merge after pass 1
+    uint8_t* q_s = sm + 2048;
     uint8_t* k_s = q_s + AT_Q_BYTES;
     uint8_t* v_s = k_s + AT_KST * AT_K_BYTES;
 
@@ -84,7 +88,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         mbar_init(q_full, 1);
         for (int s = 0; s < AT_KST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
         for (int s = 0; s < AT_VST; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 8); mbar_init(&p_ready[s], 8); mbar_init(&p_free[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], AT_SW); mbar_init(&p_ready[s], AT_SW); mbar_init(&p_free[s], 1); }
         mbar_init(o_full, 1);
         fence_mbar_init();
     }
@@ -204,31 +208,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         }
     } else {
         // =========================== softmax / epilogue ===========================
-        // thread = (query row, key half): two warps per TMEM lane quarter, each taking 32 of a tile's 64 keys
+        // thread = (query row, key part): AT_PARTS warps per TMEM lane quarter, each taking AT_KP of a tile's 64 keys
         const int q = warp & 3;                              // TMEM lane quarter of this warp
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int row = q * 32 + lane;
         const int qrow = q0 + row;
         const uint8_t* kval = p.key_valid ? p.key_valid + (size_t)b * p.L : nullptr;
         const float c2 = p.scale_log2e;
         float m = -INFINITY, l = 0.f;
-        // validity mask of this thread's 32 keys of tile t, identical in every lane
-        auto tile_mask = [&](int t) {
-            const int k = t * AT_NK + half * 32 + lane;
-            return __ballot_sync(0xffffffffu, k < p.L && (!kval || kval[k] != 0));
+        // validity bits of every tile's keys, computed once (a global load per tile would sit in the critical path of each tile)
+        for (int t = warp - 2; t < n_tiles; t += AT_SW) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k = t * AT_NK + hh * 32 + lane;
+                const uint32_t bits = __ballot_sync(0xffffffffu, k < p.L && (!kval || kval[k] != 0));
+                if (lane == 0) kmask[2 * t + hh] = bits;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SW) : "memory");
+        auto tile_mask = [&](int t) {     // this thread's AT_KP keys of tile t
+            const uint32_t w = kmask[2 * t + (part * AT_KP) / 32];
+            return (w >> ((part * AT_KP) & 31)) & (AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u));
         };
         auto load_scores = [&](int g, float* s) {
             const uint32_t sb = (uint32_t)g & 1u, n = (uint32_t)g >> 1;
             mbar_wait(&s_full[sb], n & 1u);
             tc_fence_after();
-            uint32_t a[32], c[32];
-            const uint32_t base = tmem + lane_off + TM_S + sb * 128u + (uint32_t)half * 32u;
-            tmem_ld32_nowait(base, a);
-            tmem_ld32_nowait(base + AT_NK, c);
+            uint32_t a[AT_KP], c[AT_KP];
+            const uint32_t base = tmem + lane_off + TM_S + sb * 128u + (uint32_t)(part * AT_KP);
+            if (AT_KP == 32) { tmem_ld32_nowait(base, a); tmem_ld32_nowait(base + AT_NK, c); }
+            else { tmem_ld16_nowait(base, a); tmem_ld16_nowait(base + AT_NK, c); }
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
+            for (int i = 0; i < AT_KP; ++i) s[i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[sb]);         // the buffer may take the scores of tile g + 2
@@ -236,45 +249,50 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         // ---- pass 1: running maximum and denominator over this thread's keys
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
-            float s[32];
+            float s[AT_KP];
             load_scores(t, s);
             float tm = m;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < AT_KP; ++i)
                 if ((mk >> i) & 1u) tm = fmaxf(tm, s[i]);
             if (tm > -INFINITY) {
                 float sum = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
+                for (int i = 0; i < AT_KP; ++i)
                     if ((mk >> i) & 1u) sum += exp2f((s[i] - tm) * c2);
                 l = l * exp2f((m - tm) * c2) + sum;     // m = -inf before the first valid key: exp2(-inf) = 0
                 m = tm;
             }
         }
-        // merge the two key halves of every row
-        if (half == 1) stat_x[row] = make_float2(m, l);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0) {
-            const float2 o = stat_x[row];
-            const float mm = fmaxf(m, o.x);
-            const float la = m > -INFINITY ? l * exp2f((m - mm) * c2) : 0.f;
-            const float lb = o.x > -INFINITY ? o.y * exp2f((o.x - mm) * c2) : 0.f;
-            m = mm; l = la + lb;
-            stat_x[row] = make_float2(m, l);
+        // merge the key parts of every row through one 1 KB exchange buffer: parts 1.. hand their (m, l) to part 0 in turn
+#define AT_BAR() asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SW) : "memory")
+        for (int j = 1; j < AT_PARTS; ++j) {
+            if (part == j) stat_x[row] = make_float2(m, l);
+            AT_BAR();
+            if (part == 0) {
+                const float2 o = stat_x[row];
+                const float mm = fmaxf(m, o.x);
+                const float la = m > -INFINITY ? l * exp2f((m - mm) * c2) : 0.f;
+                const float lb = o.x > -INFINITY ? o.y * exp2f((o.x - mm) * c2) : 0.f;
+                m = mm; l = la + lb;
+            }
+            AT_BAR();
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 1) { const float2 o = stat_x[row]; m = o.x; l = o.y; }
+        if (part == 0) stat_x[row] = make_float2(m, l);
+        AT_BAR();
+        if (part != 0) { const float2 o = stat_x[row]; m = o.x; l = o.y; }
+#undef AT_BAR
         const float inv_l = 1.0f / l;
         // ---- pass 2: normalised probabilities -> tensor memory (fp16 hi + lo)
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
-            float s[32];
+            float s[AT_KP];
             load_scores(n_tiles + t, s);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = ((mk >> i) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f;
-            uint32_t hi[16], lo[16];
+            for (int i = 0; i < AT_KP; ++i) s[i] = ((mk >> i) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f;
+            uint32_t hi[AT_KP / 2], lo[AT_KP / 2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < AT_KP / 2; ++i) {
                 const float a = s[2 * i], c = s[2 * i + 1];
                 const __half2 hh = __floats2half2_rn(a, c);
                 const float2 hf = __half22float2(hh);
@@ -284,20 +302,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             const uint32_t pb = (uint32_t)t & 1u, n = (uint32_t)t >> 1;
             if (n > 0) mbar_wait(&p_free[pb], (n - 1) & 1u);   // P(t-2) consumed by its MMAs
             tc_fence_after();
-            const uint32_t pbase = tmem + lane_off + TM_P + pb * 64u + (uint32_t)half * 16u;
-            tmem_st16(pbase, hi);
-            tmem_st16(pbase + 32, lo);
+            const uint32_t pbase = tmem + lane_off + TM_P + pb * 64u + (uint32_t)(part * (AT_KP / 2));
+            if (AT_KP == 32) { tmem_st16(pbase, hi); tmem_st16(pbase + 32, lo); }
+            else { tmem_st8(pbase, hi); tmem_st8(pbase + 32, lo); }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[pb]);
         }
-        // ---- epilogue: O -> split-fp16 row [hi(128) | lo(128)] of head h; each key-half group stores 64 of the 128 columns
+        // ---- epilogue: O -> split-fp16 row [hi(128) | lo(128)] of head h; the parts share the 128 columns
         mbar_wait(o_full, 0);
         tc_fence_after();
         uint16_t* orow = p.out + ((size_t)b * p.L + qrow) * 2 * p.D + h * AT_DH;
 #pragma unroll 1
-        for (int g = half * 2; g < half * 2 + 2; ++g) {
+        for (int g = part * (4 / AT_PARTS); g < (part + 1) * (4 / AT_PARTS); ++g) {
             uint32_t a[32];
             tmem_ld32_nowait(tmem + lane_off + TM_O + g * 32, a);
             tmem_ld_wait();
@@ -357,6 +375,7 @@ int launch_attention_tc(const uint16_t* qkv, const uint8_t* key_valid, uint16_t*
     PB_REQUIRE(qkv && out && B > 0 && L > 0, PB_ERR_INVALID, "attention_tc: bad argument");
     PB_REQUIRE(H * AT_DH == D, PB_ERR_INVALID, "attention_tc: head width %d unsupported (128 expected)", H > 0 ? D / H : 0);
     PB_REQUIRE(B <= 65535 && H <= 65535, PB_ERR_INVALID, "attention_tc: batch too large");
+    PB_REQUIRE(L <= 4096, PB_ERR_INVALID, "attention_tc: L=%d exceeds the 4096 keys the mask table holds", L);
     CUtensorMap qmap, kvmap;
     PB_TRY(make_tmap_qkv(&qmap, qkv, D, L, B, AT_MQ));
     PB_TRY(make_tmap_qkv(&kvmap, qkv, D, L, B, AT_NK));
