@@ -280,6 +280,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         float* bias_w = reinterpret_cast<float*>(sm + p.smem_bias_off);
         for (int i = threadIdx.x; i < p.out_C; i += blockDim.x) bias_w[i] = p.bias ? p.bias[i] : 0.f;
     }
+    // programmatic dependent launch: the next kernel of the stream may become resident and run its prologue (barriers, TMEM,
+    // weights) while this grid drains; it touches activations only after its own griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -305,6 +308,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             }
             __syncwarp();
         }
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // activations are written by the previous kernel of the stream
         uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;      // ring slot + phase counters (no divisions in the loops)
         const int nsub = p.ksteps / p.kpb;
         int b = blockIdx.x / tiles_per_b, rem = blockIdx.x - b * tiles_per_b;
@@ -361,6 +365,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         // Work items are (tile, 16-column chunk) in order; the residual / running-sum rows of item k+1 are requested
         // before the arithmetic of item k, so their HBM latency hides behind it and behind the accumulator wait.
         // Everything that costs an integer division is done once per tile; bias comes from shared memory.
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // residual / running-sum reads and the output stores depend on the previous kernel
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int grp = (warp - 4) >> 2;              // epilogue group: takes this CTA's tiles grp, grp + n_groups, ...
         const int tile_stride = (int)gridDim.x * p.n_groups;
@@ -550,11 +555,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
 // ------------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------------
+// N tile: 128 wherever N allows it.  With the stacked [hi; lo] operand a 128-wide tile costs 128 + 64 tensor cycles per
+// k-step - exactly half of the 3 x 128 of a 256-wide tile - and twice as many tiles fill the 148 SMs' last wave better
+// (320 tiles of 128 x 256 at C = 256, B x L = 8 x 5120, are 2.16 waves; 640 tiles are 4.3).
 int tc_n_tile(int N) {
     if (N <= 0 || N % 16) return 0;
-    if (N <= 256) return N;
-    if (N % 256 == 0) return 256;
+    if (N <= 128) return N;
     if (N % 128 == 0) return 128;
+    if (N <= 256) return N;
     return 0;
 }
 
@@ -732,10 +740,17 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
                     a.Cin, a.N, NT, a.K, a.D, a.L, a.B, p.total_tiles, grid, ctas_per_sm, smem_bytes, p.n_a_stages, p.a_stage_bytes, p.res_blocks,
                     p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc, p.n_groups);
     }
-    if (a.res && a.accin) tc_conv_kernel<true, true><<<grid, threads, smem_bytes, st>>>(xmap, p);
-    else if (a.res) tc_conv_kernel<true, false><<<grid, threads, smem_bytes, st>>>(xmap, p);
-    else if (a.accin) tc_conv_kernel<false, true><<<grid, threads, smem_bytes, st>>>(xmap, p);
-    else tc_conv_kernel<false, false><<<grid, threads, smem_bytes, st>>>(xmap, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("PB_TC_NO_PDL") != nullptr;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true>, xmap, p));
+    else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false>, xmap, p));
+    else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true>, xmap, p));
+    else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false>, xmap, p));
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
