@@ -38,9 +38,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text2wav", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true")
     return ap.parse_args()
 
 
@@ -411,6 +412,30 @@ def run_ours(args):
                     "tte_ms": ms3_tte, "value": world * t3["n"] / (ms3 * 1e-3), "unit": "samples/s",
                     "rtf_16k": t3["n"] / (ms3 * 1e-3) / 16000.0, "gpu_launches_per_step": t3["launch"]}
 
+    # ---- supplementary: configs[4] long-form streaming: 16 384 units in 1024-unit chunks with a 32-unit halo -------
+    streaming = None
+    if S == 0 and not args.no_streaming:
+        from parrot_tts_b200.vocoder import stream_generate
+        code5_h = torch.randint(0, 1000, (1, 16384), generator=g).pin_memory()
+        spk5 = torch.zeros(1, 1, dtype=torch.long, device=dev)
+
+        def run_stream(first_only):
+            c5 = code5_h.to(dev, non_blocking=True)
+            n = 0
+            for _, pcm in stream_generate(voc, c5, spk5, chunk_units=1024, halo_units=32, pcm16=True):
+                n += pcm.cpu().numel()       # int16 PCM of the chunk on the host
+                if first_only:
+                    break
+            return n
+
+        run_stream(False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); run_stream(True); first_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); n5 = run_stream(False); all_s = time.perf_counter() - t0
+        streaming = {"workload": "cfg5: 16 384 units streamed as 16 chunks of 1024 units (+32-unit halo), host codes -> int16 PCM on host",
+                     "time_to_first_chunk_ms": first_ms, "steady_samples_per_s": n5 / all_s, "rtf_16k": n5 / all_s / 16000.0,
+                     "total_ms": all_s * 1e3}
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -441,7 +466,7 @@ def run_ours(args):
             "rtf_16k": value / 16000.0, "rtf_22k05": value / 22050.0,
             "vocoder_algorithmic_tflops": VOC_FLOP_PER_UNIT * units * world / (ms_step * 1e-3) / 1e12 if S == 0 else None,
             "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "text2wav": text2wav,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "text2wav": text2wav, "streaming": streaming,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -457,10 +482,83 @@ class _Null:
         return False
 
 
+def run_cfg4(args):
+    """BASELINE configs[3]: 256 utterances of 256..4096 units, sharded data-parallel by longest-processing-time-first on
+    their length, batched in length buckets (each item masked to its own length = its batch-of-1 result); no collective on
+    the data path.  value = true (unpadded) samples of all ranks / slowest rank's time."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from parrot_tts_b200 import _lib, configs, sharding, synth
+    from parrot_tts_b200.vocoder import CodeGenerator
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=0) if rank == 0 else None
+    if world > 1:
+        sd = sharding.broadcast_state_dict(sd, src=0, device=dev)
+    voc = CodeGenerator(h); voc.load_state_dict(sd); voc = voc.to(dev)
+    lengths = np.random.default_rng(0).integers(256, 4097, 256).tolist()
+    bins = sharding.lpt_assign([sharding.utterance_cost(n, with_tte=False) for n in lengths], world)
+    batches = sharding.length_buckets(bins[rank], lengths, max_batch=8)
+    g = torch.Generator().manual_seed(7)
+    work = []
+    for idx in batches:
+        Lmax = max(lengths[i] for i in idx)
+        code = torch.randint(0, 1000, (len(idx), Lmax), generator=g).to(dev)
+        lens = torch.tensor([lengths[i] for i in idx], dtype=torch.int32, device=dev)
+        spk = torch.randint(0, 10, (len(idx), 1), generator=g).to(dev)
+        work.append((code, spk, lens))
+    my_units = sum(lengths[i] for i in bins[rank]); padded = sum(c.numel() for c, _, _ in work)
+
+    def step():
+        for code, spk, lens in work:
+            voc(code=code, spkr=spk, lens=lens)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    total_units = sum(lengths)
+    if rank == 0:
+        v = total_units * HOP / (ms * 1e-3)
+        print(json.dumps({"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32 (split-bf16 x3 products on tcgen05, fp32 accumulation in TMEM)", "data": "synthetic",
+                          "config": {"workload": "cfg4: 256 utterances, 256..4096 units each (numpy default_rng(0)), CodeGenerator, LPT-sharded over the ranks, length buckets of <= 8",
+                                     "rank0_units": my_units, "rank0_padded_units": padded, "rank0_batches": len(work)},
+                          "rtf_16k": v / 16000.0, "gpu_launches": int(voc.last_launches * len(work) * args.steps)}), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
     else:
         run_ours(args)
 

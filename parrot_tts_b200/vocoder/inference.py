@@ -28,3 +28,28 @@ def generate(h, generator, code):
     audio = ops.wav_to_pcm16(y_g_hat.squeeze()).cpu().numpy()
     rtf = (time.time() - start) / (y_g_hat.shape[-1] / h.sampling_rate)
     return audio, rtf
+
+
+def stream_chunks(n_units, chunk_units=1024, halo_units=32):
+    """[(lo, hi, a, b)]: chunk i synthesises units [a, b) from the window [lo, hi) = [a - halo, b + halo) clipped to the
+    utterance.  The generator is purely convolutional with a receptive-field radius of ~23 units,
+    so with halo >= 24 every kept sample equals the unchunked result."""
+    out = []
+    for a in range(0, n_units, chunk_units):
+        b = min(a + chunk_units, n_units)
+        out.append((max(a - halo_units, 0), min(b + halo_units, n_units), a, b))
+    return out
+
+
+def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32, pcm16=False):
+    """Long-form synthesis in chunks (BASELINE configs[4]): yields (first_sample, audio) per chunk, audio f32 [B, n] on the
+    device (or int16 with ``pcm16=True``), n = hop * (b - a).  ``code`` i64 [B, T] on the device.  Each chunk is one
+    ``generator(code=window, spkr=spkr)`` call on the window of units it needs; nothing is recomputed beyond the two halos."""
+    T = code.shape[1]
+    hop = generator.hop
+    for lo, hi, a, b in stream_chunks(T, chunk_units, halo_units):
+        kw = {"code": code[:, lo:hi].contiguous()}
+        if spkr is not None:
+            kw["spkr"] = spkr
+        wav = generator(**kw)[:, 0, (a - lo) * hop:(b - lo) * hop]
+        yield a * hop, (ops.wav_to_pcm16(wav.contiguous()) if pcm16 else wav)

@@ -83,3 +83,16 @@ def test_broadcast_and_sharding_world_size_2():
     for rank, ok, gathered in res:
         assert ok, f"rank {rank}: broadcast weights differ"
         assert sorted(i for b in gathered for i in b) == list(range(32))    # shards are disjoint and complete
+
+
+def test_stream_chunks_cover_the_utterance():
+    """Chunk plan of the long-form streaming path (BASELINE configs[4]): kept ranges tile [0, T), windows add the halo."""
+    from parrot_tts_b200.vocoder.inference import stream_chunks
+    for T, chunk, halo in [(16384, 1024, 32), (700, 256, 32), (5, 1024, 32), (1025, 1024, 0)]:
+        plan = stream_chunks(T, chunk, halo)
+        assert plan[0][2] == 0 and plan[-1][3] == T
+        for (lo, hi, a, b), nxt in zip(plan, plan[1:] + [None]):
+            assert 0 <= lo <= a < b <= hi <= T and b - a <= chunk
+            assert lo == max(a - halo, 0) and hi == min(b + halo, T)
+            if nxt is not None:
+                assert nxt[2] == b

@@ -232,3 +232,27 @@ def test_no_cpu_fallback():
     h, sd, gen = _code_generator(0)
     with pytest.raises(Exception):
         gen.cpu()(code=torch.zeros(1, 4, dtype=torch.long), spkr=torch.zeros(1, 1, dtype=torch.long))
+
+
+def test_streamed_chunks_equal_unchunked():
+    """BASELINE configs[4]: chunked synthesis with a 32-unit halo reproduces the unchunked waveform (the generator's
+    receptive-field radius is ~23 units)."""
+    from parrot_tts_b200.vocoder import stream_chunks, stream_generate
+    h = configs.default_vocoder_config()
+    gen = CodeGenerator(h)
+    gen.load_state_dict(synth.synth_vocoder_state_dict(h, seed=3))
+    gen = gen.to(DEV)
+    g = torch.Generator().manual_seed(11)
+    T = 700
+    code = torch.randint(0, 1000, (1, T), generator=g).to(DEV)
+    spkr = torch.tensor([[4]]).to(DEV)
+    full = gen(code=code, spkr=spkr)[:, 0]
+    parts = list(stream_generate(gen, code, spkr, chunk_units=256, halo_units=32))
+    assert [p[0] for p in parts] == [a * 320 for _, _, a, _ in stream_chunks(T, 256, 32)]
+    got = torch.cat([w for _, w in parts], dim=1)
+    assert got.shape == full.shape
+    err = float((got - full).abs().max())
+    assert err <= 1e-6, err
+    # a halo shorter than the receptive field must NOT reproduce it (the test would be vacuous otherwise)
+    bad = torch.cat([w for _, w in stream_generate(gen, code, spkr, chunk_units=256, halo_units=2)], dim=1)
+    assert float((bad - full).abs().max()) > 1e-5
