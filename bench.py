@@ -223,6 +223,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup = args.steps, max(args.warmup, 3)
     shape = workload_shape(args.workload)
@@ -500,6 +501,7 @@ def run_cfg4(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     h = configs.default_vocoder_config()
     sd = synth.synth_vocoder_state_dict(h, seed=0) if rank == 0 else None

@@ -49,6 +49,26 @@ int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int 
 int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st, int fmt = 0);
 int launch_tc_conv(const TcConvArgs& a, cudaStream_t st);
 
+// Fused ResBlock1 step (tc_pair.cu), C = 16 / 32:  out = post( (conv2(lrelu(conv1(x) + b1, mid_slope)) + b2 + unact(x) [+ accin]) * scale )
+// with x stored leaky-relu'd (res_unslope undoes it), conv1 dilation D, conv2 dilation 1, both K taps, 'same' padding.
+struct TcPairArgs {
+    const __nv_bfloat16* x = nullptr;      // [B][L][2C] split-bf16: conv1 input and conv2 residual
+    const uint8_t* w1 = nullptr;           // packed by tc_pack_conv_weight (N = Cin = C)
+    const uint8_t* w2 = nullptr;
+    const float* bias1 = nullptr;
+    const float* bias2 = nullptr;
+    const __nv_bfloat16* accin = nullptr;  // raw running sum or null (may alias out)
+    __nv_bfloat16* out = nullptr;
+    const int32_t* lens = nullptr;
+    int len_mul = 1;
+    int B = 0, L = 0, C = 0, K = 1, D = 1;
+    float mid_slope = 0.1f, post_slope = 1.f, scale = 1.f, res_unslope = 10.f;
+};
+bool tc_pair_supported(int C, int K, int D);
+int launch_tc_pair(const TcPairArgs& a, cudaStream_t st);
+// 3-D TMA map over split 16-bit activations [B][L][2C] (box: box_c channels x rows positions), shared by tc_conv.cu / tc_pair.cu
+int tc_make_tmap_act(CUtensorMap* map, const __nv_bfloat16* base, int C, int L, int B, int box_c, int rows, bool sw128);
+
 // layout conversion (test entry points, embedding stage): f32 [B][C][L] (row stride pitch) <-> split-bf16 [B][L][2C]
 int launch_f32_to_split(const float* x, int64_t pitch, __nv_bfloat16* y, int B, int C, int L, float pre_slope, cudaStream_t st);
 int launch_split_to_f32(const __nv_bfloat16* x, float* y, int64_t pitch, int B, int C, int L, cudaStream_t st);

@@ -1,6 +1,9 @@
 // pb_umma.cuh - thin inline-PTX wrappers of the sm_100a tensor-core instructions (tcgen05.mma / .ld / .st / .commit / TMEM
 // allocation) and the shared-memory matrix descriptor, shared by tc_conv.cu and attn_tc.cu.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "pb_common.cuh"
 
 namespace pb {
@@ -128,6 +131,53 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// ---- split 16-bit storage: value = hi + lo, both bf16 (fmt 0) or both fp16 (fmt 1; ~2^-22 relative for |v| in [2^-3, 65504]) ----
+__device__ __forceinline__ void split2(float a, float b, int fmt, uint32_t& hw, uint32_t& lw) {
+    if (fmt == 0) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+        hw = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - bf16lo(hw), b - bf16hi(hw));
+        lw = *reinterpret_cast<const uint32_t*>(&l2);
+    } else {
+        a = fminf(fmaxf(a, -65504.f), 65504.f);      // saturate instead of overflowing to inf
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        const __half2 h2 = __floats2half2_rn(a, b);
+        hw = *reinterpret_cast<const uint32_t*>(&h2);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+        lw = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+}
+__device__ __forceinline__ float2 join2(uint32_t hw, uint32_t lw, int fmt) {
+    if (fmt == 0) return make_float2(bf16lo(hw) + bf16lo(lw), bf16hi(hw) + bf16hi(lw));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lw));
+    return make_float2(h.x + l.x, h.y + l.y);
+}
+__device__ __forceinline__ void split1(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+    if (fmt == 0) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    } else {
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(v);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    }
+}
+
 
 }  // namespace
 }  // namespace pb

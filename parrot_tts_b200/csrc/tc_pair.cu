@@ -1,0 +1,433 @@
+// tc_pair.cu - one fused launch for a ResBlock1 step of the narrow HiFi-GAN stages (C = 16 / 32) on sm_100a:
+//     xt  = leaky_relu(conv1(leaky_relu(x), dilation d))            reference utils/vocoder/models.py:31-38 (c1)
+//     out = x + conv2(xt)  (+ running sum, x 1/3, next activation)  (c2, and models.py:100-106 for the last step of a block)
+// The intermediate xt never leaves the SM: conv1's accumulator is converted to split-bf16 rows in SHARED MEMORY (the swizzled
+// K-major layout TMA would have produced) and is the A operand of conv2's MMAs.  HBM traffic per pair drops from five tensor
+// passes (read x, write xt, read xt, read x, write out) to ~2.2 (x with halo, out; the residual re-read hits L2).
+//
+// Tile: conv1 produces 128 rows of xt, conv2 the 128 - (K-1) output rows they support (tiles advance by that many rows; the
+// K-1 garbage rows an M = 128 MMA computes past them are never stored).  Both weight sets stay resident in shared memory.
+//   warp 0       producer: TMA loads of the x tile (128 + (K-1) d rows, zero fill = conv padding)
+//   warp 1       MMA issuer, software pipelined: conv1(i+1) is issued before conv2(i), so the tensor pipe works on the next
+//                tile while the epilogue warps turn conv1(i)'s accumulator into the shared-memory operand
+//   warp 2       TMEM owner (two conv1 + two conv2 accumulator stages)
+//   warps 4..11  two epilogue groups taking alternate tiles: epilogue A (TMEM -> bias, leaky relu, edge zeros -> swizzled smem),
+//                then epilogue B (TMEM -> bias, residual, running sum, scale, activation, length mask -> global)
+#include <stdlib.h>
+
+#include "pb_tc.cuh"
+#include "pb_umma.cuh"
+
+namespace pb {
+
+namespace {
+
+constexpr int TP_M = 128;
+constexpr int TP_GROUPS = 2;
+constexpr int TP_THREADS = 128 + 128 * TP_GROUPS;
+constexpr int TP_MAX_XST = 6;
+constexpr uint32_t TP_SMEM_LIMIT = 232448;
+
+struct PairParams {
+    const uint8_t *w1, *w2;
+    const float *bias1, *bias2;
+    const __nv_bfloat16* res;      // x itself (stored leaky-relu'd): residual of conv2
+    const __nv_bfloat16* accin;
+    __nv_bfloat16* out;
+    const int32_t* lens;
+    int len_mul;
+    int B, L, C, K, D;
+    int p1, p2, m_out;             // conv1 / conv2 half widths, output rows per tile
+    int ksteps, row_bytes, lo_off, a_layout, a_sbo;
+    int x_rows, x_stage_bytes, n_x_stages, mid_bytes, w_bytes;
+    uint32_t smem_bias_off, smem_w1_off, smem_w2_off, smem_x_off, smem_mid_off;
+    int tiles_t, total_tiles;
+    float mid_slope, post_slope, scale, res_unslope;
+    uint32_t idesc, idesc_stack;
+    int acc_cols;
+};
+
+}  // namespace
+
+template <bool ACC, int KSTEPS>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
+    uint64_t* full_x = bars;                         // [TP_MAX_XST]
+    uint64_t* empty_x = bars + TP_MAX_XST;
+    uint64_t* a_full = bars + 2 * TP_MAX_XST;        // [2] conv1 accumulator ready
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* mid_full = a_empty + 2;                // [2] xt tile in shared memory
+    uint64_t* mid_empty = mid_full + 2;
+    uint64_t* b_full = mid_empty + 2;                // [2] conv2 accumulator ready
+    uint64_t* b_empty = b_full + 2;
+    uint64_t* w_full = b_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sm_base = smem_u32(sm);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&xmap);
+        for (int s = 0; s < TP_MAX_XST; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 4);
+            mbar_init(&mid_full[s], 4); mbar_init(&mid_empty[s], 1);
+            mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 4);
+        }
+        mbar_init(w_full, 1);
+        fence_mbar_init();
+    }
+    {   // biases -> shared memory; the K-1 rows past each xt tile are read (never used) by conv2: keep them finite
+        float* bw = reinterpret_cast<float*>(sm + p.smem_bias_off);
+        for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) bw[i] = i < p.C ? p.bias1[i] : p.bias2[i - p.C];
+        uint4* mz = reinterpret_cast<uint4*>(sm + p.smem_mid_off);
+        for (int i = threadIdx.x; i < 2 * p.mid_bytes / 16; i += blockDim.x) mz[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)(4 * p.acc_cols < 32 ? 32 : 4 * p.acc_cols));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_b = p.tiles_t;
+
+    if (warp == 0) {
+        // =========================== producer ===========================
+        if (elect_one()) {
+            mbar_expect_tx(w_full, (uint32_t)(2 * p.w_bytes));
+            for (int off = 0; off < p.w_bytes; off += 32768) {
+                const int n = p.w_bytes - off < 32768 ? p.w_bytes - off : 32768;
+                bulk_load_1d(sm + p.smem_w1_off + off, p.w1 + off, (uint32_t)n, w_full);
+                bulk_load_1d(sm + p.smem_w2_off + off, p.w2 + off, (uint32_t)n, w_full);
+            }
+        }
+        __syncwarp();
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        uint32_t xs = 0, xph = 0;
+        int b = blockIdx.x / tiles_per_b, rem = blockIdx.x - b * tiles_per_b;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int row0 = rem * p.m_out - p.p2 - p.p1;
+            mbar_wait(&empty_x[xs], xph ^ 1);
+            if (elect_one()) {
+                uint8_t* dst = sm + p.smem_x_off + xs * p.x_stage_bytes;
+                // the box is at most 256 rows: the tile is loaded as two boxes of x_rows / 2 rows
+                mbar_expect_tx(&full_x[xs], (uint32_t)(p.x_rows * p.row_bytes));
+                tma_load_3d(dst, &xmap, 0, row0, b, &full_x[xs]);
+                tma_load_3d(dst + (p.x_rows / 2) * p.row_bytes, &xmap, 0, row0 + p.x_rows / 2, b, &full_x[xs]);
+            }
+            __syncwarp();
+            if (++xs == (uint32_t)p.n_x_stages) { xs = 0; xph ^= 1; }
+            rem += (int)gridDim.x;
+            while (rem >= tiles_per_b) { rem -= tiles_per_b; ++b; }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        const uint32_t a_desc_hi = (uint32_t)(smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0) >> 32);
+        const uint32_t a_desc_lo = (uint32_t)smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
+        const uint32_t b_desc_hi = (uint32_t)(smem_desc(0, (uint32_t)p.C * 32u, 128, 0, 0) >> 32);
+        const uint32_t b_desc_lo = (uint32_t)smem_desc(0, (uint32_t)p.C * 32u, 128, 0, 0);
+        const uint32_t lo_step = (uint32_t)p.lo_off >> 4;
+        const uint32_t kstep_step = (uint32_t)p.C * 4u;                 // 2 planes x 2 K halves x C x 16 bytes
+        const uint32_t block_step = kstep_step * (uint32_t)KSTEPS;
+        const uint32_t tap1 = (uint32_t)(p.D * p.row_bytes) >> 4, tap2 = (uint32_t)p.row_bytes >> 4;
+        const uint32_t w1_lo = b_desc_lo | (((sm_base + p.smem_w1_off) >> 4) & 0x3fffu);
+        const uint32_t w2_lo = b_desc_lo | (((sm_base + p.smem_w2_off) >> 4) & 0x3fffu);
+        const int K = p.K;
+        const uint32_t idesc = p.idesc, idesc_stack = p.idesc_stack, acc_cols = (uint32_t)p.acc_cols;
+        // one convolution of one tile: K taps x ksteps x {a_hi.[w_hi; w_lo], a_lo.w_hi}
+        auto conv = [&](uint32_t d_tmem, uint32_t a_lo0, uint32_t tap_step, uint32_t w_lo) {
+            uint32_t acc = 0;
+            uint32_t a_tap = a_lo0, b_tap = w_lo;
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint64_t da_hi = ((uint64_t)a_desc_hi << 32) | (a_tap + 2u * ks);
+                    const uint64_t da_lo = ((uint64_t)a_desc_hi << 32) | (a_tap + 2u * ks + lo_step);
+                    const uint64_t db = ((uint64_t)b_desc_hi << 32) | (b_tap + kstep_step * ks);
+                    umma_bf16(d_tmem, da_hi, db, idesc_stack, acc);
+                    umma_bf16(d_tmem, da_lo, db, idesc, 1);
+                    acc = 1;
+                }
+                a_tap += tap_step;
+                b_tap += block_step;
+            }
+        };
+        uint32_t xs = 0, xph = 0;
+        int n_my = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) ++n_my;
+        auto conv1 = [&](int i) {
+            const uint32_t st = (uint32_t)i & 1u, n = (uint32_t)i >> 1;
+            mbar_wait(&full_x[xs], xph);
+            if (n > 0) mbar_wait(&a_empty[st], (n - 1) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_base = sm_base + p.smem_x_off + xs * (uint32_t)p.x_stage_bytes;
+                conv(tmem_base + st * acc_cols, a_desc_lo | ((a_base >> 4) & 0x3fffu), tap1, w1_lo);
+                umma_commit(&empty_x[xs]);
+                umma_commit(&a_full[st]);
+            }
+            __syncwarp();
+            if (++xs == (uint32_t)p.n_x_stages) { xs = 0; xph ^= 1; }
+        };
+        auto conv2 = [&](int i) {
+            const uint32_t st = (uint32_t)i & 1u, n = (uint32_t)i >> 1;
+            mbar_wait(&mid_full[st], n & 1u);
+            if (n > 0) mbar_wait(&b_empty[st], (n - 1) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t m_base = sm_base + p.smem_mid_off + st * (uint32_t)p.mid_bytes;
+                conv(tmem_base + (2u + st) * acc_cols, a_desc_lo | ((m_base >> 4) & 0x3fffu), tap2, w2_lo);
+                umma_commit(&mid_empty[st]);
+                umma_commit(&b_full[st]);
+            }
+            __syncwarp();
+        };
+        if (n_my > 0) conv1(0);
+        for (int i = 0; i < n_my; ++i) {
+            if (i + 1 < n_my) conv1(i + 1);
+            conv2(i);
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue groups ===========================
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int C = p.C;
+        const size_t pitch = (size_t)2 * C;
+        const float* bias1 = reinterpret_cast<const float*>(sm + p.smem_bias_off);
+        const float* bias2 = bias1 + C;
+        const int stride = (int)gridDim.x * TP_GROUPS;
+        int tile = blockIdx.x + grp * (int)gridDim.x;
+        int b = tile / tiles_per_b, rem = tile - b * tiles_per_b;
+        auto valid_of = [&](int bb) {
+            int v = p.L;
+            if (p.lens) { const int u = __ldg(p.lens + bb) * p.len_mul; v = u < v ? u : v; }
+            return v;
+        };
+        int valid = tile < p.total_tiles ? valid_of(b) : 0;
+        const bool sw128 = p.a_layout == 2;
+        for (int i = grp; tile < p.total_tiles; i += TP_GROUPS, tile += stride) {
+            const uint32_t st = (uint32_t)i & 1u, n = (uint32_t)i >> 1;
+            const int o0 = rem * p.m_out;
+            // ---------------- epilogue A: conv1 accumulator -> xt tile in shared memory ----------------
+            {
+                const int tm = o0 - p.p2 + row;                    // sequence position of this xt row
+                const bool in_seq = tm >= 0 && tm < valid;         // conv2 sees zeros outside the (valid) sequence
+                mbar_wait(&a_full[st], n & 1u);
+                if (n > 0) mbar_wait(&mid_empty[st], (n - 1) & 1u);   // conv2(i-2) has consumed this xt buffer
+                tc_fence_after();
+                uint8_t* mrow = sm + p.smem_mid_off + st * p.mid_bytes + row * p.row_bytes;
+                const uint32_t swz = sw128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                for (int n0 = 0; n0 < C; n0 += 16) {
+                    float v[16];
+                    const uint32_t taddr = tmem_base + lane_off + st * (uint32_t)p.acc_cols + (uint32_t)n0;
+                    tmem_ld16x2_sum(taddr, taddr + (uint32_t)C, v);
+                    const float4* bp = reinterpret_cast<const float4*>(bias1 + n0);
+                    uint32_t hw[8], lw[8];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 bv = bp[k4];
+                        v[4 * k4] += bv.x; v[4 * k4 + 1] += bv.y; v[4 * k4 + 2] += bv.z; v[4 * k4 + 3] += bv.w;
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; ++k2) {
+                        float a0 = v[2 * k2], a1 = v[2 * k2 + 1];
+                        a0 = in_seq ? fmaxf(a0, a0 * p.mid_slope) : 0.f;
+                        a1 = in_seq ? fmaxf(a1, a1 * p.mid_slope) : 0.f;
+                        split2(a0, a1, 0, hw[k2], lw[k2]);
+                    }
+                    // 16-byte chunks of the row: hi channels n0.. -> chunks n0/8, n0/8 + 1; lo -> lo_off/16 + the same
+                    const uint32_t ch = (uint32_t)n0 >> 3, cl = ((uint32_t)p.lo_off >> 4) + ch;
+                    *reinterpret_cast<uint4*>(mrow + ((ch ^ swz) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(mrow + (((ch + 1) ^ swz) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    *reinterpret_cast<uint4*>(mrow + ((cl ^ swz) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    *reinterpret_cast<uint4*>(mrow + (((cl + 1) ^ swz) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                }
+                tc_fence_before();
+                fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&a_empty[st]); mbar_arrive(&mid_full[st]); }
+            }
+            // ---------------- epilogue B: conv2 accumulator -> output rows ----------------
+            {
+                const int to = o0 + row;
+                const bool row_ok = row < p.m_out && to < p.L;
+                const bool live = to < valid;
+                const size_t row_el = ((size_t)b * p.L + to) * pitch;
+                uint4 R[4], A[4];
+                auto request = [&](int n0) {
+                    if (!row_ok) return;
+                    const uint4* rh = reinterpret_cast<const uint4*>(p.res + row_el + n0);
+                    const uint4* rl = reinterpret_cast<const uint4*>(p.res + row_el + C + n0);
+                    R[0] = __ldg(rh); R[1] = __ldg(rh + 1); R[2] = __ldg(rl); R[3] = __ldg(rl + 1);
+                    if (ACC) {
+                        const uint4* ah = reinterpret_cast<const uint4*>(p.accin + row_el + n0);
+                        const uint4* al = reinterpret_cast<const uint4*>(p.accin + row_el + C + n0);
+                        A[0] = ah[0]; A[1] = ah[1]; A[2] = al[0]; A[3] = al[1];
+                    }
+                };
+                request(0);
+                mbar_wait(&b_full[st], n & 1u);
+                tc_fence_after();
+                for (int n0 = 0; n0 < C; n0 += 16) {
+                    float v[16];
+                    const uint32_t taddr = tmem_base + lane_off + (2u + st) * (uint32_t)p.acc_cols + (uint32_t)n0;
+                    tmem_ld16x2_sum(taddr, taddr + (uint32_t)C, v);
+                    if (n0 + 16 >= C) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&b_empty[st]);
+                    }
+                    if (row_ok) {
+                        const float4* bp = reinterpret_cast<const float4*>(bias2 + n0);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 bv = bp[k4];
+                            v[4 * k4] += bv.x; v[4 * k4 + 1] += bv.y; v[4 * k4 + 2] += bv.z; v[4 * k4 + 3] += bv.w;
+                        }
+                        const uint32_t hh[8] = {R[0].x, R[0].y, R[0].z, R[0].w, R[1].x, R[1].y, R[1].z, R[1].w};
+                        const uint32_t ll[8] = {R[2].x, R[2].y, R[2].z, R[2].w, R[3].x, R[3].y, R[3].z, R[3].w};
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) {
+                            const float2 r = join2(hh[k2], ll[k2], 0);
+                            v[2 * k2] += fminf(r.x, r.x * p.res_unslope);
+                            v[2 * k2 + 1] += fminf(r.y, r.y * p.res_unslope);
+                        }
+                        if (ACC) {
+                            const uint32_t ah[8] = {A[0].x, A[0].y, A[0].z, A[0].w, A[1].x, A[1].y, A[1].z, A[1].w};
+                            const uint32_t al[8] = {A[2].x, A[2].y, A[2].z, A[2].w, A[3].x, A[3].y, A[3].z, A[3].w};
+#pragma unroll
+                            for (int k2 = 0; k2 < 8; ++k2) {
+                                const float2 r = join2(ah[k2], al[k2], 0);
+                                v[2 * k2] = r.x + v[2 * k2];
+                                v[2 * k2 + 1] = r.y + v[2 * k2 + 1];
+                            }
+                        }
+                        const float sc = live ? p.scale : 0.f;
+                        uint32_t hw[8], lw[8];
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) {
+                            float a0 = v[2 * k2] * sc, a1 = v[2 * k2 + 1] * sc;
+                            a0 = fmaxf(a0, a0 * p.post_slope);
+                            a1 = fmaxf(a1, a1 * p.post_slope);
+                            split2(a0, a1, 0, hw[k2], lw[k2]);
+                        }
+                        if (n0 + 16 < C) request(n0 + 16);
+                        __nv_bfloat16* oh = p.out + row_el + n0;
+                        __nv_bfloat16* ol = oh + C;
+                        st_global_v4(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                        st_global_v4(oh + 8, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+                        st_global_v4(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+                        st_global_v4(ol + 8, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                    }
+                }
+            }
+            rem += stride;
+            if (rem >= tiles_per_b) {
+                do { rem -= tiles_per_b; ++b; } while (rem >= tiles_per_b);
+                if (tile + stride < p.total_tiles) valid = valid_of(b);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)(4 * p.acc_cols < 32 ? 32 : 4 * p.acc_cols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------------
+bool tc_pair_supported(int C, int K, int D) {
+    if (C != 16 && C != 32) return false;
+    if (K < 1 || K % 2 == 0 || K > 15 || D < 1) return false;
+    const int x_rows = (int)round_up(TP_M + (K - 1) * D, 16);
+    return x_rows <= 512;
+}
+
+int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
+    PB_REQUIRE(a.x && a.w1 && a.w2 && a.out && a.bias1 && a.bias2, PB_ERR_INVALID, "tc_pair: null tensor");
+    PB_REQUIRE(tc_pair_supported(a.C, a.K, a.D), PB_ERR_INVALID, "tc_pair: C=%d K=%d D=%d unsupported", a.C, a.K, a.D);
+    PB_REQUIRE(a.B > 0 && a.L > 0, PB_ERR_INVALID, "tc_pair: bad shape");
+    PairParams p{};
+    p.w1 = a.w1; p.w2 = a.w2; p.bias1 = a.bias1; p.bias2 = a.bias2; p.res = a.x; p.accin = a.accin; p.out = a.out;
+    p.lens = a.lens; p.len_mul = a.len_mul;
+    p.B = a.B; p.L = a.L; p.C = a.C; p.K = a.K; p.D = a.D;
+    p.p1 = (a.K - 1) * a.D / 2; p.p2 = (a.K - 1) / 2; p.m_out = TP_M - (a.K - 1);
+    p.ksteps = a.C / 16;
+    p.row_bytes = a.C == 16 ? 64 : 128;
+    p.lo_off = a.C == 16 ? 32 : 64;
+    p.a_layout = a.C == 16 ? 4 : 2;
+    p.a_sbo = 8 * p.row_bytes;
+    p.x_rows = (int)round_up(TP_M + (a.K - 1) * a.D, 16);
+    p.x_stage_bytes = (int)round_up((int64_t)p.x_rows * p.row_bytes, 1024);
+    p.mid_bytes = (int)round_up((int64_t)(TP_M + a.K - 1) * p.row_bytes, 1024);
+    p.w_bytes = a.K * 2 * p.ksteps * a.C * 32;
+    p.smem_bias_off = 1024;
+    p.smem_w1_off = 2048;
+    p.smem_w2_off = p.smem_w1_off + (uint32_t)round_up(p.w_bytes, 1024);
+    p.smem_mid_off = p.smem_w2_off + (uint32_t)round_up(p.w_bytes, 1024);
+    p.smem_x_off = p.smem_mid_off + 2u * (uint32_t)p.mid_bytes;
+    const uint32_t left = TP_SMEM_LIMIT - 1024u - p.smem_x_off;
+    p.n_x_stages = (int)(left / (uint32_t)p.x_stage_bytes);
+    if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
+    PB_REQUIRE(p.n_x_stages >= 2, PB_ERR_INVALID, "tc_pair: tile does not fit in shared memory (C=%d K=%d D=%d)", a.C, a.K, a.D);
+    const uint32_t smem_bytes = p.smem_x_off + (uint32_t)p.n_x_stages * (uint32_t)p.x_stage_bytes + 1024;
+    p.tiles_t = (int)ceil_div(a.L, p.m_out);
+    const int64_t total = (int64_t)a.B * p.tiles_t;
+    PB_REQUIRE(total < (1LL << 31), PB_ERR_INVALID, "tc_pair: too many tiles");
+    p.total_tiles = (int)total;
+    p.mid_slope = a.mid_slope; p.post_slope = a.post_slope; p.scale = a.scale; p.res_unslope = a.res_unslope;
+    const uint32_t ab_fmt = (1u << 7) | (1u << 10);
+    p.idesc = (1u << 4) | ab_fmt | ((uint32_t)(a.C >> 3) << 17) | ((uint32_t)(TP_M >> 4) << 24);
+    p.idesc_stack = (1u << 4) | ab_fmt | ((uint32_t)((2 * a.C) >> 3) << 17) | ((uint32_t)(TP_M >> 4) << 24);
+    p.acc_cols = 2 * a.C;
+
+    // x tile = two boxes of x_rows / 2 rows (a TMA box holds at most 256 rows)
+    CUtensorMap xmap;
+    PB_TRY(tc_make_tmap_act(&xmap, a.x, a.C, a.L, a.B, a.C == 16 ? 32 : 64, p.x_rows / 2, a.C != 16));
+
+    static int n_sm = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int dev = 0;
+        PB_CUDA(cudaGetDevice(&dev));
+        PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (p.ksteps == 1) {
+        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 1>, xmap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 1>, xmap, p));
+    } else {
+        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 2>, xmap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 2>, xmap, p));
+    }
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // namespace pb

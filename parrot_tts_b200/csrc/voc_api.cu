@@ -1,5 +1,6 @@
 // voc_api.cu - C ABI of the HiFi-GAN code generator: handle, checkpoint ingestion (weight-norm fold + pack),
 // forward orchestration.  Reference: utils/vocoder/models.py:69-169, utils/vocoder/inference.py:65-74,104-109.
+#include <stdlib.h>
 #include <string.h>
 
 #include "pb_runtime.cuh"
@@ -331,6 +332,30 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                 const int idx = (i * c.num_kernels + j) * c.num_dilations + m;
                 const ConvSlot& s1 = h->rb1[idx];
                 const ConvSlot& s2 = h->rb2[idx];
+                static const bool no_pair = getenv("PB_TC_NO_PAIR") != nullptr;      // dev switch: two launches per ResBlock step
+                if (!no_pair && !single && tc_pair_supported(C, s1.K, s1.D)) {
+                    // narrow stages: conv1 -> conv2 fused, the intermediate stays in shared memory (tc_pair.cu)
+                    TcPairArgs f;
+                    f.x = cur; f.w1 = W(s1); f.w2 = W(s2); f.bias1 = h->A(s1.b_off); f.bias2 = h->A(s2.b_off);
+                    f.lens = lens; f.len_mul = mul; f.B = B; f.L = (int)Lo; f.C = C; f.K = s1.K; f.D = s1.D;
+                    if (m + 1 < c.num_dilations) {
+                        bf* dst = (cur == XA) ? XB : XA;
+                        f.out = dst; f.post_slope = 0.1f;
+                        PB_TRY(launch_tc_pair(f, st));
+                        cur = dst;
+                    } else {
+                        if (j > 0) f.accin = XS;
+                        if (j + 1 < c.num_kernels) {
+                            f.out = XS;
+                        } else {
+                            f.out = Y;
+                            f.scale = 1.0f / (float)c.num_kernels;
+                            f.post_slope = (i + 1 < c.num_upsamples) ? 0.1f : 0.01f;
+                        }
+                        PB_TRY(launch_tc_pair(f, st));
+                    }
+                    continue;
+                }
                 TcConvArgs a;
                 a.x = cur; a.w = W(s1); a.bias = h->A(s1.b_off); a.out = XT; a.lens = lens; a.len_mul = mul;
                 a.B = B; a.L = (int)Lo; a.Cin = C; a.N = C; a.out_C = C; a.U = 1; a.K = s1.K; a.D = s1.D;

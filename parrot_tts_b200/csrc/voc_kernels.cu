@@ -690,51 +690,64 @@ int launch_voc_embed_split(const int64_t* code, const int64_t* spkr, const float
     return PB_OK;
 }
 
-// one thread per output sample: 7 rows x CIN channels (hi + lo), rows shared with the neighbours through L1
+// conv_post + tanh on split-bf16 rows: a block stages POST_T + K - 1 input rows in shared memory as fp32 [channel][position]
+// (hi + lo joined once), then every thread produces POST_T / 256 samples from conflict-free shared-memory reads.
+constexpr int POST_T = 512;
 template <int CIN, int K>
 __global__ void __launch_bounds__(256)
 conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ wav, const int32_t* __restrict__ lens, int len_mul, int L) {
+    constexpr int ROWS = POST_T + K - 1;
+    constexpr int PITCH = ROWS + 1;
+    __shared__ float xs[CIN * PITCH];
     __shared__ float ws[CIN * K];
     for (int i = threadIdx.x; i < CIN * K; i += blockDim.x) ws[i] = w[i];
-    __syncthreads();
     const int b = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L) return;
+    const int t0 = blockIdx.x * POST_T;
     int valid = L;
     if (lens) { const int v = lens[b] * len_mul; valid = v < valid ? v : valid; }
-    float acc = 0.f;
-    if (t < valid) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int tt = t + j - (K - 1) / 2;
-            if (tt < 0 || tt >= L) continue;
+    for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
+        const int tt = t0 + r - (K - 1) / 2;
+        if (tt >= 0 && tt < L) {
             const uint4* row = reinterpret_cast<const uint4*>(x + ((size_t)b * L + tt) * 2 * CIN);
 #pragma unroll
             for (int q = 0; q < CIN / 8; ++q) {
-                const uint4 h = row[q], l = row[CIN / 8 + q];
+                const uint4 h = __ldg(row + q), l = __ldg(row + CIN / 8 + q);
                 const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float v0 = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
-                    const float v1 = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
-                    acc = fmaf(ws[(q * 8 + 2 * i) * K + j], v0, acc);
-                    acc = fmaf(ws[(q * 8 + 2 * i + 1) * K + j], v1, acc);
+                    xs[(q * 8 + 2 * i) * PITCH + r] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+                    xs[(q * 8 + 2 * i + 1) * PITCH + r] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
                 }
             }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) xs[c * PITCH + r] = 0.f;
         }
-        acc = tanhf(acc + bias[0]);
     }
-    wav[(size_t)b * L + t] = acc;
+    __syncthreads();
+    const float bv = bias[0];
+    for (int o = threadIdx.x; o < POST_T; o += blockDim.x) {
+        const int t = t0 + o;
+        if (t >= L) break;
+        float acc = 0.f;
+        if (t < valid) {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                for (int j = 0; j < K; ++j) acc = fmaf(ws[c * K + j], xs[c * PITCH + o + j], acc);
+            acc = tanhf(acc + bv);
+        }
+        wav[(size_t)b * L + t] = acc;
+    }
 }
 
 int launch_conv_post_split(const __nv_bfloat16* x, const float* w, const float* bias, float* wav, const int32_t* lens, int len_mul,
                            int B, int Cin, int L, int K, cudaStream_t st) {
     PB_REQUIRE(K == 7, PB_ERR_INVALID, "conv_post: kernel size %d unsupported (7 expected)", K);
-    dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
+    dim3 grid((unsigned)ceil_div(L, POST_T), (unsigned)B);
     if (Cin == 16) conv_post_split_kernel<16, 7><<<grid, 256, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
-    else if (Cin == 32) conv_post_split_kernel<32, 7><<<grid, 256, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
-    else { set_error("conv_post: Cin=%d unsupported", Cin); return PB_ERR_INVALID; }
+    else { set_error("conv_post: Cin=%d unsupported on the tensor-core path (16 expected)", Cin); return PB_ERR_INVALID; }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
