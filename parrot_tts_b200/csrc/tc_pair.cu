@@ -23,7 +23,8 @@ namespace pb {
 namespace {
 
 constexpr int TP_M = 128;
-constexpr int TP_GROUPS = 2;
+constexpr int TP_GROUPS = 3;      // epilogue warpgroups, tiles round-robin
+constexpr int TP_STAGES = 3;      // conv1 accumulator / xt tile / conv2 accumulator stages (tiles in flight)
 constexpr int TP_THREADS = 128 + 128 * TP_GROUPS;
 constexpr int TP_MAX_XST = 6;
 constexpr uint32_t TP_SMEM_LIMIT = 232448;
@@ -44,7 +45,7 @@ struct PairParams {
     int tiles_t, total_tiles;
     float mid_slope, post_slope, scale, res_unslope;
     uint32_t idesc, idesc_stack;
-    int acc_cols;
+    int acc_cols, tmem_cols;
 };
 
 }  // namespace
@@ -57,13 +58,13 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
     uint64_t* full_x = bars;                         // [TP_MAX_XST]
     uint64_t* empty_x = bars + TP_MAX_XST;
-    uint64_t* a_full = bars + 2 * TP_MAX_XST;        // [2] conv1 accumulator ready
-    uint64_t* a_empty = a_full + 2;
-    uint64_t* mid_full = a_empty + 2;                // [2] xt tile in shared memory
-    uint64_t* mid_empty = mid_full + 2;
-    uint64_t* b_full = mid_empty + 2;                // [2] conv2 accumulator ready
-    uint64_t* b_empty = b_full + 2;
-    uint64_t* w_full = b_empty + 2;
+    uint64_t* a_full = bars + 2 * TP_MAX_XST;        // [TP_STAGES] conv1 accumulator ready
+    uint64_t* a_empty = a_full + TP_STAGES;
+    uint64_t* mid_full = a_empty + TP_STAGES;        // [TP_STAGES] xt tile in shared memory
+    uint64_t* mid_empty = mid_full + TP_STAGES;
+    uint64_t* b_full = mid_empty + TP_STAGES;        // [TP_STAGES] conv2 accumulator ready
+    uint64_t* b_empty = b_full + TP_STAGES;
+    uint64_t* w_full = b_empty + TP_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,7 +73,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
         for (int s = 0; s < TP_MAX_XST; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < TP_STAGES; ++s) {
             mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 4);
             mbar_init(&mid_full[s], 4); mbar_init(&mid_empty[s], 1);
             mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 4);
@@ -84,11 +85,11 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
         float* bw = reinterpret_cast<float*>(sm + p.smem_bias_off);
         for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) bw[i] = i < p.C ? p.bias1[i] : p.bias2[i - p.C];
         uint4* mz = reinterpret_cast<uint4*>(sm + p.smem_mid_off);
-        for (int i = threadIdx.x; i < 2 * p.mid_bytes / 16; i += blockDim.x) mz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < TP_STAGES * p.mid_bytes / 16; i += blockDim.x) mz[i] = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)(4 * p.acc_cols < 32 ? 32 : 4 * p.acc_cols));
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,7 +164,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
         int n_my = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) ++n_my;
         auto conv1 = [&](int i) {
-            const uint32_t st = (uint32_t)i & 1u, n = (uint32_t)i >> 1;
+            const uint32_t st = (uint32_t)i % TP_STAGES, n = (uint32_t)i / TP_STAGES;
             mbar_wait(&full_x[xs], xph);
             if (n > 0) mbar_wait(&a_empty[st], (n - 1) & 1u);
             tc_fence_after();
@@ -177,21 +178,23 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
             if (++xs == (uint32_t)p.n_x_stages) { xs = 0; xph ^= 1; }
         };
         auto conv2 = [&](int i) {
-            const uint32_t st = (uint32_t)i & 1u, n = (uint32_t)i >> 1;
+            const uint32_t st = (uint32_t)i % TP_STAGES, n = (uint32_t)i / TP_STAGES;
             mbar_wait(&mid_full[st], n & 1u);
             if (n > 0) mbar_wait(&b_empty[st], (n - 1) & 1u);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t m_base = sm_base + p.smem_mid_off + st * (uint32_t)p.mid_bytes;
-                conv(tmem_base + (2u + st) * acc_cols, a_desc_lo | ((m_base >> 4) & 0x3fffu), tap2, w2_lo);
+                conv(tmem_base + (TP_STAGES + st) * acc_cols, a_desc_lo | ((m_base >> 4) & 0x3fffu), tap2, w2_lo);
                 umma_commit(&mid_empty[st]);
                 umma_commit(&b_full[st]);
             }
             __syncwarp();
         };
-        if (n_my > 0) conv1(0);
+        // conv1 runs TP_STAGES - 1 tiles ahead of conv2: the tensor pipe works on the following tiles while the epilogue warps
+        // turn conv1(i)'s accumulator into the shared-memory operand of conv2(i)
+        for (int i = 0; i < TP_STAGES - 1 && i < n_my; ++i) conv1(i);
         for (int i = 0; i < n_my; ++i) {
-            if (i + 1 < n_my) conv1(i + 1);
+            if (i + TP_STAGES - 1 < n_my) conv1(i + TP_STAGES - 1);
             conv2(i);
         }
     } else if (warp >= 4) {
@@ -216,7 +219,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
         int valid = tile < p.total_tiles ? valid_of(b) : 0;
         const bool sw128 = p.a_layout == 2;
         for (int i = grp; tile < p.total_tiles; i += TP_GROUPS, tile += stride) {
-            const uint32_t st = (uint32_t)i & 1u, n = (uint32_t)i >> 1;
+            const uint32_t st = (uint32_t)i % TP_STAGES, n = (uint32_t)i / TP_STAGES;
             const int o0 = rem * p.m_out;
             // ---------------- epilogue A: conv1 accumulator -> xt tile in shared memory ----------------
             {
@@ -280,7 +283,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
                 tc_fence_after();
                 for (int n0 = 0; n0 < C; n0 += 16) {
                     float v[16];
-                    const uint32_t taddr = tmem_base + lane_off + (2u + st) * (uint32_t)p.acc_cols + (uint32_t)n0;
+                    const uint32_t taddr = tmem_base + lane_off + (TP_STAGES + st) * (uint32_t)p.acc_cols + (uint32_t)n0;
                     tmem_ld16x2_sum(taddr, taddr + (uint32_t)C, v);
                     if (n0 + 16 >= C) {
                         tc_fence_before();
@@ -343,7 +346,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)(4 * p.acc_cols < 32 ? 32 : 4 * p.acc_cols));
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -379,7 +382,7 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     p.smem_w1_off = 2048;
     p.smem_w2_off = p.smem_w1_off + (uint32_t)round_up(p.w_bytes, 1024);
     p.smem_mid_off = p.smem_w2_off + (uint32_t)round_up(p.w_bytes, 1024);
-    p.smem_x_off = p.smem_mid_off + 2u * (uint32_t)p.mid_bytes;
+    p.smem_x_off = p.smem_mid_off + (uint32_t)TP_STAGES * (uint32_t)p.mid_bytes;
     const uint32_t left = TP_SMEM_LIMIT - 1024u - p.smem_x_off;
     p.n_x_stages = (int)(left / (uint32_t)p.x_stage_bytes);
     if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
@@ -394,6 +397,8 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     p.idesc = (1u << 4) | ab_fmt | ((uint32_t)(a.C >> 3) << 17) | ((uint32_t)(TP_M >> 4) << 24);
     p.idesc_stack = (1u << 4) | ab_fmt | ((uint32_t)((2 * a.C) >> 3) << 17) | ((uint32_t)(TP_M >> 4) << 24);
     p.acc_cols = 2 * a.C;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * TP_STAGES * p.acc_cols) p.tmem_cols *= 2;
 
     // x tile = two boxes of x_rows / 2 rows (a TMA box holds at most 256 rows)
     CUtensorMap xmap;
