@@ -379,14 +379,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         auto request = [&](bool ok, size_t off, uint4 (&r)[4], uint4 (&a)[4]) {
             if (!ok || (p.ablate & 4)) return;
             if (RES) {
-                const uint4* rh = reinterpret_cast<const uint4*>(p.res + off);
-                const uint4* rl = reinterpret_cast<const uint4*>(p.res + off + p.out_C);
-                r[0] = __ldg(rh); r[1] = __ldg(rh + 1); r[2] = __ldg(rl); r[3] = __ldg(rl + 1);
+                ld_global_nc_v8(p.res + off, r[0], r[1]);
+                ld_global_nc_v8(p.res + off + p.out_C, r[2], r[3]);
             }
             if (ACC) {   // may alias `out` of an earlier item of this same thread: plain loads
-                const uint4* ah = reinterpret_cast<const uint4*>(p.accin + off);
-                const uint4* al = reinterpret_cast<const uint4*>(p.accin + off + p.out_C);
-                a[0] = ah[0]; a[1] = ah[1]; a[2] = al[0]; a[3] = al[1];
+                ld_global_v8(p.accin + off, a[0], a[1]);
+                ld_global_v8(p.accin + off + p.out_C, a[2], a[3]);
             }
         };
 
@@ -403,7 +401,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             // next item
             TileCtx nxt = cur;
             int tile_n = tile, n0n = n0 + 16;
-            if (n0n >= p.NT) { n0n = 0; tile_n += tile_stride; locate_next(tile_n, nxt); }
+            if (n0n >= p.NT) {
+                n0n = 0; tile_n += tile_stride; locate_next(tile_n, nxt);
+                // residual / running-sum rows of the NEXT tile: pull them into L2 now, a whole tile ahead of their use
+                if ((RES || ACC) && nxt.ok && nxt.row_ok && p.U == 1) {
+                    const size_t rb = nxt.row_el * sizeof(__nv_bfloat16);
+                    const int row_bytes = 4 * p.out_C;
+                    for (int o = 0; o < row_bytes; o += 128) {
+                        if (RES) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.res) + rb + o));
+                        if (ACC) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.accin) + rb + o));
+                    }
+                }
+            }
             size_t offn = 0; int con = 0; bool liven = false;
             if (nxt.ok) item(nxt, n0n, offn, con, liven);
 
@@ -479,10 +488,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                     for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], p.fmt, hw[i], lw[i]);
                     __nv_bfloat16* oh = p.out + off;
                     __nv_bfloat16* ol = oh + p.out_C;
-                    st_global_v4(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-                    st_global_v4(oh + 8, make_uint4(hw[4], hw[5], hw[6], hw[7]));
-                    st_global_v4(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-                    st_global_v4(ol + 8, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                    st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+                    st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
                 }
                 if (p.out_f32) {
                     float* of = p.out_f32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch

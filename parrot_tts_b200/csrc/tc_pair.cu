@@ -269,13 +269,11 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
                 uint4 R[4], A[4];
                 auto request = [&](int n0) {
                     if (!row_ok) return;
-                    const uint4* rh = reinterpret_cast<const uint4*>(p.res + row_el + n0);
-                    const uint4* rl = reinterpret_cast<const uint4*>(p.res + row_el + C + n0);
-                    R[0] = __ldg(rh); R[1] = __ldg(rh + 1); R[2] = __ldg(rl); R[3] = __ldg(rl + 1);
+                    ld_global_nc_v8(p.res + row_el + n0, R[0], R[1]);
+                    ld_global_nc_v8(p.res + row_el + C + n0, R[2], R[3]);
                     if (ACC) {
-                        const uint4* ah = reinterpret_cast<const uint4*>(p.accin + row_el + n0);
-                        const uint4* al = reinterpret_cast<const uint4*>(p.accin + row_el + C + n0);
-                        A[0] = ah[0]; A[1] = ah[1]; A[2] = al[0]; A[3] = al[1];
+                        ld_global_v8(p.accin + row_el + n0, A[0], A[1]);
+                        ld_global_v8(p.accin + row_el + C + n0, A[2], A[3]);
                     }
                 };
                 request(0);
@@ -327,10 +325,8 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
                         if (n0 + 16 < C) request(n0 + 16);
                         __nv_bfloat16* oh = p.out + row_el + n0;
                         __nv_bfloat16* ol = oh + C;
-                        st_global_v4(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-                        st_global_v4(oh + 8, make_uint4(hw[4], hw[5], hw[6], hw[7]));
-                        st_global_v4(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-                        st_global_v4(ol + 8, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                        st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+                        st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
                     }
                 }
             }
