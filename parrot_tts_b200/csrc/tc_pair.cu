@@ -8,8 +8,8 @@
 // Tile: conv1 produces 128 rows of xt, conv2 the 128 - (K-1) output rows they support (tiles advance by that many rows; the
 // K-1 garbage rows an M = 128 MMA computes past them are never stored).  Both weight sets stay resident in shared memory.
 //   warp 0       producer: TMA loads of the x tile (128 + (K-1) d rows, zero fill = conv padding)
-//   warp 1       MMA issuer, software pipelined: conv1(i+1) is issued before conv2(i), so the tensor pipe works on the next
-//                tile while the epilogue warps turn conv1(i)'s accumulator into the shared-memory operand
+//   warps 1, 3   MMA issuers: warp 1 issues conv1 of every tile (running ahead), warp 3 conv2, so the tensor pipe works on the
+//                next tiles while the epilogue warps turn conv1(i)'s accumulator into the shared-memory operand
 //   warp 2       TMEM owner (two conv1 + two conv2 accumulator stages)
 //   warps 4..11  two epilogue groups taking alternate tiles: epilogue A (TMEM -> bias, leaky relu, edge zeros -> swizzled smem),
 //                then epilogue B (TMEM -> bias, residual, running sum, scale, activation, length mask -> global)
@@ -125,8 +125,9 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
             rem += (int)gridDim.x;
             while (rem >= tiles_per_b) { rem -= tiles_per_b; ++b; }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
+    } else if (warp == 1 || warp == 3) {
+        // =========================== MMA issuers: warp 1 issues every conv1, warp 3 every conv2 ===========================
+        // (one issuing thread sustains ~70 cycles per MMA here; the narrow MMAs need ~40, so two issuers keep the pipe fed)
         mbar_wait(w_full, 0);
         tc_fence_after();
         const uint32_t a_desc_hi = (uint32_t)(smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0) >> 32);
@@ -190,12 +191,10 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
             }
             __syncwarp();
         };
-        // conv1 runs TP_STAGES - 1 tiles ahead of conv2: the tensor pipe works on the following tiles while the epilogue warps
-        // turn conv1(i)'s accumulator into the shared-memory operand of conv2(i)
-        for (int i = 0; i < TP_STAGES - 1 && i < n_my; ++i) conv1(i);
-        for (int i = 0; i < n_my; ++i) {
-            if (i + TP_STAGES - 1 < n_my) conv1(i + TP_STAGES - 1);
-            conv2(i);
+        if (warp == 1) {
+            for (int i = 0; i < n_my; ++i) conv1(i);      // runs ahead of conv2 by up to TP_STAGES tiles (a_empty / full_x gate it)
+        } else {
+            for (int i = 0; i < n_my; ++i) conv2(i);
         }
     } else if (warp >= 4) {
         // =========================== epilogue groups ===========================
