@@ -334,15 +334,16 @@ def run_ours(args):
     units = B * T
     rb_ms = sum(sec_ms[f"resblocks{i}"] for i in range(5))
     rb_bytes = sum(RESBLOCK_BYTES_PER_UNIT) * units
-    n_rb_launch = 90
+    n_rb_launch = 72      # 18 x 3 tc_conv launches (stages 1-3) + 9 x 2 fused tc_pair launches (stages 4-5) for the 90 ResBlock convs
     achieved = rb_bytes / (rb_ms * 1e-3) / 1e9
     # per-unit MMACs of the 90 ResBlock convs: 3 products per MAC on the tensor pipe (split-bf16, 2 MMAs
     # per k-step with the stacked operand for N <= 128, 3 for N = 256)
     rb_mmac_per_unit = 41.288e6 * 3 + 20.644e6 + 10.322e6
     roofline = {
         "bound": "hbm",
-        "kernel": "tc_conv_kernel (ResBlock1 dilated convs as tcgen05 implicit GEMMs on split-bf16 operands, 90 launches/step; "
-                  "lrelu + bias + residual + resblock mean fused in the epilogue)",
+        "kernel": "tc_conv_kernel + tc_pair_kernel (the 90 ResBlock1 dilated convs as tcgen05 implicit GEMMs on split-bf16 operands: "
+                  "54 single-conv launches for C >= 64, 18 fused conv1->conv2 launches for C = 32 / 16; lrelu + bias + residual + "
+                  "resblock mean fused in the epilogues)",
         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
         "peak_source": peak_src,
         "bytes_per_launch_avg": rb_bytes / n_rb_launch, "ms_per_launch_avg": rb_ms / n_rb_launch,

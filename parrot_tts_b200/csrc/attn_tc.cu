@@ -5,15 +5,16 @@
 //
 // One CTA = one (batch item, head, 128-query tile), 320 threads:
 //   warp 0      producer: TMA loads of the Q tile and of 64-key K / V tiles (128-byte swizzle) from the split-fp16 qkv rows
-//   warp 1      MMA issuer + TMEM owner:  S = Q.K^T  (operands from shared memory),  O += P.V  (P from TENSOR MEMORY, V from
-//               shared memory as an MN-major operand - no transpose of V anywhere)
-//   warps 2..9  softmax / epilogue: thread = (query row = TMEM lane, half of a tile's keys); scores and probabilities are
+//   warp 1      Q.K^T issuer + TMEM owner:  S = Q.K^T  (both operands from shared memory)
+//   warp 18     P.V issuer:  O += P.V  (P from TENSOR MEMORY, V from shared memory as an MN-major operand - no transpose of V)
+//   warps 2..17 softmax / epilogue: thread = (query row = TMEM lane, half of a tile's keys); scores and probabilities are
 //               double-buffered in tensor memory so the tensor pipe and the exponentials overlap
 // Products are evaluated on split-fp16 operands (x = hi + lo): a.b ~ a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, with [b_hi; b_lo]
 // stacked along N so that a k-step costs two MMAs; accumulation is fp32 in TMEM.
 // Softmax is exact two-pass (pass 1: row maximum and denominator; pass 2: normalised probabilities -> P.V), which keeps the
 // reference's order of operations (normalise, then multiply by V) and needs no rescaling of the output accumulator.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "pb_tte.cuh"
 #include "pb_umma.cuh"
@@ -25,7 +26,7 @@ namespace {
 constexpr int AT_PARTS = 4;      // softmax warps per TMEM lane quarter: each takes 64 / AT_PARTS keys of a tile
 constexpr int AT_KP = 64 / AT_PARTS;
 constexpr int AT_SW = 4 * AT_PARTS;  // softmax warps
-constexpr int AT_THREADS = 64 + 32 * AT_SW;  // producer warp, MMA warp, softmax warps
+constexpr int AT_THREADS = 96 + 32 * AT_SW;  // producer warp, Q.K^T issuer, softmax warps, P.V issuer
 constexpr int AT_MQ = 128;       // queries per CTA
 constexpr int AT_NK = 64;        // keys per tile
 constexpr int AT_DH = 128;       // head width (d_model 256 / 2 heads)
@@ -45,6 +46,7 @@ struct AttnParams {
     uint16_t* out;                // split-fp16 rows [B*L][2*D]: head h writes hi at h*128, lo at D + h*128
     int B, L, H, D;
     float scale_log2e;            // (1 / sqrt(d_head)) * log2(e)
+    int ablate;                   // dev only (PB_AT_ABLATE): 1 = skip the exponentials of pass 2, 2 = skip the P stores, 4 = skip the pass-1 exponentials
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -69,7 +71,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
     uint64_t* p_ready = s_free + 2;                // [2] probability buffers
     uint64_t* p_free = p_ready + 2;
     uint64_t* o_full = p_free + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint64_t* s1_full = o_full + 1;                // [4] pass 1: four score buffers (the P / O columns are still unused)
+    uint64_t* s1_free = s1_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s1_free + 4);
     uint32_t* kmask = reinterpret_cast<uint32_t*>(sm + 512);   // [n_tiles][2] validity bits of each tile's keys (L <= 4096)
     float2* stat_x = reinterpret_cast<float2*>(sm + 1024);     // [128] (m, l) exchange buffer for the merge after pass 1
     uint8_t* q_s = sm + 2048;
@@ -90,6 +94,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         for (int s = 0; s < AT_VST; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], AT_SW); mbar_init(&p_ready[s], AT_SW); mbar_init(&p_free[s], 1); }
         mbar_init(o_full, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(&s1_full[s], 1); mbar_init(&s1_free[s], AT_SW); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -141,21 +146,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         const uint32_t id_base = (1u << 4) | ((uint32_t)(AT_MQ >> 4) << 24);
         const uint32_t id_s2 = id_base | ((uint32_t)((2 * AT_NK) >> 3) << 17);
         const uint32_t id_s1 = id_base | ((uint32_t)(AT_NK >> 3) << 17);
-        const uint32_t id_o = id_base | (1u << 16) | ((uint32_t)(AT_DH >> 3) << 17);
-        const uint32_t q_base = smem_u32(q_s), k_base = smem_u32(k_s), v_base = smem_u32(v_s);
+        const uint32_t q_base = smem_u32(q_s), k_base = smem_u32(k_s);
         // K-major, 128-byte swizzle: rows 128 bytes apart, 8-row groups 1024 bytes apart
         const uint64_t kdesc0 = smem_desc(0, 16, 1024, 2, 0);
-        // MN-major, 128-byte swizzle: 64-element MN groups LBO = one 64-key box apart, 8-key groups 1024 bytes apart
-        const uint64_t vdesc0 = smem_desc(0, AT_NK * 128, 1024, 2, 0);
         auto addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3fffu); };
         mbar_wait(q_full, 0);
         tc_fence_after();
-        uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-        // S(g) -> score buffer g & 1 (g counts tiles over both passes); its previous use must have been read
-        auto qk_tile = [&](int g) {
-            const uint32_t sb = (uint32_t)g & 1u, n = (uint32_t)g >> 1;
+        uint32_t ks = 0, kph = 0;
+        // S of tile t of pass 1 -> one of FOUR score buffers (the P / O columns are unused until pass 2), of pass 2 -> one of two;
+        // the buffer's previous use must have been read by the softmax warps
+        auto qk_tile = [&](int pass, int t) {
+            const uint32_t nb = pass == 0 ? 4u : 2u;
+            const uint32_t sb = (uint32_t)t % nb, n = (uint32_t)t / nb;
+            uint64_t* full = pass == 0 ? &s1_full[sb] : &s_full[sb];
+            uint64_t* free_ = pass == 0 ? &s1_free[sb] : &s_free[sb];
             mbar_wait(&k_full[ks], kph);
-            if (n > 0) mbar_wait(&s_free[sb], (n - 1) & 1u);
+            if (n > 0) mbar_wait(free_, (n - 1) & 1u);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t kb = k_base + ks * AT_K_BYTES;
@@ -172,18 +178,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
                         umma_bf16(d, a_lo, bd, id_s1, 1);       // q_lo . k_hi
                         acc = 1;
                     }
-                umma_commit(&s_full[sb]);
+                umma_commit(full);
                 umma_commit(&k_empty[ks]);
             }
             __syncwarp();
             if (++ks == AT_KST) { ks = 0; kph ^= 1; }
         };
-        // ---- pass 1: scores only (row maximum / denominator); the two score buffers keep the tensor pipe ahead of the softmax warps
-        for (int t = 0; t < n_tiles; ++t) qk_tile(t);
-        // ---- pass 2: S(t+1) is issued before P(t).V(t), so it runs while the softmax warps turn S(t) into P(t)
-        qk_tile(n_tiles);
+        // ---- pass 1: scores only (row maximum / denominator), up to four tiles ahead of the softmax warps
+        for (int t = 0; t < n_tiles; ++t) qk_tile(0, t);
+        // every pass-1 buffer must have been read before pass 2 reuses the columns
+        for (int j = 0; j < 4 && j < n_tiles; ++j) {
+            const uint32_t uses = (uint32_t)(n_tiles - j + 3) / 4u;
+            mbar_wait(&s1_free[j], (uses - 1) & 1u);
+        }
+        // ---- pass 2: S(t) runs up to two tiles ahead; P(t).V(t) is issued by its own warp as soon as P(t) is in tensor memory
+        for (int t = 0; t < n_tiles; ++t) qk_tile(1, t);
+    } else if (warp == 2 + AT_SW) {
+        // =========================== P.V issuer ===========================
+        const uint32_t id_o = (1u << 4) | ((uint32_t)(AT_MQ >> 4) << 24) | (1u << 16) | ((uint32_t)(AT_DH >> 3) << 17);
+        const uint32_t v_base = smem_u32(v_s);
+        // MN-major, 128-byte swizzle: 64-element MN groups LBO = one 64-key box apart, 8-key groups 1024 bytes apart
+        const uint64_t vdesc0 = smem_desc(0, AT_NK * 128, 1024, 2, 0);
+        auto addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3fffu); };
+        uint32_t vs = 0, vph = 0;
         for (int t = 0; t < n_tiles; ++t) {
-            if (t + 1 < n_tiles) qk_tile(n_tiles + t + 1);
             const uint32_t pb = (uint32_t)t & 1u, n = (uint32_t)t >> 1;
             mbar_wait(&v_full[vs], vph);
             mbar_wait(&p_ready[pb], n & 1u);
@@ -206,7 +224,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             __syncwarp();
             if (++vs == AT_VST) { vs = 0; vph ^= 1; }
         }
-    } else {
+    } else if (warp >= 2 && warp < 2 + AT_SW) {
         // =========================== softmax / epilogue ===========================
         // thread = (query row, key part): AT_PARTS warps per TMEM lane quarter, each taking AT_KP of a tile's 64 keys
         const int q = warp & 3;                              // TMEM lane quarter of this warp
@@ -231,9 +249,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             const uint32_t w = kmask[2 * t + (part * AT_KP) / 32];
             return (w >> ((part * AT_KP) & 31)) & (AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u));
         };
-        auto load_scores = [&](int g, float* s) {
-            const uint32_t sb = (uint32_t)g & 1u, n = (uint32_t)g >> 1;
-            mbar_wait(&s_full[sb], n & 1u);
+        auto load_scores = [&](int pass, int t, float* s) {
+            const uint32_t nb = pass == 0 ? 4u : 2u;
+            const uint32_t sb = (uint32_t)t % nb, n = (uint32_t)t / nb;
+            mbar_wait(pass == 0 ? &s1_full[sb] : &s_full[sb], n & 1u);
             tc_fence_after();
             uint32_t a[AT_KP], c[AT_KP];
             const uint32_t base = tmem + lane_off + TM_S + sb * 128u + (uint32_t)(part * AT_KP);
@@ -244,13 +263,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             for (int i = 0; i < AT_KP; ++i) s[i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[sb]);         // the buffer may take the scores of tile g + 2
+            if (lane == 0) mbar_arrive(pass == 0 ? &s1_free[sb] : &s_free[sb]);   // the buffer may take another tile's scores
         };
         // ---- pass 1: running maximum and denominator over this thread's keys
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
             float s[AT_KP];
-            load_scores(t, s);
+            load_scores(0, t, s);
             float tm = m;
 #pragma unroll
             for (int i = 0; i < AT_KP; ++i)
@@ -259,7 +278,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
                 float sum = 0.f;
 #pragma unroll
                 for (int i = 0; i < AT_KP; ++i)
-                    if ((mk >> i) & 1u) sum += exp2f((s[i] - tm) * c2);
+                    if ((mk >> i) & 1u) sum += (p.ablate & 4) ? 1.f : exp2f((s[i] - tm) * c2);
                 l = l * exp2f((m - tm) * c2) + sum;     // m = -inf before the first valid key: exp2(-inf) = 0
                 m = tm;
             }
@@ -287,9 +306,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
             float s[AT_KP];
-            load_scores(n_tiles + t, s);
+            load_scores(1, t, s);
 #pragma unroll
-            for (int i = 0; i < AT_KP; ++i) s[i] = ((mk >> i) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f;
+            for (int i = 0; i < AT_KP; ++i) s[i] = (p.ablate & 1) ? 0.01f : (((mk >> i) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f);
             uint32_t hi[AT_KP / 2], lo[AT_KP / 2];
 #pragma unroll
             for (int i = 0; i < AT_KP / 2; ++i) {
@@ -303,9 +322,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             if (n > 0) mbar_wait(&p_free[pb], (n - 1) & 1u);   // P(t-2) consumed by its MMAs
             tc_fence_after();
             const uint32_t pbase = tmem + lane_off + TM_P + pb * 64u + (uint32_t)(part * (AT_KP / 2));
-            if (AT_KP == 32) { tmem_st16(pbase, hi); tmem_st16(pbase + 32, lo); }
-            else { tmem_st8(pbase, hi); tmem_st8(pbase + 32, lo); }
-            tmem_st_wait();
+            if (!(p.ablate & 2)) {
+                if (AT_KP == 32) { tmem_st16(pbase, hi); tmem_st16(pbase + 32, lo); }
+                else { tmem_st8(pbase, hi); tmem_st8(pbase + 32, lo); }
+                tmem_st_wait();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[pb]);
@@ -382,6 +403,7 @@ int launch_attention_tc(const uint16_t* qkv, const uint8_t* key_valid, uint16_t*
     AttnParams p{};
     p.key_valid = key_valid; p.out = out; p.B = B; p.L = L; p.H = H; p.D = D;
     p.scale_log2e = sqrtf(1.0f / (float)AT_DH) * 1.4426950408889634f;
+    { static const int abl = getenv("PB_AT_ABLATE") ? atoi(getenv("PB_AT_ABLATE")) : 0; p.ablate = abl; }
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
