@@ -43,6 +43,7 @@ struct TcConvArgs {
 
 int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)
 size_t tc_packed_weight_bytes(int Cin, int N, int K);
+bool tc_use_cluster(int Cin, int N, int K);     // layer runs on CTA pairs (cta_group::2); decides the packed weight layout
 // torch Conv1d weight f32 [Cout][Cin][K]  -> packed split-bf16 B operand (N = Cout)
 int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt = 0);
 // torch ConvTranspose1d weight f32 [Cin][Cout][Kt], stride U, padding (Kt-U)/2 -> 3-tap polyphase operand (N = U*Cout)

@@ -54,6 +54,7 @@ struct TcParams {
     int tanh_out;
     uint32_t idesc, idesc_stack;
     int single_pass, stack, acc_cols;
+    int cluster;                         // 1: CTA pairs (cta_group::2): M = 256 per pair, each CTA streams half of the weight rows
     int fmt;                             // split storage / MMA operand type: 0 bf16, 1 fp16
     int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
     int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads
@@ -70,17 +71,25 @@ struct TcParams {
 //   MODE 0:              D += A_hi.B_hi^T                                               (plain bf16)
 // ------------------------------------------------------------------------------------------------------------------------
 struct MmaCtx {
-    uint64_t *full_a, *empty_a, *full_b, *empty_b, *acc_full, *acc_empty, *b_res_full;
+    uint64_t *full_a, *empty_a, *full_b, *empty_b, *acc_full, *acc_empty, *b_res_full, *peer_a, *peer_b;
     uint32_t sm_base, tmem_base;
+    int cta0, nctas;      // first tile and tile stride of this CTA (pair)
 };
 
-template <int MODE>
+template <int MODE, bool CL>
 __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi_word, uint32_t b_hi_word, uint32_t a_k, uint32_t b_k,
                                             uint32_t lo_step, uint32_t lo_rows_step, uint32_t idesc, uint32_t idesc_stack,
                                             uint32_t accumulate) {
     const uint64_t da_hi = ((uint64_t)a_hi_word << 32) | a_k;
     const uint64_t db_hi = ((uint64_t)b_hi_word << 32) | b_k;
-    if (MODE == 2) {
+    if (CL) {
+        // CTA pair, M = 256.  Operand R1 (N = 256 over the pair: rank 0 holds the 128 hi rows, rank 1 the 128 lo rows) gives
+        // a_hi.[w_hi; w_lo]; operand R2 (N = 128: rank r holds hi rows 64r..64r+63, K-half stride 1 KB) gives a_lo.w_hi.
+        // lo_rows_step carries R2's offset inside the k-step, idesc_stack the N = 256 descriptor.
+        umma2_bf16(d_tmem, da_hi, db_hi, idesc_stack, accumulate);
+        const uint64_t db_r2 = ((uint64_t)b_hi_word << 32) | (b_k + lo_rows_step);   // lo_rows_step = R2 offset + the LBO change (2 KB -> 1 KB)
+        umma2_bf16(d_tmem, ((uint64_t)a_hi_word << 32) | (a_k + lo_step), db_r2, idesc, 1);
+    } else if (MODE == 2) {
         umma_bf16(d_tmem, da_hi, db_hi, idesc_stack, accumulate);
         umma_bf16(d_tmem, ((uint64_t)a_hi_word << 32) | (a_k + lo_step), db_hi, idesc, 1);
     } else {
@@ -92,8 +101,9 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi_word,
     }
 }
 
-template <int KSTEPS, int MODE>
+template <int KSTEPS, int MODE, bool CL = false>
 __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) {
+    auto commit_ = [](uint64_t* bar) { if (CL) umma2_commit(bar); else umma_commit(bar); };
     if (p.res_blocks > 0) { mbar_wait(mc.b_res_full, 0); tc_fence_after(); }
     uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, acc_s = 0, acc_ph = 0;
     // everything the inner loops need, read from the parameter block once
@@ -108,23 +118,28 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
     const uint32_t a_desc_lo = (uint32_t)smem_desc(0, 16, (uint32_t)p.a_sbo, (uint32_t)p.a_layout, 0);
     // B k-step = [K half 0: hi rows, lo rows][K half 1: hi rows, lo rows]: LBO (K-half stride) = 2*NT*16 bytes, the lo rows
     // start NT*16 bytes after the hi rows, so [hi; lo] is also ONE operand of 2*NT rows
-    const uint32_t b_desc_hi = (uint32_t)(smem_desc(0, (uint32_t)p.NT * 32u, 128, 0, 0) >> 32);
-    const uint32_t b_desc_lo = (uint32_t)smem_desc(0, (uint32_t)p.NT * 32u, 128, 0, 0);
+    // (CTA pair: a k-step of this CTA is [R1: 2 K halves x NT rows][R2: 2 K halves x NT/2 rows] = 6 KB at NT = 128; R1's K-half
+    //  stride is NT*16 bytes, R2's NT/2*16 - the difference of the two descriptor low words is folded into lo_rows_step)
+    const uint32_t b_lbo = CL ? (uint32_t)p.NT * 16u : (uint32_t)p.NT * 32u;
+    const uint32_t b_desc_hi = (uint32_t)(smem_desc(0, b_lbo, 128, 0, 0) >> 32);
+    const uint32_t b_desc_lo = (uint32_t)smem_desc(0, b_lbo, 128, 0, 0);
     const uint32_t tap_step = (uint32_t)(p.D * p.a_row_bytes) >> 4;   // in 16-byte units
     const uint32_t lo_step = (uint32_t)p.lo_off >> 4;
-    const uint32_t lo_rows_step = (uint32_t)p.NT;                    // NT*16 bytes
-    const uint32_t kstep_step = (uint32_t)p.NT * 4u;                 // 2 planes x 2 K halves x NT x 16 bytes
+    const uint32_t lo_rows_step = CL ? ((uint32_t)smem_desc(0, (uint32_t)p.NT * 8u, 128, 0, 0) - b_desc_lo) + (uint32_t)p.NT * 2u
+                                     : (uint32_t)p.NT;               // NT*16 bytes (pair: R2 starts NT*32 bytes into the k-step)
+    const uint32_t kstep_step = CL ? (uint32_t)p.NT * 3u : (uint32_t)p.NT * 4u;   // k-step size in 16-byte units
     const uint32_t block_step = kstep_step * KSTEPS;
     const uint32_t a_base0 = mc.sm_base + p.smem_a_off, b_res0 = mc.sm_base + p.smem_b_off, b_ring0 = mc.sm_base + p.smem_ring_off;
-    int nt = blockIdx.x % n_tiles_n;
-    const int nt_adv = (int)(gridDim.x % (unsigned)n_tiles_n);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int nt = mc.cta0 % n_tiles_n;
+    const int nt_adv = mc.nctas % n_tiles_n;
+    for (int tile = mc.cta0; tile < p.total_tiles; tile += mc.nctas) {
         mbar_wait(&mc.acc_empty[acc_s], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = mc.tmem_base + acc_s * acc_cols;
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&mc.full_a[a_s], a_ph);
+            if (CL) mbar_wait(&mc.peer_a[a_s], a_ph);      // the peer CTA's half of the A rows has landed too
             tc_fence_after();
             // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address advanced by
             // whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K views of one staged
@@ -144,7 +159,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
                     for (int j = 0; j < (skip_mma ? 0 : j0); ++j) {
 #pragma unroll
                         for (int ks = 0; ks < KSTEPS; ++ks) {
-                            issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_tap + 2u * ks, b_tap + kstep_step * ks, lo_step, lo_rows_step,
+                            issue_kstep<MODE, CL>(d_tmem, a_desc_hi, b_desc_hi, a_tap + 2u * ks, b_tap + kstep_step * ks, lo_step, lo_rows_step,
                                               idesc, idesc_stack, acc);
                             acc = 1;
                         }
@@ -152,8 +167,8 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
                         b_tap += block_step;
                     }
                     if (j0 == K) {
-                        umma_commit(&mc.empty_a[a_s]);
-                        if (last_c) umma_commit(&mc.acc_full[acc_s]);
+                        commit_(&mc.empty_a[a_s]);
+                        if (last_c) commit_(&mc.acc_full[acc_s]);
                     }
                 }
                 __syncwarp();
@@ -162,6 +177,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
             for (int j = j0; j < K; ++j) {
                 for (int kb = 0; kb < nsub; ++kb) {
                     mbar_wait(&mc.full_b[b_s], b_ph);
+                    if (CL) mbar_wait(&mc.peer_b[b_s], b_ph);
                     tc_fence_after();
                     if (elect_one()) {
                         uint32_t b_k = b_desc_lo | (((b_ring0 + b_s * b_sub_bytes) >> 4) & 0x3fffu);
@@ -170,22 +186,22 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
                         if (kpb == KSTEPS) {
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks) {
-                                issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_k + 2u * ks, b_k + kstep_step * ks, lo_step, lo_rows_step,
+                                issue_kstep<MODE, CL>(d_tmem, a_desc_hi, b_desc_hi, a_k + 2u * ks, b_k + kstep_step * ks, lo_step, lo_rows_step,
                                                   idesc, idesc_stack, acc);
                                 acc = 1;
                             }
                         } else {
                             for (int ks = 0; ks < kpb; ++ks) {
-                                issue_kstep<MODE>(d_tmem, a_desc_hi, b_desc_hi, a_k, b_k, lo_step, lo_rows_step, idesc, idesc_stack, acc);
+                                issue_kstep<MODE, CL>(d_tmem, a_desc_hi, b_desc_hi, a_k, b_k, lo_step, lo_rows_step, idesc, idesc_stack, acc);
                                 acc = 1;
                                 a_k += 2u;
                                 b_k += kstep_step;
                             }
                         }
-                        umma_commit(&mc.empty_b[b_s]);
+                        commit_(&mc.empty_b[b_s]);
                         if (j + 1 == K && kb + 1 == nsub) {
-                            umma_commit(&mc.empty_a[a_s]);
-                            if (last_c) umma_commit(&mc.acc_full[acc_s]);
+                            commit_(&mc.empty_a[a_s]);
+                            if (last_c) commit_(&mc.acc_full[acc_s]);
                         }
                     }
                     __syncwarp();
@@ -202,7 +218,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-template <bool RES, bool ACC>
+template <bool RES, bool ACC, bool CL>
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -216,17 +232,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     uint64_t* acc_empty = acc_full + TC_MAX_ACC;
     uint64_t* b_res_full = acc_full + 2 * TC_MAX_ACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2 * TC_MAX_ACC + 2);
+    uint64_t* peer_a = acc_full + 2 * TC_MAX_ACC + 4;        // leader CTA of a pair: the peer's A tile / weight half has landed
+    uint64_t* peer_b = peer_a + TC_MAX_STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sm_base = smem_u32(sm);
+    // CTA pair (cta_group::2): rank 0 issues the MMAs for both CTAs; tiles are handed out per pair
+    const uint32_t rank = CL ? cluster_ctarank() : 0u;
+    const int cta0 = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nctas = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int ROWS_PER_TILE = CL ? 2 * TC_M : TC_M;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
         for (int s = 0; s < TC_MAX_STAGES; ++s) {
             mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
             mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1);
+            mbar_init(&peer_a[s], 1); mbar_init(&peer_b[s], 1);
         }
-        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        // accumulator release: 4 epilogue warps per CTA; the leader of a pair also collects the peer's 4
+        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CL ? 8 : 4); }
         mbar_init(b_res_full, 1);
         fence_mbar_init();
     }
@@ -237,9 +262,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     // programmatic dependent launch: the next kernel of the stream may become resident and run its prologue (barriers, TMEM,
     // weights) while this grid drains; it touches activations only after its own griddepcontrol.wait
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 2) { if (CL) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); }
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -265,11 +291,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         asm volatile("griddepcontrol.wait;" ::: "memory");   // activations are written by the previous kernel of the stream
         uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;      // ring slot + phase counters (no divisions in the loops)
         const int nsub = p.ksteps / p.kpb;
-        int b = blockIdx.x / tiles_per_b, rem = blockIdx.x - b * tiles_per_b;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int b = cta0 / tiles_per_b, rem = cta0 - b * tiles_per_b;
+        for (int tile = cta0; tile < p.total_tiles; tile += nctas) {
             int tt = rem, nt = 0;
             if (p.n_tiles_n != 1) { tt = rem / p.n_tiles_n; nt = rem - tt * p.n_tiles_n; }
-            const int row0 = tt * TC_M - p.pad;
+            const int row0 = tt * ROWS_PER_TILE + (int)rank * TC_M - p.pad;
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&empty_a[a_s], a_ph ^ 1);
                 if (elect_one()) {
@@ -287,32 +313,58 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                 const int blk0 = (nt * p.nchunks + c) * p.K;
                 int j0 = p.res_blocks - blk0;                 // taps below j0 are resident
                 j0 = j0 < 0 ? 0 : (j0 > p.K ? p.K : j0);
-                const uint8_t* wsrc = p.w + (size_t)(blk0 + j0) * p.b_block_bytes;
+                // (CTA pair: a sub-block is stored as [rank 0 half][rank 1 half]; b_sub_bytes is one half)
+                const uint8_t* wsrc = p.w + (size_t)(blk0 + j0) * p.b_block_bytes + (CL ? (size_t)rank * p.b_sub_bytes : 0);
+                const size_t sub_stride = CL ? 2 * (size_t)p.b_sub_bytes : (size_t)p.b_sub_bytes;
                 for (int jb = 0; jb < (p.K - j0) * nsub; ++jb) {
                     mbar_wait(&empty_b[b_s], b_ph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&full_b[b_s], (uint32_t)p.b_sub_bytes);
-                        bulk_load_1d(sm + p.smem_ring_off + b_s * p.b_sub_bytes, wsrc + (size_t)jb * p.b_sub_bytes, (uint32_t)p.b_sub_bytes,
+                        bulk_load_1d(sm + p.smem_ring_off + b_s * p.b_sub_bytes, wsrc + (size_t)jb * sub_stride, (uint32_t)p.b_sub_bytes,
                                      &full_b[b_s]);
                     }
                     __syncwarp();
                     if (++b_s == (uint32_t)p.n_b_stages) { b_s = 0; b_ph ^= 1; }
                 }
             }
-            rem += (int)gridDim.x;
+            rem += nctas;
             while (rem >= tiles_per_b) { rem -= tiles_per_b; ++b; }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        MmaCtx mc{full_a, empty_a, full_b, empty_b, acc_full, acc_empty, b_res_full, sm_base, tmem_base};
-        switch (p.ksteps * 4 + (p.single_pass ? 0 : (p.stack ? 2 : 1))) {
-            case 1 * 4 + 2: mma_issuer<1, 2>(p, mc); break;
-            case 2 * 4 + 2: mma_issuer<2, 2>(p, mc); break;
-            case 4 * 4 + 2: mma_issuer<4, 2>(p, mc); break;
-            case 4 * 4 + 1: mma_issuer<4, 1>(p, mc); break;
-            case 1 * 4 + 0: mma_issuer<1, 0>(p, mc); break;
-            case 2 * 4 + 0: mma_issuer<2, 0>(p, mc); break;
-            default: mma_issuer<4, 0>(p, mc); break;
+        MmaCtx mc{full_a, empty_a, full_b, empty_b, acc_full, acc_empty, b_res_full, peer_a, peer_b, sm_base, tmem_base, cta0, nctas};
+        if (CL) {
+            if (rank == 0) {
+                mma_issuer<4, 1, true>(p, mc);
+            } else {
+                // peer CTA: relay "my half has landed" to the leader, in the leader's consumption order
+                uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;
+                const int nsub = p.ksteps / p.kpb;
+                for (int tile = cta0; tile < p.total_tiles; tile += nctas) {
+                    for (int c = 0; c < p.nchunks; ++c) {
+                        mbar_wait(&full_a[a_s], a_ph);
+                        if (lane == 0) mbar_arrive_remote(&peer_a[a_s], 0);
+                        __syncwarp();
+                        if (++a_s == (uint32_t)p.n_a_stages) { a_s = 0; a_ph ^= 1; }
+                        for (int jb = 0; jb < p.K * nsub; ++jb) {
+                            mbar_wait(&full_b[b_s], b_ph);
+                            if (lane == 0) mbar_arrive_remote(&peer_b[b_s], 0);
+                            __syncwarp();
+                            if (++b_s == (uint32_t)p.n_b_stages) { b_s = 0; b_ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else {
+            switch (p.ksteps * 4 + (p.single_pass ? 0 : (p.stack ? 2 : 1))) {
+                case 1 * 4 + 2: mma_issuer<1, 2>(p, mc); break;
+                case 2 * 4 + 2: mma_issuer<2, 2>(p, mc); break;
+                case 4 * 4 + 2: mma_issuer<4, 2>(p, mc); break;
+                case 4 * 4 + 1: mma_issuer<4, 1>(p, mc); break;
+                case 1 * 4 + 0: mma_issuer<1, 0>(p, mc); break;
+                case 2 * 4 + 0: mma_issuer<2, 0>(p, mc); break;
+                default: mma_issuer<4, 0>(p, mc); break;
+            }
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
@@ -322,7 +374,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         asm volatile("griddepcontrol.wait;" ::: "memory");   // residual / running-sum reads and the output stores depend on the previous kernel
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int grp = (warp - 4) >> 2;              // epilogue group: takes this CTA's tiles grp, grp + n_groups, ...
-        const int tile_stride = (int)gridDim.x * p.n_groups;
+        const int tile_stride = nctas * p.n_groups;
         const int row = q * 32 + lane;
         const int Lout = p.L * p.U;
         const size_t out_pitch = (size_t)2 * p.out_C;
@@ -341,7 +393,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             int tt = c.rem;
             c.nt = 0;
             if (n_tiles_n != 1) { tt = c.rem / n_tiles_n; c.nt = c.rem - tt * n_tiles_n; }
-            const int t = tt * TC_M + row;
+            const int t = tt * ROWS_PER_TILE + (int)rank * TC_M + row;
             c.row_ok = t < p.L;
             c.orow0 = t * p.U;
             c.row_el = ((size_t)c.b * Lout + c.orow0) * out_pitch;
@@ -388,7 +440,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             }
         };
 
-        int tile = blockIdx.x + grp * (int)gridDim.x, n0 = 0;
+        int tile = cta0 + grp * nctas, n0 = 0;
         uint32_t acc_i = (uint32_t)grp;                   // local tile counter: this group sees i = grp + k*n_groups
         const uint32_t acc_mask = (uint32_t)p.n_acc - 1u, acc_shift = (uint32_t)__ffs(p.n_acc) - 1u;   // n_acc is a power of two
         TileCtx cur;
@@ -435,7 +487,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
             if (n0n == 0) {                            // accumulator fully read: hand it back before the arithmetic
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[as]);   // one arrival per epilogue warp
+                if (lane == 0) {                              // one arrival per epilogue warp, at the MMA issuer's CTA
+                    if (CL && rank != 0) mbar_arrive_remote(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
+                }
             }
             if (cur.row_ok && !(p.ablate & 32)) {
                 const float4* bp = reinterpret_cast<const float4*>(bias_s + co);
@@ -507,9 +561,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
 
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();          // no CTA of the pair exits (or frees TMEM) while the other may still signal it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (CL) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -533,7 +588,21 @@ static int tc_cin_tile(int Cin) {
     return 0;
 }
 
-size_t tc_packed_weight_bytes(int Cin, int N, int K) { return (size_t)Cin * N * K * 4; }
+bool tc_use_cluster(int Cin, int N, int K);
+// split 16-bit hi + lo = 4 bytes per weight; the CTA-pair layout stores the hi rows a second time (operand R2): 6 bytes
+size_t tc_packed_weight_bytes(int Cin, int N, int K) { return (size_t)Cin * N * K * (tc_use_cluster(Cin, N, K) ? 6 : 4); }
+
+// CTA pairs (cta_group::2) for the wide layers whose weights cannot stay resident: M = 256 per pair, each CTA streams (and
+// reads) half of the weight rows - halves the L2 -> SM weight traffic and the B-operand shared-memory traffic that bound
+// the 128 / 256-channel layers.  A pure function of the layer shape: the packed weight layout depends on it.
+// EXPERIMENTAL, off unless PB_TC_CLUSTER=1: parity-green (every vocoder / TTE GPU test passes with it), but measured slower
+// than the single-CTA path on B200 (stage 1: 2.23 vs 1.75 ms, stage 2: 2.28 vs 1.76 ms per 8 x 1024 units) - the leader waits
+// on a relayed "peer half landed" signal per ring slot and issues for both CTAs; kept as the base for a TMA-multicast version.
+bool tc_use_cluster(int Cin, int N, int K) {
+    static const bool on = getenv("PB_TC_CLUSTER") != nullptr && atoi(getenv("PB_TC_CLUSTER")) != 0;
+    if (!on) return false;
+    return Cin % 64 == 0 && tc_n_tile(N) == 128 && (size_t)Cin * N * K * 4 > 160 * 1024;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -592,12 +661,18 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.lo_off = a.Cin >= 64 ? p.a_tile_bytes : (a.Cin == 32 ? 64 : 32);
     p.a_layout = cin_t == 16 ? 4 : 2;
     p.a_sbo = 8 * p.a_row_bytes;
+    p.cluster = tc_use_cluster(a.Cin, a.N, a.K) ? 1 : 0;      // (always the 3-product form: the packed layout is the pair layout)
     p.b_block_bytes = 2 * p.ksteps * NT * 32;           // one (n tile, channel chunk, tap): ksteps x {hi, lo} planes
     p.kpb = 32768 / (2 * NT * 32);                       // k-steps per streamed sub-block (<= 32 KB: 6+ MMAs per barrier round trip)
     if (p.kpb < 1) p.kpb = 1;
     if (p.kpb > p.ksteps) p.kpb = p.ksteps;
     while (p.ksteps % p.kpb) --p.kpb;
     p.b_sub_bytes = p.kpb * 2 * NT * 32;
+    if (p.cluster) {      // one block per ring slot; a block is [rank 0: ksteps x (R1 + R2)][rank 1: ...], R1 + R2 = NT*48 bytes
+        p.kpb = p.ksteps;
+        p.b_sub_bytes = p.ksteps * NT * 48;
+        p.b_block_bytes = 2 * p.b_sub_bytes;
+    }
     p.total_blocks = p.n_tiles_n * p.nchunks * a.K;
     p.w_total_bytes = p.total_blocks * p.b_block_bytes;
     p.smem_bias_off = 1024;
@@ -616,7 +691,17 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     // wider layers run one CTA per SM with up to 3 epilogue groups (PB_TC_2CTA=0/1 forces either, dev switch)
     static const int force_2cta = getenv("PB_TC_2CTA") ? atoi(getenv("PB_TC_2CTA")) : -1;
     const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
-    if (want_2cta && budget(TC_SMEM_HALF) >= w_all + 3u * (uint32_t)p.a_stage_bytes) {
+    if (p.cluster) {
+        const uint32_t bud = budget(TC_SMEM_LIMIT);
+        p.res_blocks = 0;
+        p.n_a_stages = 2;
+        uint32_t left = bud - 2u * (uint32_t)p.a_stage_bytes;
+        p.n_b_stages = (int)(left / (uint32_t)p.b_sub_bytes);
+        if (p.n_b_stages > TC_MAX_STAGES) p.n_b_stages = TC_MAX_STAGES;
+        left -= (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
+        p.n_a_stages += (int)(left / (uint32_t)p.a_stage_bytes);
+        PB_REQUIRE(p.n_b_stages >= 2, PB_ERR_INVALID, "tc_conv: tile does not fit in shared memory (Cin=%d N=%d K=%d D=%d)", a.Cin, a.N, a.K, a.D);
+    } else if (want_2cta && budget(TC_SMEM_HALF) >= w_all + 3u * (uint32_t)p.a_stage_bytes) {
         ctas_per_sm = 2;
         p.res_blocks = p.total_blocks; b_res_bytes = w_all;
         p.n_a_stages = (int)((budget(TC_SMEM_HALF) - w_all) / (uint32_t)p.a_stage_bytes);
@@ -651,7 +736,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.smem_ring_off = p.smem_b_off + b_res_bytes;
     const uint32_t smem_bytes = p.smem_ring_off + ring_bytes + 1024;
     PB_REQUIRE(smem_bytes <= (ctas_per_sm == 2 ? TC_SMEM_HALF : TC_SMEM_LIMIT), PB_ERR_INVALID, "tc_conv: shared memory plan %u exceeds the limit", smem_bytes);
-    p.tiles_t = (int)ceil_div(a.L, TC_M);
+    p.tiles_t = (int)ceil_div(a.L, p.cluster ? 2 * TC_M : TC_M);
     const int64_t total = (int64_t)a.B * p.tiles_t * p.n_tiles_n;
     PB_REQUIRE(total < (1LL << 31), PB_ERR_INVALID, "tc_conv: too many tiles");
     p.total_tiles = (int)total;
@@ -662,7 +747,11 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.idesc_stack = (1u << 4) | ab_fmt | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     p.fmt = a.fmt;
     p.single_pass = a.single_pass;
-    p.stack = (!a.single_pass && NT <= 128) ? 1 : 0;
+    p.stack = ((!a.single_pass && NT <= 128) || p.cluster) ? 1 : 0;
+    if (p.cluster) {      // M = 256 over the pair
+        p.idesc = (1u << 4) | ab_fmt | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((2 * TC_M) >> 4) << 24);
+        p.idesc_stack = (1u << 4) | ab_fmt | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)((2 * TC_M) >> 4) << 24);
+    }
     p.acc_cols = p.stack ? 2 * NT : NT;
     p.n_acc = (512 / ctas_per_sm) / p.acc_cols;
     if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
@@ -691,31 +780,52 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         int dev = 0;
         PB_CUDA(cudaGetDevice(&dev));
         PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
         attr_set = true;
     }
-    const int grid = p.total_tiles < n_sm * ctas_per_sm ? p.total_tiles : n_sm * ctas_per_sm;
+    int grid = p.total_tiles < n_sm * ctas_per_sm ? p.total_tiles : n_sm * ctas_per_sm;
+    if (p.cluster) grid = 2 * (p.total_tiles < n_sm / 2 ? p.total_tiles : n_sm / 2);      // CTA pairs
     {
         static const bool dbg = getenv("PB_TC_DEBUG") != nullptr;
         if (dbg)
-            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d groups=%d\n",
+            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d groups=%d cluster=%d\n",
                     a.Cin, a.N, NT, a.K, a.D, a.L, a.B, p.total_tiles, grid, ctas_per_sm, smem_bytes, p.n_a_stages, p.a_stage_bytes, p.res_blocks,
-                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc, p.n_groups);
+                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc, p.n_groups, p.cluster);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     static const bool no_pdl = getenv("PB_TC_NO_PDL") != nullptr;
-    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-    if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true>, xmap, p));
-    else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false>, xmap, p));
-    else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true>, xmap, p));
-    else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false>, xmap, p));
+    if (!no_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.cluster) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    if (p.cluster) {
+        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, true>, xmap, p));
+        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, true>, xmap, p));
+        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, true>, xmap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, true>, xmap, p));
+    } else {
+        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, false>, xmap, p));
+        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, false>, xmap, p));
+        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, false>, xmap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, false>, xmap, p));
+    }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -733,6 +843,7 @@ struct PackDev {
     // transposed conv: N = U*Cout, 3 taps; source tap index for (phase, tap) or -1
     int convtr, Cout, Kt, U;
     int fmt;
+    int cluster;      // CTA-pair layout: block = [rank 0: ksteps x 4 KB][rank 1: ...], rank = (n % NT) / (NT / 2)
 };
 
 __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
@@ -768,16 +879,32 @@ __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
         // block base (in 16-bit elements): block index * (2 planes * ksteps * NT * 16); inside a k-step the K half is outermost,
         // then the plane, so that rows [0, NT) = hi and [NT, 2NT) = lo of ONE 2NT-row operand with LBO = 2*NT*16 bytes
         const int64_t blk = ((int64_t)(nt * d.nchunks + c) * d.K + j) * (2LL * d.ksteps * d.NT * 16);
-        const int64_t kstep = blk + (int64_t)ks * (2LL * d.NT * 16);
-        const int64_t within = ((int64_t)ng * 8 + r) * 8 + e;
-        out[kstep + (int64_t)(kc * 2 + 0) * d.NT * 8 + within] = hi;
-        out[kstep + (int64_t)(kc * 2 + 1) * d.NT * 8 + within] = lo;
+        if (!d.cluster) {
+            const int64_t kstep = blk + (int64_t)ks * (2LL * d.NT * 16);
+            const int64_t within = ((int64_t)ng * 8 + r) * 8 + e;
+            out[kstep + (int64_t)(kc * 2 + 0) * d.NT * 8 + within] = hi;
+            out[kstep + (int64_t)(kc * 2 + 1) * d.NT * 8 + within] = lo;
+        } else {
+            // pair layout, in 16-bit elements: block = [rank][k-step][R1: 2 K halves x NT rows x 8][R2: 2 K halves x NT/2 rows x 8]
+            //   rank 0: R1 = hi rows 0..NT-1, R2 = hi rows 0..NT/2-1;   rank 1: R1 = lo rows 0..NT-1, R2 = hi rows NT/2..NT-1
+            const int half = d.NT / 2;
+            const int nn = ng * 8 + r;
+            const int64_t ks_el = (int64_t)d.NT * 24;                        // R1 (NT*16) + R2 (NT*8) elements per k-step
+            const int64_t rank_el = (int64_t)d.ksteps * ks_el;
+            const int64_t blk2 = ((int64_t)(nt * d.nchunks + c) * d.K + j) * (2 * rank_el);
+            const int64_t r1 = (int64_t)ks * ks_el + ((int64_t)kc * d.NT + nn) * 8 + e;
+            out[blk2 + r1] = hi;                                             // rank 0, R1
+            out[blk2 + rank_el + r1] = lo;                                   // rank 1, R1
+            const int64_t r2 = (int64_t)ks * ks_el + (int64_t)d.NT * 16 + ((int64_t)kc * half + nn % half) * 8 + e;
+            out[blk2 + (int64_t)(nn / half) * rank_el + r2] = hi;            // R2 of the rank that owns this row
+        }
     }
 }
 
 static int pack_common(PackDev d, uint8_t* packed, cudaStream_t st) {
     d.cin_t = tc_cin_tile(d.Cin);
     d.NT = tc_n_tile(d.N);
+    d.cluster = tc_use_cluster(d.Cin, d.N, d.K) ? 1 : 0;
     PB_REQUIRE(d.cin_t > 0 && d.NT > 0, PB_ERR_INVALID, "tc_pack: unsupported Cin=%d / N=%d", d.Cin, d.N);
     d.ksteps = d.cin_t / 16;
     d.nchunks = d.Cin / d.cin_t;

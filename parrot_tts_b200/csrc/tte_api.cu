@@ -102,10 +102,11 @@ extern "C" int pb_tte_create(const pb_tte_cfg* cfg, pb_tte** out) {
             add_slot(h, p + ".convlayer.conv1.packed", {F, cfg->conv_k1 * D}, false);
             add_slot(h, p + ".convlayer.conv2.packed", {D, cfg->conv_k2 * F}, false);
             if (cfg->gemm_mode == 1) {   // tcgen05 operands (split-fp16, packed by tc_pack_conv_weight): same element count in bytes/4
-                add_slot(h, p + ".attention.qkv_eff.tc", {3 * D, D}, false);
-                add_slot(h, p + ".attention.wo_eff.tc", {D, D}, false);
-                add_slot(h, p + ".convlayer.conv1.tc", {F, cfg->conv_k1 * D}, false);
-                add_slot(h, p + ".convlayer.conv2.tc", {D, cfg->conv_k2 * F}, false);
+                auto tc_floats = [](int Cin, int N, int K) { return (int64_t)(tc_packed_weight_bytes(Cin, N, K) / sizeof(float)); };
+                add_slot(h, p + ".attention.qkv_eff.tc", {tc_floats(D, 3 * D, 1)}, false);
+                add_slot(h, p + ".attention.wo_eff.tc", {tc_floats(D, D, 1)}, false);
+                add_slot(h, p + ".convlayer.conv1.tc", {tc_floats(D, F, cfg->conv_k1)}, false);
+                add_slot(h, p + ".convlayer.conv2.tc", {tc_floats(F, D, cfg->conv_k2)}, false);
             }
         }
     }
@@ -114,7 +115,7 @@ extern "C" int pb_tte_create(const pb_tte_cfg* cfg, pb_tte** out) {
     if (cfg->gemm_mode == 1) {
         const int np = (int)round_up(cfg->n_codes, 256);
         add_slot(h, "head.weight.pad", {np, D}, false);      // zero rows past n_codes
-        add_slot(h, "head.weight.tc", {np, D}, false);
+        add_slot(h, "head.weight.tc", {(int64_t)(tc_packed_weight_bytes(D, np, 1) / sizeof(float))}, false);
         add_slot(h, "head.bias.pad", {np}, false);
     }
     int st = h->arena.reserve(h->arena_bytes);

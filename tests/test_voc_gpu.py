@@ -256,3 +256,28 @@ def test_streamed_chunks_equal_unchunked():
     # a halo shorter than the receptive field must NOT reproduce it (the test would be vacuous otherwise)
     bad = torch.cat([w for _, w in stream_generate(gen, code, spkr, chunk_units=256, halo_units=2)], dim=1)
     assert float((bad - full).abs().max()) > 1e-5
+
+
+def test_cta_pair_path_matches_torch():
+    """The experimental cta_group::2 path of tc_conv (PB_TC_CLUSTER=1, read once per process) in a subprocess: wide conv with
+    streamed weights (C = 128, k = 7, dilation 3, residual) and a wide GEMM (TTE-sized), against torch fp32."""
+    import subprocess
+    import sys
+    code = r'''
+import torch, torch.nn.functional as F
+from parrot_tts_b200 import ops
+g = torch.Generator().manual_seed(5)
+C, L, K, D = 128, 700, 7, 3
+x = torch.randn(2, C, L, generator=g); w = torch.randn(C, C, K, generator=g) / (C * K) ** 0.5
+b = torch.randn(C, generator=g); r = torch.randn(2, C, L, generator=g)
+ref = F.conv1d(x, w, b, dilation=D, padding=(K - 1) * D // 2) + r
+got = ops.conv1d_tc(x.cuda(), w.cuda(), b.cuda(), dilation=D, res=r.cuda()).cpu()
+e1 = float((got - ref).abs().max())
+xm = torch.randn(300, 256, generator=g); wm = torch.randn(768, 256, generator=g) / 16
+e2 = float((ops.linear(xm.cuda(), wm.cuda(), None, mode=1).cpu() - xm @ wm.t()).abs().max())
+print("ERR", e1, e2)
+assert e1 < 1e-4 and e2 < 2e-5, (e1, e2)
+'''
+    env = dict(os.environ, PB_TC_CLUSTER="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
