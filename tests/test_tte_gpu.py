@@ -233,3 +233,34 @@ def test_lit_parrot_checkpoint_roundtrip(tmp_path):
     batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([3])}
     ids_ref, _ = tte_oracle.parrot_infer(sd, batch)
     assert model.infer(_to_dev(batch)) == ids_ref
+
+
+def test_full_size_tensor_core_vs_fp32_path():
+    """BASELINE configs[2] size (32 x 256 chars -> 2048 units): the tcgen05 path (gemm_mode 1) against the fp32 SIMT path
+    (gemm_mode 0) of the same library - durations identical, unit ids identical except at genuine near-ties of the fp32
+    logits (top-2 margin < 1e-4), and at most a handful of those."""
+    cfg = _cfg()
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=0, dur_mode="const8")
+    g = _gen(0)
+    phones = torch.randint(2, VOCAB, (32, 256), generator=g).to(DEV)
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": (torch.arange(32) % NSPK).to(DEV)}
+    out = {}
+    for mode in (0, 1):
+        m = Parrot(cfg, VOCAB, 0)
+        m.load_state_dict(sd, strict=True)
+        m = m.eval().to(DEV)
+        m.gemm_mode = mode
+        logits, _, tgt_mask, log_dur = m(batch, inference=True)
+        out[mode] = (logits, tgt_mask, log_dur)
+        del m
+    assert out[0][0].shape == (32, 2048, 1000)
+    assert torch.equal(out[0][1], out[1][1])                       # same durations -> same target mask
+    assert torch.allclose(out[0][2], out[1][2], atol=1e-5, rtol=0)
+    ids0, ids1 = out[0][0].argmax(-1), out[1][0].argmax(-1)
+    bad = (ids0 != ids1).nonzero()
+    top2 = torch.topk(out[0][0], 2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]
+    assert bad.shape[0] <= 8, f"{bad.shape[0]} id mismatches of {ids0.numel()}"
+    for b, t in bad.tolist():
+        assert float(margin[b, t]) < 1e-4, f"id mismatch at a clear-cut position b={b} t={t} margin={float(margin[b, t])}"
+    assert float((out[0][0] - out[1][0]).abs().max()) < 2e-3
