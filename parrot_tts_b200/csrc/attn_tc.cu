@@ -36,10 +36,14 @@ constexpr uint32_t AT_Q_BYTES = 4 * AT_MQ * 128;          // [hi c0][hi c1][lo c
 constexpr uint32_t AT_K_BYTES = 4 * AT_NK * 128;          // per channel half: [hi rows][lo rows]
 constexpr uint32_t AT_V_BYTES = 4 * AT_NK * 128;          // [Vhi d0][Vhi d1][Vlo d0][Vlo d1], each 64 keys x 128 bytes
 constexpr uint32_t AT_SMEM = 2048 + AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES + 1024;   // = 232448, the 227 KB per-CTA limit
-// tensor memory columns (512): two score buffers, two probability buffers, the output accumulator
-constexpr uint32_t TM_S = 0;      // 2 x 128: [0,64) q_hi.k_hi + q_lo.k_hi, [64,128) q_hi.k_lo
-constexpr uint32_t TM_P = 256;    // 2 x 64:  [0,32) P_hi (64 keys, 2 per column), [32,64) P_lo
-constexpr uint32_t TM_O = 384;    // 128
+// tensor memory columns (512).  Q lives in tensor memory for the whole CTA (copied once with tcgen05.cp), so the Q.K^T MMAs
+// read only K from shared memory (the A-operand reads were 60 % of that kernel's shared-memory traffic).
+constexpr uint32_t TM_S = 0;      // pass 2: one score buffer [0,128): [0,64) q_hi.k_hi + q_lo.k_hi, [64,128) q_hi.k_lo
+                                  // pass 1: three score buffers [0,128) [128,256) [256,384) (the P / O columns are still unused)
+constexpr uint32_t TM_P = 128;    // 2 x 64:  [0,32) P_hi (64 keys, 2 per column), [32,64) P_lo
+constexpr uint32_t TM_O = 256;    // 128
+constexpr uint32_t TM_Q = 384;    // 128: [0,64) Q_hi (8 k-steps x 8 columns), [64,128) Q_lo
+constexpr uint32_t AT_S1 = 3;     // pass-1 score buffers
 
 struct AttnParams {
     const uint8_t* key_valid;     // [B][L] 1 = attend, or null
@@ -155,8 +159,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         uint32_t ks = 0, kph = 0;
         // S of tile t of pass 1 -> one of FOUR score buffers (the P / O columns are unused until pass 2), of pass 2 -> one of two;
         // the buffer's previous use must have been read by the softmax warps
+        // Q: shared memory -> tensor memory, one 128-row x 32-byte k-step per tcgen05.cp; copies and MMAs execute in issue order
+        if (elect_one()) {
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t sd = addr(kdesc0, q_base + (pl * 2 + c) * (AT_MQ * 128) + k4 * 32);
+                        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem + TM_Q + pl * 64 + (c * 4 + k4) * 8), "l"(sd) : "memory");
+                    }
+        }
+        __syncwarp();
         auto qk_tile = [&](int pass, int t) {
-            const uint32_t nb = pass == 0 ? 4u : 2u;
+            const uint32_t nb = pass == 0 ? AT_S1 : 1u;
             const uint32_t sb = (uint32_t)t % nb, n = (uint32_t)t / nb;
             uint64_t* full = pass == 0 ? &s1_full[sb] : &s_full[sb];
             uint64_t* free_ = pass == 0 ? &s1_free[sb] : &s_free[sb];
@@ -171,11 +188,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t a_hi = addr(kdesc0, q_base + (0 * 2 + c) * (AT_MQ * 128) + k4 * 32);
-                        const uint64_t a_lo = addr(kdesc0, q_base + (1 * 2 + c) * (AT_MQ * 128) + k4 * 32);
+                        const uint32_t qa = tmem + TM_Q + (uint32_t)(c * 4 + k4) * 8u;
                         const uint64_t bd = addr(kdesc0, kb + c * (2 * AT_NK * 128) + k4 * 32);
-                        umma_bf16(d, a_hi, bd, id_s2, acc);     // q_hi . [k_hi; k_lo]
-                        umma_bf16(d, a_lo, bd, id_s1, 1);       // q_lo . k_hi
+                        umma_f16_ts(d, qa, bd, id_s2, acc);          // q_hi . [k_hi; k_lo]
+                        umma_f16_ts(d, qa + 64u, bd, id_s1, 1);      // q_lo . k_hi
                         acc = 1;
                     }
                 umma_commit(full);
@@ -187,8 +203,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         // ---- pass 1: scores only (row maximum / denominator), up to four tiles ahead of the softmax warps
         for (int t = 0; t < n_tiles; ++t) qk_tile(0, t);
         // every pass-1 buffer must have been read before pass 2 reuses the columns
-        for (int j = 0; j < 4 && j < n_tiles; ++j) {
-            const uint32_t uses = (uint32_t)(n_tiles - j + 3) / 4u;
+        for (int j = 0; j < (int)AT_S1 && j < n_tiles; ++j) {
+            const uint32_t uses = ((uint32_t)(n_tiles - j) + AT_S1 - 1u) / AT_S1;
             mbar_wait(&s1_free[j], (uses - 1) & 1u);
         }
         // ---- pass 2: S(t) runs up to two tiles ahead; P(t).V(t) is issued by its own warp as soon as P(t) is in tensor memory
@@ -250,7 +266,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             return (w >> ((part * AT_KP) & 31)) & (AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u));
         };
         auto load_scores = [&](int pass, int t, float* s) {
-            const uint32_t nb = pass == 0 ? 4u : 2u;
+            const uint32_t nb = pass == 0 ? AT_S1 : 1u;
             const uint32_t sb = (uint32_t)t % nb, n = (uint32_t)t / nb;
             mbar_wait(pass == 0 ? &s1_full[sb] : &s_full[sb], n & 1u);
             tc_fence_after();
