@@ -38,12 +38,14 @@ constexpr uint32_t AT_V_BYTES = 4 * AT_NK * 128;          // [Vhi d0][Vhi d1][Vl
 constexpr uint32_t AT_SMEM = 2048 + AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES + 1024;   // = 232448, the 227 KB per-CTA limit
 // tensor memory columns (512).  Q lives in tensor memory for the whole CTA (copied once with tcgen05.cp), so the Q.K^T MMAs
 // read only K from shared memory (the A-operand reads were 60 % of that kernel's shared-memory traffic).
-constexpr uint32_t TM_S = 0;      // pass 2: one score buffer [0,128): [0,64) q_hi.k_hi + q_lo.k_hi, [64,128) q_hi.k_lo
-                                  // pass 1: three score buffers [0,128) [128,256) [256,384) (the P / O columns are still unused)
+constexpr uint32_t TM_S = 0;      // score buffers of 64 columns (one per key of the tile; the three products of the split
+                                  // accumulate in place - with Q in tensor memory a 64-wide MMA costs N/2 = 32 cycles, so the
+                                  // stacked [k_hi; k_lo] form would only double the accumulator read-back): 2 in pass 2, 4 in pass 1
 constexpr uint32_t TM_P = 128;    // 2 x 64:  [0,32) P_hi (64 keys, 2 per column), [32,64) P_lo
 constexpr uint32_t TM_O = 256;    // 128
 constexpr uint32_t TM_Q = 384;    // 128: [0,64) Q_hi (8 k-steps x 8 columns), [64,128) Q_lo
-constexpr uint32_t AT_S1 = 3;     // pass-1 score buffers
+constexpr uint32_t AT_S1 = 4;     // pass-1 score buffers (columns [0,256): the P region is still unused)
+constexpr uint32_t AT_S2 = 2;     // pass-2 score buffers (columns [0,128))
 
 struct AttnParams {
     const uint8_t* key_valid;     // [B][L] 1 = attend, or null
@@ -148,7 +150,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         // =========================== MMA issuer ===========================
         // instruction descriptors: D f32, A/B f16; S: N = 128 (stacked) / 64, K-major B; O: N = 128, MN-major B
         const uint32_t id_base = (1u << 4) | ((uint32_t)(AT_MQ >> 4) << 24);
-        const uint32_t id_s2 = id_base | ((uint32_t)((2 * AT_NK) >> 3) << 17);
         const uint32_t id_s1 = id_base | ((uint32_t)(AT_NK >> 3) << 17);
         const uint32_t q_base = smem_u32(q_s), k_base = smem_u32(k_s);
         // K-major, 128-byte swizzle: rows 128 bytes apart, 8-row groups 1024 bytes apart
@@ -173,7 +174,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         }
         __syncwarp();
         auto qk_tile = [&](int pass, int t) {
-            const uint32_t nb = pass == 0 ? AT_S1 : 1u;
+            const uint32_t nb = pass == 0 ? AT_S1 : AT_S2;
             const uint32_t sb = (uint32_t)t % nb, n = (uint32_t)t / nb;
             uint64_t* full = pass == 0 ? &s1_full[sb] : &s_full[sb];
             uint64_t* free_ = pass == 0 ? &s1_free[sb] : &s_free[sb];
@@ -182,16 +183,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t kb = k_base + ks * AT_K_BYTES;
-                const uint32_t d = tmem + TM_S + sb * 128u;
+                const uint32_t d = tmem + TM_S + sb * 64u;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const uint32_t qa = tmem + TM_Q + (uint32_t)(c * 4 + k4) * 8u;
-                        const uint64_t bd = addr(kdesc0, kb + c * (2 * AT_NK * 128) + k4 * 32);
-                        umma_f16_ts(d, qa, bd, id_s2, acc);          // q_hi . [k_hi; k_lo]
-                        umma_f16_ts(d, qa + 64u, bd, id_s1, 1);      // q_lo . k_hi
+                        const uint64_t b_hi = addr(kdesc0, kb + c * (2 * AT_NK * 128) + k4 * 32);
+                        const uint64_t b_lo = addr(kdesc0, kb + c * (2 * AT_NK * 128) + AT_NK * 128 + k4 * 32);
+                        umma_f16_ts(d, qa, b_hi, id_s1, acc);        // q_hi . k_hi
+                        umma_f16_ts(d, qa + 64u, b_hi, id_s1, 1);    // q_lo . k_hi
+                        umma_f16_ts(d, qa, b_lo, id_s1, 1);          // q_hi . k_lo
                         acc = 1;
                     }
                 umma_commit(full);
@@ -266,17 +269,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             return (w >> ((part * AT_KP) & 31)) & (AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u));
         };
         auto load_scores = [&](int pass, int t, float* s) {
-            const uint32_t nb = pass == 0 ? AT_S1 : 1u;
+            const uint32_t nb = pass == 0 ? AT_S1 : AT_S2;
             const uint32_t sb = (uint32_t)t % nb, n = (uint32_t)t / nb;
             mbar_wait(pass == 0 ? &s1_full[sb] : &s_full[sb], n & 1u);
             tc_fence_after();
-            uint32_t a[AT_KP], c[AT_KP];
-            const uint32_t base = tmem + lane_off + TM_S + sb * 128u + (uint32_t)(part * AT_KP);
-            if (AT_KP == 32) { tmem_ld32_nowait(base, a); tmem_ld32_nowait(base + AT_NK, c); }
-            else { tmem_ld16_nowait(base, a); tmem_ld16_nowait(base + AT_NK, c); }
+            uint32_t a[AT_KP];
+            const uint32_t base = tmem + lane_off + TM_S + sb * 64u + (uint32_t)(part * AT_KP);
+            if (AT_KP == 32) tmem_ld32_nowait(base, a); else tmem_ld16_nowait(base, a);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < AT_KP; ++i) s[i] = __uint_as_float(a[i]) + __uint_as_float(c[i]);
+            for (int i = 0; i < AT_KP; ++i) s[i] = __uint_as_float(a[i]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pass == 0 ? &s1_free[sb] : &s_free[sb]);   // the buffer may take another tile's scores
