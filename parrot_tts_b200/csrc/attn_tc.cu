@@ -30,12 +30,13 @@ constexpr int AT_THREADS = 96 + 32 * AT_SW;  // producer warp, Q.K^T issuer, sof
 constexpr int AT_MQ = 128;       // queries per CTA
 constexpr int AT_NK = 64;        // keys per tile
 constexpr int AT_DH = 128;       // head width (d_model 256 / 2 heads)
-constexpr int AT_KST = 3;        // K ring (needed one tile ahead of V: S(t+1) is issued while P(t) is being computed)
-constexpr int AT_VST = 2;        // V ring
+constexpr int AT_KST = 4;        // K ring: 3 stages of their own + the first half of the Q tile's shared memory, free once Q is in TMEM
+constexpr int AT_VST = 3;        // V ring: 2 stages + the second half of the Q tile's shared memory
+// (the kernel is bound by the latency of the K / V tile loads from L2: bytes in flight per SM are what buys throughput)
 constexpr uint32_t AT_Q_BYTES = 4 * AT_MQ * 128;          // [hi c0][hi c1][lo c0][lo c1], each 128 rows x 128 bytes
 constexpr uint32_t AT_K_BYTES = 4 * AT_NK * 128;          // per channel half: [hi rows][lo rows]
 constexpr uint32_t AT_V_BYTES = 4 * AT_NK * 128;          // [Vhi d0][Vhi d1][Vlo d0][Vlo d1], each 64 keys x 128 bytes
-constexpr uint32_t AT_SMEM = 2048 + AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES + 1024;   // = 232448, the 227 KB per-CTA limit
+constexpr uint32_t AT_SMEM = 2048 + AT_Q_BYTES + (AT_KST - 1) * AT_K_BYTES + (AT_VST - 1) * AT_V_BYTES + 1024;   // = 232448, the 227 KB per-CTA limit
 // tensor memory columns (512).  Q lives in tensor memory for the whole CTA (copied once with tcgen05.cp), so the Q.K^T MMAs
 // read only K from shared memory (the A-operand reads were 60 % of that kernel's shared-memory traffic).
 constexpr uint32_t TM_S = 0;      // score buffers of 64 columns (one per key of the tile; the three products of the split
@@ -52,8 +53,15 @@ struct AttnParams {
     uint16_t* out;                // split-fp16 rows [B*L][2*D]: head h writes hi at h*128, lo at D + h*128
     int B, L, H, D;
     float scale_log2e;            // (1 / sqrt(d_head)) * log2(e)
-    int ablate;                   // dev only (PB_AT_ABLATE): 1 = skip the exponentials of pass 2, 2 = skip the P stores, 4 = skip the pass-1 exponentials
+    int ablate;                   // dev only (PB_AT_ABLATE): 1 = skip the exponentials of pass 2, 2 = skip the P stores, 4 = skip the pass-1 exponentials, 8 = skip the MMAs, 16 = skip the K / V loads
 };
+
+// 2^x on the SFU (ex2.approx.ftz: 2 ulp, flushes results below 2^-126 to zero - the probabilities it would lose are < 1e-38)
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -79,12 +87,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
     uint64_t* o_full = p_free + 2;
     uint64_t* s1_full = o_full + 1;                // [4] pass 1: four score buffers (the P / O columns are still unused)
     uint64_t* s1_free = s1_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s1_free + 4);
+    uint64_t* q_done = s1_free + 4;                // Q has been copied to tensor memory: its shared memory may be reused
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_done + 1);
     uint32_t* kmask = reinterpret_cast<uint32_t*>(sm + 512);   // [n_tiles][2] validity bits of each tile's keys (L <= 4096)
     float2* stat_x = reinterpret_cast<float2*>(sm + 1024);     // [128] (m, l) exchange buffer for the merge after pass 1
     uint8_t* q_s = sm + 2048;
     uint8_t* k_s = q_s + AT_Q_BYTES;
-    uint8_t* v_s = k_s + AT_KST * AT_K_BYTES;
+    uint8_t* v_s = k_s + (AT_KST - 1) * AT_K_BYTES;
+    // stage -> shared memory: the last K stage and the last V stage alias the two halves of the Q tile
+    auto k_stage = [&](uint32_t st) { return st + 1 < AT_KST ? k_s + st * AT_K_BYTES : q_s; };
+    auto v_stage = [&](uint32_t st) { return st + 1 < AT_VST ? v_s + st * AT_V_BYTES : q_s + AT_K_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -100,6 +112,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         for (int s = 0; s < AT_VST; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], AT_SW); mbar_init(&p_ready[s], AT_SW); mbar_init(&p_free[s], 1); }
         mbar_init(o_full, 1);
+        mbar_init(q_done, 1);
         for (int s = 0; s < 4; ++s) { mbar_init(&s1_full[s], 1); mbar_init(&s1_free[s], AT_SW); }
         fence_mbar_init();
     }
@@ -123,23 +136,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             for (int t = 0; t < n_tiles; ++t) {
                 const int k0 = t * AT_NK;
                 mbar_wait(&k_empty[ks], kph ^ 1);
+                if (ks + 1 == AT_KST && kph == 0) mbar_wait(q_done, 0);      // first use of the stage that aliases the Q tile
                 if (elect_one()) {
-                    uint8_t* dst = k_s + ks * AT_K_BYTES;
+                    uint8_t* dst = k_stage(ks);
+                    if (p.ablate & 16) mbar_arrive(&k_full[ks]); else {
                     mbar_expect_tx(&k_full[ks], AT_K_BYTES);
                     for (int c = 0; c < 2; ++c)
                         for (int pl = 0; pl < 2; ++pl)   // per channel half: hi rows then lo rows (one stacked 128-row operand)
                             tma_load_3d(dst + (c * 2 + pl) * (AT_NK * 128), &kvmap, pl * C3 + p.D + h * AT_DH + c * 64, k0, b, &k_full[ks]);
+                    }
                 }
                 __syncwarp();
                 if (++ks == AT_KST) { ks = 0; kph ^= 1; }
                 if (pass == 1) {
                     mbar_wait(&v_empty[vs], vph ^ 1);
+                    if (vs + 1 == AT_VST && vph == 0) mbar_wait(q_done, 0);
                     if (elect_one()) {
-                        uint8_t* dst = v_s + vs * AT_V_BYTES;
+                        uint8_t* dst = v_stage(vs);
+                        if (p.ablate & 16) mbar_arrive(&v_full[vs]); else {
                         mbar_expect_tx(&v_full[vs], AT_V_BYTES);
                         for (int pl = 0; pl < 2; ++pl)
                             for (int c = 0; c < 2; ++c)  // [Vhi d0][Vhi d1][Vlo d0][Vlo d1]: 64-wide MN groups
                                 tma_load_3d(dst + (pl * 2 + c) * (AT_NK * 128), &kvmap, pl * C3 + 2 * p.D + h * AT_DH + c * 64, k0, b, &v_full[vs]);
+                        }
                     }
                     __syncwarp();
                     if (++vs == AT_VST) { vs = 0; vph ^= 1; }
@@ -171,6 +190,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
                         const uint64_t sd = addr(kdesc0, q_base + (pl * 2 + c) * (AT_MQ * 128) + k4 * 32);
                         asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem + TM_Q + pl * 64 + (c * 4 + k4) * 8), "l"(sd) : "memory");
                     }
+            umma_commit(q_done);
         }
         __syncwarp();
         auto qk_tile = [&](int pass, int t) {
@@ -182,9 +202,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             if (n > 0) mbar_wait(free_, (n - 1) & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t kb = k_base + ks * AT_K_BYTES;
+                const uint32_t kb = ks + 1 < AT_KST ? k_base + ks * AT_K_BYTES : q_base;
                 const uint32_t d = tmem + TM_S + sb * 64u;
                 uint32_t acc = 0;
+                if (!(p.ablate & 8))
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -226,8 +247,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             mbar_wait(&p_ready[pb], n & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t vb = v_base + vs * AT_V_BYTES;
+                const uint32_t vb = vs + 1 < AT_VST ? v_base + vs * AT_V_BYTES : smem_u32(q_s) + AT_K_BYTES;
                 const uint32_t pa = tmem + TM_P + pb * 64u;
+                if (!(p.ablate & 8))
 #pragma unroll
                 for (int k4 = 0; k4 < AT_NK / 16; ++k4) {
                     const uint64_t b_hi = addr(vdesc0, vb + k4 * (16 * 128));
@@ -288,17 +310,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             const uint32_t mk = tile_mask(t);
             float s[AT_KP];
             load_scores(0, t, s);
+            constexpr uint32_t FULL = AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u);
             float tm = m;
+            if (mk == FULL) {      // every key of the tile is valid (all tiles but the last of an unpadded item): no per-key tests
 #pragma unroll
-            for (int i = 0; i < AT_KP; ++i)
-                if ((mk >> i) & 1u) tm = fmaxf(tm, s[i]);
-            if (tm > -INFINITY) {
+                for (int i = 0; i < AT_KP; ++i) tm = fmaxf(tm, s[i]);
+                const float off = tm * c2;
                 float sum = 0.f;
 #pragma unroll
-                for (int i = 0; i < AT_KP; ++i)
-                    if ((mk >> i) & 1u) sum += (p.ablate & 4) ? 1.f : exp2f((s[i] - tm) * c2);
-                l = l * exp2f((m - tm) * c2) + sum;     // m = -inf before the first valid key: exp2(-inf) = 0
+                for (int i = 0; i < AT_KP; ++i) sum += (p.ablate & 4) ? 1.f : ex2f(fmaf(s[i], c2, -off));
+                l = l * ex2f((m - tm) * c2) + sum;      // m = -inf before the first valid key: 2^-inf = 0
                 m = tm;
+            } else {
+#pragma unroll
+                for (int i = 0; i < AT_KP; ++i)
+                    if ((mk >> i) & 1u) tm = fmaxf(tm, s[i]);
+                if (tm > -INFINITY) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < AT_KP; ++i)
+                        if ((mk >> i) & 1u) sum += ex2f((s[i] - tm) * c2);
+                    l = l * ex2f((m - tm) * c2) + sum;
+                    m = tm;
+                }
             }
         }
         // merge the key parts of every row through one 1 KB exchange buffer: parts 1.. hand their (m, l) to part 0 in turn
@@ -309,8 +343,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             if (part == 0) {
                 const float2 o = stat_x[row];
                 const float mm = fmaxf(m, o.x);
-                const float la = m > -INFINITY ? l * exp2f((m - mm) * c2) : 0.f;
-                const float lb = o.x > -INFINITY ? o.y * exp2f((o.x - mm) * c2) : 0.f;
+                const float la = m > -INFINITY ? l * ex2f((m - mm) * c2) : 0.f;
+                const float lb = o.x > -INFINITY ? o.y * ex2f((o.x - mm) * c2) : 0.f;
                 m = mm; l = la + lb;
             }
             AT_BAR();
@@ -320,13 +354,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         if (part != 0) { const float2 o = stat_x[row]; m = o.x; l = o.y; }
 #undef AT_BAR
         const float inv_l = 1.0f / l;
+        const float moff = m * c2;
         // ---- pass 2: normalised probabilities -> tensor memory (fp16 hi + lo)
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
             float s[AT_KP];
             load_scores(1, t, s);
 #pragma unroll
-            for (int i = 0; i < AT_KP; ++i) s[i] = (p.ablate & 1) ? 0.01f : (((mk >> i) & 1u) ? exp2f((s[i] - m) * c2) * inv_l : 0.f);
+            for (int i = 0; i < AT_KP; ++i) {
+                const float e = ex2f(fmaf(s[i], c2, -moff)) * inv_l;
+                s[i] = (p.ablate & 1) ? 0.01f : (((mk >> i) & 1u) ? e : 0.f);
+            }
             uint32_t hi[AT_KP / 2], lo[AT_KP / 2];
 #pragma unroll
             for (int i = 0; i < AT_KP / 2; ++i) {
