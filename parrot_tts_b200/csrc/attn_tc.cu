@@ -3,16 +3,19 @@
 //   softmax(q.k^T / sqrt(d_head) + key_padding_mask) . v        modules/fft.py:53-59; torch F.multi_head_attention_forward
 // (the projections around it are GEMMs of tc_conv.cu).  Scores are never written to HBM.
 //
-// One CTA = one (batch item, head, 128-query tile), 320 threads:
+// One CTA = one (batch item, head, 128-query tile), 19 warps:
 //   warp 0      producer: TMA loads of the Q tile and of 64-key K / V tiles (128-byte swizzle) from the split-fp16 qkv rows
-//   warp 1      Q.K^T issuer + TMEM owner:  S = Q.K^T  (both operands from shared memory)
-//   warp 18     P.V issuer:  O += P.V  (P from TENSOR MEMORY, V from shared memory as an MN-major operand - no transpose of V)
-//   warps 2..17 softmax / epilogue: thread = (query row = TMEM lane, half of a tile's keys); scores and probabilities are
+//   warp 1      Q.K^T issuer + TMEM owner: copies Q into TENSOR MEMORY once (tcgen05.cp), then S = Q.K^T with the A operand from
+//               tensor memory and K from shared memory
+//   warp 18     P.V issuer:  O += P.V  (P from tensor memory, V from shared memory as an MN-major operand - no transpose of V)
+//   warps 2..17 softmax / epilogue: thread = (query row = TMEM lane, a quarter of a tile's keys); scores and probabilities are
 //               double-buffered in tensor memory so the tensor pipe and the exponentials overlap
-// Products are evaluated on split-fp16 operands (x = hi + lo): a.b ~ a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, with [b_hi; b_lo]
-// stacked along N so that a k-step costs two MMAs; accumulation is fp32 in TMEM.
-// Softmax is exact two-pass (pass 1: row maximum and denominator; pass 2: normalised probabilities -> P.V), which keeps the
-// reference's order of operations (normalise, then multiply by V) and needs no rescaling of the output accumulator.
+// Products are evaluated on split-fp16 operands (x = hi + lo): a.b ~ a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, three MMAs per k-step
+// accumulating in place (fp32, TMEM).
+// Softmax is exact two-pass (pass 1: row maximum; pass 2: exp(s - max) -> P.V and the denominator, applied to O at the end):
+// no rescaling of the output accumulator is ever needed and every exponential is evaluated once.
+// Measured limits on B200 (PB_AT_ABLATE): barrier / TMEM-load skeleton 0.27 ms, + exponentials 0.34 ms alone, + MMAs and K / V
+// loads 0.28 ms alone per decoder-layer launch (B = 32, L = 2048); they overlap to 0.49 ms.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -305,65 +308,52 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(pass == 0 ? &s1_free[sb] : &s_free[sb]);   // the buffer may take another tile's scores
         };
-        // ---- pass 1: running maximum and denominator over this thread's keys
+        // ---- pass 1: row maximum over this thread's keys (the denominator is accumulated in pass 2 from the very exponentials
+        //      that are multiplied with V, and applied to O at the end: normalise-after instead of the reference's
+        //      normalise-before - the same value up to fp32 rounding, and half the exponentials)
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
             float s[AT_KP];
             load_scores(0, t, s);
             constexpr uint32_t FULL = AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u);
-            float tm = m;
             if (mk == FULL) {      // every key of the tile is valid (all tiles but the last of an unpadded item): no per-key tests
 #pragma unroll
-                for (int i = 0; i < AT_KP; ++i) tm = fmaxf(tm, s[i]);
-                const float off = tm * c2;
-                float sum = 0.f;
-#pragma unroll
-                for (int i = 0; i < AT_KP; ++i) sum += (p.ablate & 4) ? 1.f : ex2f(fmaf(s[i], c2, -off));
-                l = l * ex2f((m - tm) * c2) + sum;      // m = -inf before the first valid key: 2^-inf = 0
-                m = tm;
+                for (int i = 0; i < AT_KP; ++i) m = fmaxf(m, s[i]);
             } else {
 #pragma unroll
                 for (int i = 0; i < AT_KP; ++i)
-                    if ((mk >> i) & 1u) tm = fmaxf(tm, s[i]);
-                if (tm > -INFINITY) {
-                    float sum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < AT_KP; ++i)
-                        if ((mk >> i) & 1u) sum += ex2f((s[i] - tm) * c2);
-                    l = l * ex2f((m - tm) * c2) + sum;
-                    m = tm;
-                }
+                    if ((mk >> i) & 1u) m = fmaxf(m, s[i]);
             }
         }
-        // merge the key parts of every row through one 1 KB exchange buffer: parts 1.. hand their (m, l) to part 0 in turn
+        // merge the key parts of every row through one 1 KB exchange buffer: parts 1.. hand their value to part 0 in turn
 #define AT_BAR() asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SW) : "memory")
-        for (int j = 1; j < AT_PARTS; ++j) {
-            if (part == j) stat_x[row] = make_float2(m, l);
-            AT_BAR();
-            if (part == 0) {
-                const float2 o = stat_x[row];
-                const float mm = fmaxf(m, o.x);
-                const float la = m > -INFINITY ? l * ex2f((m - mm) * c2) : 0.f;
-                const float lb = o.x > -INFINITY ? o.y * ex2f((o.x - mm) * c2) : 0.f;
-                m = mm; l = la + lb;
+        auto merge_parts = [&](float v, bool is_max) {
+            float* xbuf = reinterpret_cast<float*>(stat_x);
+            for (int j = 1; j < AT_PARTS; ++j) {
+                if (part == j) xbuf[row] = v;
+                AT_BAR();
+                if (part == 0) v = is_max ? fmaxf(v, xbuf[row]) : v + xbuf[row];
+                AT_BAR();
             }
+            if (part == 0) xbuf[row] = v;
             AT_BAR();
-        }
-        if (part == 0) stat_x[row] = make_float2(m, l);
-        AT_BAR();
-        if (part != 0) { const float2 o = stat_x[row]; m = o.x; l = o.y; }
-#undef AT_BAR
-        const float inv_l = 1.0f / l;
+            if (part != 0) v = xbuf[row];
+            AT_BAR();
+            return v;
+        };
+        m = merge_parts(m, true);
         const float moff = m * c2;
         // ---- pass 2: normalised probabilities -> tensor memory (fp16 hi + lo)
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t mk = tile_mask(t);
+            constexpr uint32_t FULL2 = AT_KP == 32 ? 0xffffffffu : ((1u << AT_KP) - 1u);
             float s[AT_KP];
             load_scores(1, t, s);
 #pragma unroll
             for (int i = 0; i < AT_KP; ++i) {
-                const float e = ex2f(fmaf(s[i], c2, -moff)) * inv_l;
-                s[i] = (p.ablate & 1) ? 0.01f : (((mk >> i) & 1u) ? e : 0.f);
+                const float e = ex2f(fmaf(s[i], c2, -moff));
+                s[i] = (p.ablate & 1) ? 0.01f : ((mk == FULL2 || ((mk >> i) & 1u)) ? e : 0.f);
+                l += s[i];
             }
             uint32_t hi[AT_KP / 2], lo[AT_KP / 2];
 #pragma unroll
@@ -387,7 +377,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[pb]);
         }
-        // ---- epilogue: O -> split-fp16 row [hi(128) | lo(128)] of head h; the parts share the 128 columns
+        // ---- epilogue: O / l -> split-fp16 row [hi(128) | lo(128)] of head h; the parts share the 128 columns
+        l = merge_parts(l, false);
+#undef AT_BAR
+        const float inv_l = 1.0f / l;
         mbar_wait(o_full, 0);
         tc_fence_after();
         uint16_t* orow = p.out + ((size_t)b * p.L + qrow) * 2 * p.D + h * AT_DH;
@@ -400,7 +393,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
                 uint32_t hw[16], lw[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float x0 = __uint_as_float(a[2 * i]), x1 = __uint_as_float(a[2 * i + 1]);
+                    const float x0 = __uint_as_float(a[2 * i]) * inv_l, x1 = __uint_as_float(a[2 * i + 1]) * inv_l;
                     const __half2 hh = __floats2half2_rn(x0, x1);
                     const float2 hf = __half22float2(hh);
                     hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
