@@ -118,6 +118,26 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared::cluster address of the mbarrier at the same offset in CTA `target_cta` of the cluster
+__device__ __forceinline__ uint32_t cluster_bar_addr(uint64_t* bar, uint32_t target_cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(target_cta));
+    return ra;
+}
+// TMA tile loads issued by either CTA of a pair into its OWN shared memory, completion signalled on the LEADER's mbarrier
+// (cta_group::2: the barrier may live in the peer CTA) - the leader's MMA warp then waits on one barrier for both halves
+__device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+        : "memory");
+}
 // arrive on an mbarrier of another CTA of the cluster (same shared-memory offset as `bar` here)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_cta) {
     uint32_t ra;

