@@ -222,8 +222,8 @@ def run_ours(args):
     _lib.load()  # fails loudly if the extension is missing
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    quiet = _StdoutToStderr() if world > 1 else None     # NCCL prints its version banner to stdout
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup = args.steps, max(args.warmup, 3)
     shape = workload_shape(args.workload)
@@ -470,10 +470,28 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "text2wav": text2wav, "streaming": streaming,
         }
+        if quiet is not None:
+            quiet.restore()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class _StdoutToStderr:
+    """Route fd 1 to stderr while libraries that print to stdout (NCCL's version banner) run; stdout must carry only the JSON line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
 
 
 class _Null:
@@ -501,8 +519,8 @@ def run_cfg4(args):
     _lib.load()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    quiet = _StdoutToStderr() if world > 1 else None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     h = configs.default_vocoder_config()
     sd = synth.synth_vocoder_state_dict(h, seed=0) if rank == 0 else None
@@ -546,6 +564,8 @@ def run_cfg4(args):
     total_units = sum(lengths)
     if rank == 0:
         v = total_units * HOP / (ms * 1e-3)
+        if quiet is not None:
+            quiet.restore()
         print(json.dumps({"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f32 (split-bf16 x3 products on tcgen05, fp32 accumulation in TMEM)", "data": "synthetic",
