@@ -58,7 +58,7 @@ def attention(sd, p, x, key_padding_mask, n_head):
     q, k, v = heads(q), heads(k), heads(v)
     q = q * math.sqrt(1.0 / float(dh))
     if key_padding_mask is not None:
-        m = torch.zeros(B, L, dtype=x.dtype).masked_fill_(key_padding_mask, float("-inf"))
+        m = torch.zeros(B, L, dtype=x.dtype, device=x.device).masked_fill_(key_padding_mask, float("-inf"))
         m = m.view(B, 1, 1, L).expand(-1, n_head, -1, -1).reshape(B * n_head, 1, L)
         s = torch.baddbmm(m, q, k.transpose(-2, -1))
     else:
@@ -119,7 +119,7 @@ def length_regulator(batch_seq, batch_dur):
         seq = seq.repeat_interleave(dur, dim=0)
         out_lens.append(seq.shape[0])
         expanded.append(F.pad(seq, (0, 0, 0, max_len - seq.shape[0]), "constant", 0.0))
-    return torch.stack(expanded), get_mask_from_lengths(out_lens, max_len), out_lens
+    return torch.stack(expanded), get_mask_from_lengths(out_lens, max_len).to(batch_seq.device), out_lens
 
 
 def _n_layers(sd, stack):

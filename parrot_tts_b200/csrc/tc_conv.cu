@@ -450,19 +450,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             int tile_n = tile, n0n = n0 + 16;
             if (n0n >= p.NT) {
                 n0n = 0; tile_n += tile_stride; locate_next(tile_n, nxt);
-                // residual / running-sum rows of the NEXT tile: pull them into L2 now, a whole tile ahead of their use
-                if ((RES || ACC) && nxt.ok && nxt.row_ok && p.U == 1) {
-                    const size_t rb = nxt.row_el * sizeof(__nv_bfloat16);
-                    const int row_bytes = 4 * p.out_C;
-                    for (int o = 0; o < row_bytes; o += 128) {
-                        if (RES) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.res) + rb + o));
-                        if (ACC) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.accin) + rb + o));
-                    }
-                }
             }
             size_t offn = 0; int con = 0; bool liven = false;
             if (nxt.ok) item(nxt, n0n, offn, con, liven);
 
+            if ((RES || ACC) && n0 == 0 && p.U == 1) {
+                // residual / running-sum rows of this group's NEXT tile: pull this N tile's columns into L2 now, a whole
+                // tile period ahead of their use (the loads then see L2 latency, not DRAM latency under load)
+                TileCtx pf = cur;
+                locate_next(tile + tile_stride, pf);
+                if (pf.ok && pf.row_ok) {
+                    const int part_bytes = 2 * p.NT;
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const size_t rb = (pf.row_el + (size_t)h * p.out_C + (size_t)pf.nt * p.NT) * sizeof(__nv_bfloat16);
+                        for (int o = 0; o < part_bytes; o += 128) {
+                            if (RES) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.res) + rb + o));
+                            if (ACC) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.accin) + rb + o));
+                        }
+                    }
+                }
+            }
             const uint32_t as = acc_i & acc_mask;
             if (n0 == 0) {
                 mbar_wait(&acc_full[as], (acc_i >> acc_shift) & 1u);

@@ -224,6 +224,11 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
             {
                 const int tm = o0 - p.p2 + row;                    // sequence position of this xt row
                 const bool in_seq = tm >= 0 && tm < valid;         // conv2 sees zeros outside the (valid) sequence
+                if (ACC) {      // running-sum row this thread adds in epilogue B: pull it into L2 a conv ahead (row <= 128 B)
+                    const int to = o0 + row;
+                    if (row < p.m_out && to < p.L)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.accin + ((size_t)b * p.L + to) * pitch));
+                }
                 mbar_wait(&a_full[st], n & 1u);
                 if (n > 0) mbar_wait(&mid_empty[st], (n - 1) & 1u);   // conv2(i-2) has consumed this xt buffer
                 tc_fence_after();

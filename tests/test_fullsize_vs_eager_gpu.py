@@ -1,0 +1,137 @@
+"""Full-size parity and the "existing Blackwell kernels" bar (last row).
+
+The oracle is a set of plain torch functions, so on the GPU box it can also be executed on the device: that IS the
+reference's own GPU path (eager PyTorch -> cuDNN / cuBLAS fp32 kernels for sm_100, TF32 off), at sizes the CPU oracle
+would need minutes for.  Each test
+  * compares the product path with it at the full BASELINE size (configs[1] vocoder 8 x 1024 units; configs[2] TTE
+    32 x 256 chars -> 2048 units) - waveform within 1e-3 abs, durations / masks bit-exact, unit ids bit-exact except at
+    genuine near-ties of the fp32 logits (top-2 margin < 1e-4; the two fp32 evaluation orders disagree there too);
+  * times both with CUDA events and appends the pair to gpurun_out/eager_bar.json (copied to profiles/ by hand).
+The oracle stays the checker: nothing here is on the product path."""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+
+from oracle import tte_oracle, voc_oracle
+from parrot_tts_b200 import configs, synth
+from parrot_tts_b200.tte import Parrot
+from parrot_tts_b200.vocoder import CodeGenerator
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _time_ms(fn, warmup=2, reps=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2]
+
+
+def _record(name, entry):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "eager_bar.json")
+    data = {}
+    if os.path.exists(path):
+        with open(path) as f:
+            data = json.load(f)
+    data[name] = entry
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_exact():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_vocoder_cfg2_full_size_vs_eager_torch():
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=0)
+    gen = CodeGenerator(h)
+    gen.load_state_dict(sd)
+    gen = gen.to(DEV)
+    g = torch.Generator().manual_seed(0)
+    code = torch.randint(0, 1000, (8, 1024), generator=g).to(DEV)
+    spkr = torch.randint(0, 10, (8, 1), generator=g).to(DEV)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+
+    ours = gen(code=code, spkr=spkr)
+    ref = voc_oracle.code_generator_forward(sd_dev, h, code, spkr)
+    assert ours.shape == ref.shape == (8, 1, 320 * 1024)
+    err = float((ours - ref).abs().max())
+    assert err <= 1e-3, err                                       # north_star tolerance
+    assert err <= 2e-4, err                                       # what the split-bf16 path actually achieves
+
+    t_ours = _time_ms(lambda: gen(code=code, spkr=spkr))
+    t_ref = _time_ms(lambda: voc_oracle.code_generator_forward(sd_dev, h, code, spkr))
+    torch.backends.cudnn.allow_tf32 = True                        # the reference's default cuDNN setting
+    t_ref_tf32 = _time_ms(lambda: voc_oracle.code_generator_forward(sd_dev, h, code, spkr))
+    torch.backends.cudnn.allow_tf32 = False
+    samples = ours.numel()
+    _record("vocoder_cfg2", {
+        "workload": "configs[1]: 8 x 1024 units -> 2 621 440 samples", "max_abs_err": err,
+        "ours_ms": t_ours, "eager_torch_fp32_ms": t_ref, "eager_torch_tf32_ms": t_ref_tf32,
+        "ours_samples_per_s": samples / t_ours * 1e3, "eager_fp32_samples_per_s": samples / t_ref * 1e3,
+        "eager_tf32_samples_per_s": samples / t_ref_tf32 * 1e3, "torch": torch.__version__,
+        "note": "eager = the reference graph (weight norm folded per call, as its hook does) on cuDNN"})
+    assert t_ours < t_ref, (t_ours, t_ref)
+
+
+def test_tte_cfg3_full_size_vs_eager_torch():
+    d = tempfile.mkdtemp(prefix="parrot_tte_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({f"s{i}": i for i in range(10)}, f)
+    cfg = configs.default_tte_config(root_path=d)
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=0, dur_mode="const8")
+    m = Parrot(cfg, 150, 0)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(DEV)
+    g = torch.Generator().manual_seed(0)
+    phones = torch.randint(2, 150, (32, 256), generator=g).to(DEV)
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": (torch.arange(32) % 10).to(DEV)}
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+
+    logits, _, tgt_mask, log_dur = m(batch, inference=True)
+    ref = tte_oracle.parrot_forward(sd_dev, batch)
+    assert logits.shape == ref["logits"].shape == (32, 2048, 1000)
+    assert torch.equal(tgt_mask, ref["tgt_mask"])                  # bit-exact durations -> identical masks
+    assert torch.allclose(log_dur, ref["log_dur"], atol=1e-5, rtol=0)
+    live = tgt_mask
+    lerr = float((logits - ref["logits"])[live].abs().max())
+    assert lerr <= 2e-3, lerr
+    ids, rids = logits.argmax(-1), ref["logits"].argmax(-1)
+    bad = ((ids != rids) & live).nonzero()
+    top2 = torch.topk(ref["logits"], 2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]
+    assert bad.shape[0] <= 8, f"{bad.shape[0]} id mismatches of {int(live.sum())}"
+    for b, t in bad.tolist():
+        assert float(margin[b, t]) < 1e-4, (b, t, float(margin[b, t]))   # only genuine fp32 near-ties may differ
+
+    t_ours = _time_ms(lambda: m(batch, inference=True))
+    t_ref = _time_ms(lambda: tte_oracle.parrot_forward(sd_dev, batch), warmup=1, reps=3)
+    units = int(live.sum())
+    _record("tte_cfg3", {
+        "workload": "configs[2] TTE: 32 x 256 chars -> 32 x 2048 units", "max_logit_err": lerr,
+        "id_mismatches": int(bad.shape[0]), "units": units,
+        "ours_ms": t_ours, "eager_torch_fp32_ms": t_ref,
+        "ours_units_per_s": units / t_ours * 1e3, "eager_units_per_s": units / t_ref * 1e3,
+        "torch": torch.__version__,
+        "note": "eager = nn.MultiheadAttention slow path restated (scores materialised), cuBLAS fp32, TF32 off"})
+    assert t_ours < t_ref, (t_ours, t_ref)
