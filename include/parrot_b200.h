@@ -95,6 +95,12 @@ int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, const int64_t
 /* generate() tail (utils/vocoder/inference.py:71-73): pcm = (int16) trunc(wav * 32768) (wraps like a C cast). */
 int pb_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, void* stream);
 
+/* Peak normalisation of the generated PCM before it is written out - `librosa.util.normalize(audio.astype(np.float32))`
+ * with its defaults (norm = inf over the utterance; utils/vocoder/inference.py:169, demo.ipynb cell 13):
+ *   out[b, i] = float(pcm[b, i]) / max_i |pcm[b, i]|   (an all-zero item is returned unchanged)
+ * pcm i16 [B, n]; peak i32 [B] (device, written: the per-item peak); out f32 [B, n].  Asynchronous on `stream`. */
+int pb_pcm16_peak_normalize(const int16_t* pcm, int32_t B, int64_t n, int32_t* peak, float* out, void* stream);
+
 /* Number of this library's kernel launches issued by the last pb_voc_forward / pb_tte_* call on the handle. */
 int64_t pb_voc_last_launches(const pb_voc* h);
 

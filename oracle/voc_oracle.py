@@ -85,3 +85,20 @@ def to_int16(y):
     # utils/vocoder/inference.py:71-73: (y * 32768).cpu().numpy().astype('int16')
     # numpy float->int16 truncates toward zero (C cast; wraps when |y*32768| >= 32768).
     return (y.squeeze() * MAX_WAV_VALUE).numpy().astype("int16")
+
+
+def peak_normalize(audio):
+    """`librosa.util.normalize(audio.astype(np.float32))` (utils/vocoder/inference.py:169, demo.ipynb cell 13).
+
+    librosa is a third-party dependency that is NOT vendored in the reference (requirements.txt:8, unpinned) and is
+    absent here, so this restates its published algorithm for the defaults the reference uses (norm=inf, axis=0,
+    threshold=tiny, fill=None): magnitudes are taken in float64, the peak below `tiny` is replaced by 1, the quotient is
+    stored into an array of the input's dtype (float32).  Parity for this one function is unpinned by any reference run."""
+    import numpy as np
+    s = np.asarray(audio).astype(np.float32)
+    length = np.abs(s).astype(float).max(axis=0, keepdims=True)
+    length[length < np.finfo(np.float32).tiny] = 1.0
+    out = np.empty_like(s)
+    out[:] = s / length
+    return out
+

@@ -54,6 +54,7 @@ SIGNATURES = {
     "pb_voc_finalize": (C.c_int, [_P, _P]),
     "pb_voc_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     "pb_wav_to_pcm16": (C.c_int, [_P, _I64, _P, _P]),
+    "pb_pcm16_peak_normalize": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "pb_voc_last_launches": (_I64, [_P]),
     "pb_voc_set_timing": (C.c_int, [_P, _I32]),
     "pb_voc_section_count": (C.c_int, [_P]),

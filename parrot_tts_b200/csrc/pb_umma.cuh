@@ -138,6 +138,15 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
         : "memory");
 }
+// TMA store of a [rows x box_c] tile from shared memory (bulk-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING shared memory (the buffers may be rewritten)
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // arrive on an mbarrier of another CTA of the cluster (same shared-memory offset as `bar` here)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_cta) {
     uint32_t ra;

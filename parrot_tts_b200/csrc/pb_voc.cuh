@@ -74,5 +74,6 @@ int launch_conv_post_split(const __nv_bfloat16* x, const float* w /*[Cin][K]*/, 
                            const int32_t* lens, int len_mul, int B, int Cin, int L, int K, cudaStream_t st);
 
 int launch_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, cudaStream_t st);
+int launch_pcm16_peak_normalize(const int16_t* pcm, int B, int64_t n, int32_t* peak, float* out, cudaStream_t st);
 
 }  // namespace pb

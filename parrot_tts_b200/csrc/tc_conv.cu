@@ -48,7 +48,8 @@ struct TcParams {
     int a_loads, a_row_bytes, a_tile_bytes, a_stage_bytes, lo_off, a_layout, a_sbo;
     int n_a_stages, n_b_stages, b_block_bytes, b_sub_bytes, kpb, w_total_bytes;
     int res_blocks, total_blocks;          // weight blocks [nt][chunk][tap] below res_blocks stay resident in shared memory
-    uint32_t smem_a_off, smem_b_off, smem_ring_off, smem_bias_off;
+    uint32_t smem_a_off, smem_b_off, smem_ring_off, smem_bias_off, smem_stage_off;
+    int tma_out;    // epilogue writes through per-warp staging tiles + TMA stores (U == 1 layers)
     int tiles_t, total_tiles;
     float post_slope, scale, res_unslope;
     int tanh_out;
@@ -218,7 +219,8 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
 // ------------------------------------------------------------------------------------------------------------------------
 template <bool RES, bool ACC, bool CL>
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap omap,
+               const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
@@ -244,6 +246,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
         if (CL) prefetch_tmap(&wmap);
+        if (p.tma_out) prefetch_tmap(&omap);
         for (int s = 0; s < TC_MAX_STAGES; ++s) {
             mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
             mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1);
@@ -363,8 +366,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
-        // Work items are (tile, 16-column chunk) in order; the residual / running-sum rows of item k+1 are requested
-        // before the arithmetic of item k, so their HBM latency hides behind it and behind the accumulator wait.
+        // Work items are (tile, 16-column chunk) in order; the residual / running-sum rows of item k+1 are requested as soon
+        // as item k has consumed its own, so their latency hides behind the rest of item k and the next accumulator read.
         // Everything that costs an integer division is done once per tile; bias comes from shared memory.
         asm volatile("griddepcontrol.wait;" ::: "memory");   // residual / running-sum reads and the output stores depend on the previous kernel
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -476,6 +479,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 mbar_wait(&acc_full[as], (acc_i >> acc_shift) & 1u);
                 tc_fence_after();
             }
+            float4 bv4[4];                                // bias of this item, fetched while the accumulator read is in flight
+            {
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + co);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bv4[i] = bp[i];
+            }
             float v[16];
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_cols + (uint32_t)n0;
@@ -485,8 +494,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 } else if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
                 else tmem_ld16(taddr, v);
             }
-            uint4 Rn[4], An[4];
-            request(nxt.ok && nxt.row_ok, offn, Rn, An);
             if (n0n == 0) {                            // accumulator fully read: hand it back before the arithmetic
                 tc_fence_before();
                 __syncwarp();
@@ -495,10 +502,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 }
             }
             if (cur.row_ok && !(p.ablate & 32)) {
-                const float4* bp = reinterpret_cast<const float4*>(bias_s + co);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 bv = bp[i];
+                    const float4 bv = bv4[i];
                     v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
                 }
                 if (RES) {
@@ -521,6 +527,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                         v[2 * i + 1] = r.y + v[2 * i + 1];
                     }
                 }
+            }
+            // R / A are dead from here: the next item's residual / running-sum rows are requested into the SAME registers (no
+            // register-to-register hand-over at the loop edge - that copy made every item wait for its loads right away) and
+            // have the rest of this item plus the next accumulator read to arrive
+            request(nxt.ok && nxt.row_ok, offn, R, A);
+            uint32_t hw[8], lw[8];
+            if (cur.row_ok && !(p.ablate & 32)) {
                 if (p.res_f32) {      // fp32 residual stream [B][Lout][out_C] (TTE)
                     const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + (off - (size_t)co) / 2 + co);
 #pragma unroll
@@ -540,13 +553,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
                 }
                 if (p.out && !(p.ablate & 2)) {
-                    uint32_t hw[8], lw[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], p.fmt, hw[i], lw[i]);
-                    __nv_bfloat16* oh = p.out + off;
-                    __nv_bfloat16* ol = oh + p.out_C;
-                    st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
-                    st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                    if (!p.tma_out) {
+                        __nv_bfloat16* oh = p.out + off;
+                        __nv_bfloat16* ol = oh + p.out_C;
+                        st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+                        st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                    }
                 }
                 if (p.out_f32) {
                     float* of = p.out_f32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch
@@ -555,13 +569,34 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                         *reinterpret_cast<float4*>(of + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { R[i] = Rn[i]; A[i] = An[i]; }
+            if (p.tma_out && !(p.ablate & 2)) {
+                // Row-per-thread 32-byte global stores cost ~50 L1 wavefronts per instruction (every lane its own line); instead the
+                // warp parks its [32 rows x 16 ch] hi and lo tiles in shared memory (32B-swizzled: conflict-free 16-byte stores) and
+                // one lane hands them to the TMA unit.  Rows past the end of the sequence are clipped by the tensor map.
+                uint8_t* sbw = sm + p.smem_stage_off + (uint32_t)(warp - 4) * 2048u;
+                if (lane == 0) bulk_wait_group_read<0>();          // the previous item's stores have read this buffer
+                __syncwarp();
+                const uint32_t sx = ((uint32_t)lane >> 2) & 1u;     // 32B swizzle: 16-byte chunk ^= address bit 7
+                uint8_t* rp = sbw + lane * 32;
+                *reinterpret_cast<uint4*>(rp + (sx << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(rp + ((sx ^ 1u) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                *reinterpret_cast<uint4*>(rp + 1024 + (sx << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                *reinterpret_cast<uint4*>(rp + 1024 + ((sx ^ 1u) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                fence_proxy_async();
+                __syncwarp();
+                const int t0 = cur.orow0 - lane;                    // first row of this warp's 32 (U == 1)
+                if (lane == 0 && t0 < p.L) {
+                    tma_store_3d(&omap, sbw, co, t0, cur.b);
+                    tma_store_3d(&omap, sbw + 1024, p.out_C + co, t0, cur.b);
+                    bulk_commit_group();
+                }
+            }
             if (n0n == 0) acc_i += (uint32_t)p.n_groups;
             cur = nxt; tile = tile_n; n0 = n0n; off = offn; co = con; live = liven;
         }
     }
 
+    if (p.tma_out && warp >= 4 && lane == 0) bulk_wait_group<0>();     // this lane's TMA stores have completed
     tc_fence_before();
     __syncthreads();
     if (CL) cluster_sync_all();          // no CTA of the pair exits (or frees TMEM) while the other may still signal it
@@ -641,6 +676,22 @@ int tc_make_tmap_act(CUtensorMap* map, const __nv_bfloat16* base, int C, int L, 
     return make_tmap_act(map, base, C, L, B, box_c, rows, sw128);
 }
 
+// 3-D map over a split output [B][L][2C] for the TMA-store epilogue: box (16 ch, rows <= 32, 1), 32B swizzle
+int tc_make_tmap_out(CUtensorMap* map, __nv_bfloat16* base, int C, int L, int B, int rows) {
+    EncodeTiledFn fn = encode_fn();
+    PB_REQUIRE(fn != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    PB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, PB_ERR_INVALID, "tc_conv: output base must be 16-byte aligned");
+    PB_REQUIRE(rows >= 1 && rows <= 32, PB_ERR_INVALID, "tc_conv: output box of %d rows", rows);
+    cuuint64_t gdim[3] = {(cuuint64_t)2 * C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)4 * C, (cuuint64_t)4 * C * L};
+    cuuint32_t box[3] = {16, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_REQUIRE(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed (%d): C=%d L=%d B=%d rows=%d", (int)r, C, L, B, rows);
+    return PB_OK;
+}
+
 int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     PB_REQUIRE(a.x && a.w && (a.out || a.out_f32), PB_ERR_INVALID, "tc_conv: null tensor");
     PB_REQUIRE(a.B > 0 && a.L > 0 && a.K >= 1 && a.D >= 1 && a.U >= 1, PB_ERR_INVALID, "tc_conv: bad shape");
@@ -690,11 +741,23 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     int ctas_per_sm = 1;
     uint32_t b_res_bytes = 0, ring_bytes = 0;
     const uint32_t w_all = (uint32_t)round_up(p.w_total_bytes, 1024);
-    auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off; };   // barriers + bias + alignment slack
+    // TMA-store epilogue (U == 1, split output): 2 KB of staging per epilogue warp, up to 3 groups of 4 warps.
+    // PB_TC_TMA_OUT: 0 = never, 1 = layers that run one CTA per SM without CTA pairs (default), 2 = every eligible layer (dev switch)
+    static const int tma_out_mode = getenv("PB_TC_TMA_OUT") ? atoi(getenv("PB_TC_TMA_OUT")) : 1;
     // two CTAs per SM (two producers, two MMA issuers, one epilogue group each) measured best for the 16-channel layers;
     // wider layers run one CTA per SM with up to 3 epilogue groups (PB_TC_2CTA=0/1 forces either, dev switch)
     static const int force_2cta = getenv("PB_TC_2CTA") ? atoi(getenv("PB_TC_2CTA")) : -1;
     const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
+    p.tma_out = (a.out != nullptr && a.U == 1 && tma_out_mode > 0 && !want_2cta && (tma_out_mode > 1 || !p.cluster)) ? 1 : 0;
+    uint32_t stage_bytes = p.tma_out ? 3u * 4u * 2048u : 0u;
+    auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off - stage_bytes; };   // barriers + bias + alignment slack
+    if (p.tma_out && !p.cluster && budget(TC_SMEM_LIMIT) < w_all + 2u * (uint32_t)p.a_stage_bytes) {
+        // the staging tiles would cost weight residency: every resident block counts (measured ~6 us per block on the 64-channel
+        // k = 11 layers), so they are kept only where the weights are partly resident anyway AND the epilogue does three global
+        // accesses per item (residual + running sum + store)
+        const bool full_without = TC_SMEM_LIMIT - 1024u - p.smem_a_off >= w_all + 2u * (uint32_t)p.a_stage_bytes;
+        if (full_without || !(a.res && a.accin)) { p.tma_out = 0; stage_bytes = 0; }
+    }
     if (p.cluster) {
         const uint32_t bud = budget(TC_SMEM_LIMIT);
         p.res_blocks = 0;
@@ -738,7 +801,8 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     ring_bytes = (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
     p.smem_b_off = p.smem_a_off + (uint32_t)p.n_a_stages * (uint32_t)p.a_stage_bytes;
     p.smem_ring_off = p.smem_b_off + b_res_bytes;
-    const uint32_t smem_bytes = p.smem_ring_off + ring_bytes + 1024;
+    p.smem_stage_off = p.smem_ring_off + ring_bytes;
+    const uint32_t smem_bytes = p.smem_stage_off + stage_bytes + 1024;
     PB_REQUIRE(smem_bytes <= (ctas_per_sm == 2 ? TC_SMEM_HALF : TC_SMEM_LIMIT), PB_ERR_INVALID, "tc_conv: shared memory plan %u exceeds the limit", smem_bytes);
     p.tiles_t = (int)ceil_div(a.L, p.cluster ? 2 * TC_M : TC_M);
     const int64_t total = (int64_t)a.B * p.tiles_t * p.n_tiles_n;
@@ -789,6 +853,8 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         PB_REQUIRE(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
     }
 
+    CUtensorMap omap = xmap;      // only read when tma_out
+    if (p.tma_out) PB_TRY(tc_make_tmap_out(&omap, a.out, a.out_C, a.L, a.B, 32));
     {
         static const int abl = getenv("PB_TC_ABLATE") ? atoi(getenv("PB_TC_ABLATE")) : 0;
         p.ablate = abl;
@@ -814,9 +880,9 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     {
         static const bool dbg = getenv("PB_TC_DEBUG") != nullptr;
         if (dbg)
-            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d groups=%d cluster=%d\n",
+            fprintf(stderr, "[tc_conv] Cin=%d N=%d(NT=%d) K=%d D=%d L=%d B=%d: tiles=%d grid=%d ctas/sm=%d smem=%u a_stages=%dx%d res_blocks=%d/%d (block %d B) ring=%dx%d kpb=%d n_acc=%d groups=%d cluster=%d tma_out=%d\n",
                     a.Cin, a.N, NT, a.K, a.D, a.L, a.B, p.total_tiles, grid, ctas_per_sm, smem_bytes, p.n_a_stages, p.a_stage_bytes, p.res_blocks,
-                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc, p.n_groups, p.cluster);
+                    p.total_blocks, p.b_block_bytes, p.n_b_stages, p.b_sub_bytes, p.kpb, p.n_acc, p.n_groups, p.cluster, p.tma_out);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
@@ -835,15 +901,15 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     }
     cfg.attrs = attr; cfg.numAttrs = na;
     if (p.cluster) {
-        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, true>, xmap, wmap, p));
-        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, true>, xmap, wmap, p));
-        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, true>, xmap, wmap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, true>, xmap, wmap, p));
+        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, true>, xmap, wmap, omap, p));
+        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, true>, xmap, wmap, omap, p));
+        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, true>, xmap, wmap, omap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, true>, xmap, wmap, omap, p));
     } else {
-        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, false>, xmap, wmap, p));
-        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, false>, xmap, wmap, p));
-        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, false>, xmap, wmap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, false>, xmap, wmap, p));
+        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, false>, xmap, wmap, omap, p));
+        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, false>, xmap, wmap, omap, p));
+        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, false>, xmap, wmap, omap, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, false>, xmap, wmap, omap, p));
     }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());

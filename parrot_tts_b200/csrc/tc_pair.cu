@@ -46,13 +46,16 @@ struct PairParams {
     float mid_slope, post_slope, scale, res_unslope;
     uint32_t idesc, idesc_stack;
     int acc_cols, tmem_cols;
+    int tma_out;                   // epilogue B writes through per-warp staging tiles + TMA stores
+    uint32_t smem_stage_off;
 };
 
 }  // namespace
 
 template <bool ACC, int KSTEPS>
 __global__ void __launch_bounds__(TP_THREADS, 1)
-tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
+tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap_tail,
+               const PairParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
@@ -72,6 +75,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
+        if (p.tma_out) { prefetch_tmap(&omap); prefetch_tmap(&omap_tail); }
         for (int s = 0; s < TP_MAX_XST; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
         for (int s = 0; s < TP_STAGES; ++s) {
             mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 4);
@@ -285,6 +289,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
                 tc_fence_after();
                 for (int n0 = 0; n0 < C; n0 += 16) {
                     float v[16];
+                    uint32_t hw[8], lw[8];
                     const uint32_t taddr = tmem_base + lane_off + (TP_STAGES + st) * (uint32_t)p.acc_cols + (uint32_t)n0;
                     tmem_ld16x2_sum(taddr, taddr + (uint32_t)C, v);
                     if (n0 + 16 >= C) {
@@ -318,7 +323,6 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
                             }
                         }
                         const float sc = live ? p.scale : 0.f;
-                        uint32_t hw[8], lw[8];
 #pragma unroll
                         for (int k2 = 0; k2 < 8; ++k2) {
                             float a0 = v[2 * k2] * sc, a1 = v[2 * k2 + 1] * sc;
@@ -327,10 +331,35 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
                             split2(a0, a1, 0, hw[k2], lw[k2]);
                         }
                         if (n0 + 16 < C) request(n0 + 16);
-                        __nv_bfloat16* oh = p.out + row_el + n0;
-                        __nv_bfloat16* ol = oh + C;
-                        st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
-                        st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                        if (!p.tma_out) {
+                            __nv_bfloat16* oh = p.out + row_el + n0;
+                            __nv_bfloat16* ol = oh + C;
+                            st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+                            st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                        }
+                    }
+                    if (p.tma_out) {
+                        // the warp parks its [32 rows x 16 ch] hi / lo tiles in shared memory (32B swizzle) and one lane hands them to
+                        // the TMA unit: row-per-thread 32-byte global stores cost ~50 L1 wavefronts per instruction.  The last warp of a
+                        // tile owns fewer than 32 output rows (m_out < 128): it uses the map whose box has exactly that many.
+                        uint8_t* sbw = sm + p.smem_stage_off + (uint32_t)(warp - 4) * 2048u;
+                        if (lane == 0) bulk_wait_group_read<0>();
+                        __syncwarp();
+                        const uint32_t sx = ((uint32_t)lane >> 2) & 1u;
+                        uint8_t* rp = sbw + lane * 32;
+                        *reinterpret_cast<uint4*>(rp + (sx << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(rp + ((sx ^ 1u) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                        *reinterpret_cast<uint4*>(rp + 1024 + (sx << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4*>(rp + 1024 + ((sx ^ 1u) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        const int t0 = o0 + q * 32;
+                        if (lane == 0 && t0 < p.L) {
+                            const CUtensorMap* om = q == 3 ? &omap_tail : &omap;
+                            tma_store_3d(om, sbw, n0, t0, b);
+                            tma_store_3d(om, sbw + 1024, C + n0, t0, b);
+                            bulk_commit_group();
+                        }
                     }
                 }
             }
@@ -342,6 +371,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const PairParams p) {
         }
     }
 
+    if (p.tma_out && warp >= 4 && lane == 0) bulk_wait_group<0>();     // this lane's TMA stores have completed
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -384,10 +414,17 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     p.smem_mid_off = p.smem_w2_off + (uint32_t)round_up(p.w_bytes, 1024);
     p.smem_x_off = p.smem_mid_off + (uint32_t)TP_STAGES * (uint32_t)p.mid_bytes;
     const uint32_t left = TP_SMEM_LIMIT - 1024u - p.smem_x_off;
-    p.n_x_stages = (int)(left / (uint32_t)p.x_stage_bytes);
+    // TMA-store epilogue: 2 KB of staging per epilogue warp, when at least 3 xt stages remain (PB_TC_TMA_OUT=0 disables).  Measured
+    // per launch on B200: -6 us at C = 32 (k = 3), but +5 .. +30 us at C = 16, where the kernel is bound by shared-memory traffic
+    // (narrow A-operand reads + the xt tile) and the staging tiles add to it - so 32-channel layers only.
+    static const int tma_out_mode = getenv("PB_TC_TMA_OUT") ? atoi(getenv("PB_TC_TMA_OUT")) : 1;
+    const uint32_t stage_bytes = (uint32_t)TP_GROUPS * 4u * 2048u;
+    p.tma_out = (tma_out_mode > 0 && a.C == 32 && left >= stage_bytes + 3u * (uint32_t)p.x_stage_bytes && p.m_out > 96) ? 1 : 0;
+    p.n_x_stages = (int)((left - (p.tma_out ? stage_bytes : 0u)) / (uint32_t)p.x_stage_bytes);
     if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
     PB_REQUIRE(p.n_x_stages >= 2, PB_ERR_INVALID, "tc_pair: tile does not fit in shared memory (C=%d K=%d D=%d)", a.C, a.K, a.D);
-    const uint32_t smem_bytes = p.smem_x_off + (uint32_t)p.n_x_stages * (uint32_t)p.x_stage_bytes + 1024;
+    p.smem_stage_off = p.smem_x_off + (uint32_t)p.n_x_stages * (uint32_t)p.x_stage_bytes;
+    const uint32_t smem_bytes = p.smem_stage_off + (p.tma_out ? stage_bytes : 0u) + 1024;
     p.tiles_t = (int)ceil_div(a.L, p.m_out);
     const int64_t total = (int64_t)a.B * p.tiles_t;
     PB_REQUIRE(total < (1LL << 31), PB_ERR_INVALID, "tc_pair: too many tiles");
@@ -403,6 +440,12 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     // x tile = two boxes of x_rows / 2 rows (a TMA box holds at most 256 rows)
     CUtensorMap xmap;
     PB_TRY(tc_make_tmap_act(&xmap, a.x, a.C, a.L, a.B, a.C == 16 ? 32 : 64, p.x_rows / 2, a.C != 16));
+
+    CUtensorMap omap = xmap, omap_tail = xmap;      // only read when tma_out
+    if (p.tma_out) {
+        PB_TRY(tc_make_tmap_out(&omap, a.out, a.C, a.L, a.B, 32));
+        PB_TRY(tc_make_tmap_out(&omap_tail, a.out, a.C, a.L, a.B, p.m_out - 96));
+    }
 
     static int n_sm = 0;
     static bool attr_set = false;
@@ -424,11 +467,11 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (p.ksteps == 1) {
-        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 1>, xmap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 1>, xmap, p));
+        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 1>, xmap, omap, omap_tail, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 1>, xmap, omap, omap_tail, p));
     } else {
-        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 2>, xmap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 2>, xmap, p));
+        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 2>, xmap, omap, omap_tail, p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 2>, xmap, omap, omap_tail, p));
     }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());

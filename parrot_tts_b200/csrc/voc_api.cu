@@ -533,6 +533,11 @@ extern "C" int pb_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, void* 
     return launch_wav_to_pcm16(wav, n, pcm, (cudaStream_t)stream);
 }
 
+extern "C" int pb_pcm16_peak_normalize(const int16_t* pcm, int32_t B, int64_t n, int32_t* peak, float* out, void* stream) {
+    PB_REQUIRE(pcm && peak && out && B >= 0 && n >= 0, PB_ERR_INVALID, "pb_pcm16_peak_normalize: bad argument");
+    return launch_pcm16_peak_normalize(pcm, B, n, peak, out, (cudaStream_t)stream);
+}
+
 // ---- per-op entry points (unit tests): torch-layout weights are packed on the fly ------------------
 extern "C" int pb_conv1d(const float* x, const float* w, const float* bias, const float* res, float* y, int32_t B, int32_t Cin,
                          int32_t Cout, int32_t L, int32_t K, int32_t dilation, float pre_slope, float post_slope,

@@ -771,4 +771,57 @@ int launch_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, cudaStream_t 
     return PB_OK;
 }
 
+// Peak normalisation of generated PCM (librosa.util.normalize defaults: norm = inf over the utterance; an all-zero
+// utterance is left as it is).  Pass 1: per-item max |pcm| with one atomicMax per block; pass 2: float(pcm) / float(peak),
+// IEEE division (librosa divides in float64 and rounds to float32: identical for 16-bit integers, 53 >= 2*24 + 2).
+__global__ void pcm16_peak_kernel(const int16_t* __restrict__ pcm, int64_t n, int32_t* __restrict__ peak) {
+    const int16_t* x = pcm + (size_t)blockIdx.y * n;
+    int m = 0;
+    const int64_t n8 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 8 : 0;     // 16-byte vector body when the item is aligned
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = (int)(int16_t)(w[k] & 0xffffu), b = (int)(int16_t)(w[k] >> 16);
+            m = max(m, max(a < 0 ? -a : a, b < 0 ? -b : b));
+        }
+    }
+    for (int64_t i = n8 * 8 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)x[i];
+        m = max(m, a < 0 ? -a : a);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    __shared__ int sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = max(m, sm[w]);
+        if (m > 0) atomicMax(peak + blockIdx.y, m);
+    }
+}
+
+__global__ void pcm16_scale_kernel(const int16_t* __restrict__ pcm, int64_t n, const int32_t* __restrict__ peak, float* __restrict__ out) {
+    const int pk = peak[blockIdx.y];
+    const float len = pk > 0 ? (float)pk : 1.0f;
+    const int16_t* x = pcm + (size_t)blockIdx.y * n;
+    float* o = out + (size_t)blockIdx.y * n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = __fdiv_rn((float)x[i], len);
+}
+
+int launch_pcm16_peak_normalize(const int16_t* pcm, int B, int64_t n, int32_t* peak, float* out, cudaStream_t st) {
+    if (B <= 0 || n <= 0) return PB_OK;
+    PB_CUDA(cudaMemsetAsync(peak, 0, sizeof(int32_t) * (size_t)B, st));
+    const int64_t want = ceil_div(n, 2048), cap = 148 * 8 / B > 0 ? 148 * 8 / B : 1;     // ~8 blocks per SM over all items
+    const int per_item = (int)(want < cap ? want : cap);
+    dim3 grid((unsigned)per_item, (unsigned)B);
+    pcm16_peak_kernel<<<grid, 256, 0, st>>>(pcm, n, peak);
+    PB_COUNT_LAUNCH();
+    pcm16_scale_kernel<<<grid, 256, 0, st>>>(pcm, n, peak, out);
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 }  // namespace pb

@@ -88,6 +88,25 @@ def wav_to_pcm16(wav):
     return pcm
 
 
+def peak_normalize(pcm):
+    """`librosa.util.normalize(audio.astype(np.float32))` on the device (utils/vocoder/inference.py:169, demo cell 13):
+    int16 PCM [n] or [B, n] -> float32 of the same shape, every utterance divided by its own max |sample|
+    (an all-zero utterance is returned unchanged)."""
+    _need_cuda(pcm)
+    if pcm.dtype != torch.int16:
+        raise TypeError("peak_normalize expects the int16 PCM that generate() returns")
+    pcm = pcm.contiguous()
+    if pcm.dim() not in (1, 2):
+        raise ValueError("peak_normalize: [n] or [B, n] expected")
+    B, n = (1, pcm.numel()) if pcm.dim() == 1 else pcm.shape
+    out = torch.empty(pcm.shape, device=pcm.device, dtype=torch.float32)
+    peak = torch.empty(max(B, 1), device=pcm.device, dtype=torch.int32)
+    with torch.cuda.device(pcm.device):
+        _lib.check(_lib.load().pb_pcm16_peak_normalize(_lib.ptr(pcm), B, n, _lib.ptr(peak), _lib.ptr(out),
+                                                        _lib.stream_ptr(pcm.device)))
+    return out
+
+
 def linear(x, w, bias=None, mode=0):
     """nn.Linear: x [M,K] . w[N,K]^T + bias (fp32)."""
     _need_cuda(x, w, bias)

@@ -30,6 +30,19 @@ def generate(h, generator, code):
     return audio, rtf
 
 
+def normalize(audio, device="cuda"):
+    """Drop-in for ``librosa.util.normalize(audio.astype(np.float32))`` as the reference calls it on generated audio
+    (utils/vocoder/inference.py:169, demo.ipynb cell 13): int16 PCM -> float32 divided by the utterance's peak.
+    numpy in -> numpy out (the reduction and the division run on the device); a device tensor [n] / [B, n] stays there."""
+    if torch.is_tensor(audio):
+        return ops.peak_normalize(audio)
+    import numpy as np
+    a = np.ascontiguousarray(audio)
+    if a.dtype != np.int16:
+        raise TypeError("normalize expects the int16 audio that generate() returns")
+    return ops.peak_normalize(torch.from_numpy(a).to(device)).cpu().numpy()
+
+
 def stream_chunks(n_units, chunk_units=1024, halo_units=32):
     """[(lo, hi, a, b)]: chunk i synthesises units [a, b) from the window [lo, hi) = [a - halo, b + halo) clipped to the
     utterance.  The generator is purely convolutional with a receptive-field radius of ~23 units,

@@ -228,6 +228,22 @@ def test_pcm16_matches_reference_cast():
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("shape", [(1,), (7,), (4099,), (3, 40961), (2, 163840)])
+def test_peak_normalize_matches_librosa_restatement(shape):
+    """librosa.util.normalize of the int16 audio (utils/vocoder/inference.py:169): bit-exact float32 result per utterance."""
+    g = np.random.default_rng(sum(shape))
+    pcm = g.integers(-9000, 9000, size=shape, dtype=np.int16)
+    if len(shape) == 2:
+        pcm[1] = 0                                            # an all-zero utterance is returned unchanged
+        pcm[0, 5] = -32768                                    # |-32768| does not fit int16: the peak is taken in int32
+    ref = np.stack([voc_oracle.peak_normalize(r) for r in pcm]) if len(shape) == 2 else voc_oracle.peak_normalize(pcm)
+    got = ops.peak_normalize(torch.from_numpy(pcm).to(DEV)).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, ref)
+    if len(shape) == 1:
+        from parrot_tts_b200.vocoder import normalize
+        assert np.array_equal(normalize(pcm), ref)            # numpy in, numpy out: the reference's call shape
+
+
 def test_no_cpu_fallback():
     h, sd, gen = _code_generator(0)
     with pytest.raises(Exception):
