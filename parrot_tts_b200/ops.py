@@ -83,6 +83,8 @@ def wav_to_pcm16(wav):
     _need_cuda(wav)
     wav = _f32(wav)
     pcm = torch.empty(wav.shape, device=wav.device, dtype=torch.int16)
+    if wav.numel() == 0:
+        return pcm
     with torch.cuda.device(wav.device):
         _lib.check(_lib.load().pb_wav_to_pcm16(_lib.ptr(wav), wav.numel(), _lib.ptr(pcm), _lib.stream_ptr(wav.device)))
     return pcm
@@ -101,6 +103,8 @@ def peak_normalize(pcm):
     B, n = (1, pcm.numel()) if pcm.dim() == 1 else pcm.shape
     out = torch.empty(pcm.shape, device=pcm.device, dtype=torch.float32)
     peak = torch.empty(max(B, 1), device=pcm.device, dtype=torch.int32)
+    if pcm.numel() == 0:
+        return out
     with torch.cuda.device(pcm.device):
         _lib.check(_lib.load().pb_pcm16_peak_normalize(_lib.ptr(pcm), B, n, _lib.ptr(peak), _lib.ptr(out),
                                                         _lib.stream_ptr(pcm.device)))

@@ -1,0 +1,103 @@
+"""Batching front door for the vocoder.
+
+The reference synthesises one utterance per call - ``DataLoader(batch_size=1)`` (inference.py:31-37) and
+``Pool.imap(inference, idxs)`` over single items (utils/vocoder/inference.py:146-171,253-256) - then converts to int16 on the
+host and peak-normalises with librosa before writing the wav (:71-73,169).  Here the same per-utterance results come out of
+length-bucketed ragged batches: every item is masked to its own length inside the kernels (``lens=``), so it equals its
+batch-of-1 result; the x32768 / int16 cast and the peak normalisation run on the device; utterances longer than
+``long_form_units`` are streamed in chunks with a halo (BASELINE configs[4]); under ``torch.distributed`` each rank takes its
+longest-processing-time-first share and nothing is exchanged on the data path.
+
+Host logic only - every sample is produced by the CUDA library (no CPU fallback: CPU tensors raise in the ops)."""
+import torch
+
+from . import ops, sharding
+from .vocoder.inference import stream_generate
+
+
+def plan_batches(lengths, max_batch=8, max_pad_ratio=1.25, long_form_units=None, indices=None):
+    """-> (batches, long_form, empty): ``batches`` = lists of utterance indices (longest first, shortest item within
+    ``max_pad_ratio`` of the longest, at most ``max_batch`` items); ``long_form`` = indices streamed on their own;
+    ``empty`` = zero-length utterances (no launch).  Pure function of the lengths: every rank computes the same plan
+    without communicating."""
+    idx = list(range(len(lengths))) if indices is None else list(indices)
+    long_form = [i for i in idx if long_form_units is not None and lengths[i] > long_form_units]
+    skip = set(long_form)
+    rest = [i for i in idx if i not in skip]
+    empty = [i for i in rest if lengths[i] == 0]
+    rest = [i for i in rest if lengths[i] > 0]
+    return sharding.length_buckets(rest, lengths, max_batch, max_pad_ratio), long_form, empty
+
+
+def rank_share(lengths, world_size, rank):
+    """Indices of the utterances rank ``rank`` synthesises (LPT on the vocoder cost; same on every rank)."""
+    costs = [sharding.utterance_cost(n, with_tte=False) for n in lengths]
+    return sorted(sharding.lpt_assign(costs, world_size)[rank])
+
+
+class BatchSynthesizer:
+    """``synth = BatchSynthesizer(generator); audio = synth(codes, spkrs)`` - list of unit sequences in, list of per-utterance
+    audio out (same order).  ``generator`` is a ``parrot_tts_b200.vocoder.CodeGenerator`` on a CUDA device."""
+
+    def __init__(self, generator, max_batch=8, max_pad_ratio=1.25, long_form_units=8192, chunk_units=1024, halo_units=32):
+        self.generator = generator
+        self.max_batch = int(max_batch)
+        self.max_pad_ratio = float(max_pad_ratio)
+        self.long_form_units = long_form_units
+        self.chunk_units = int(chunk_units)
+        self.halo_units = int(halo_units)
+        self.last_plan = None
+
+    def _device(self):
+        return next(self.generator.parameters()).device
+
+    def __call__(self, codes, spkrs=None, pcm16=True, normalize=False, indices=None, to_host=True):
+        """codes: list of 1-D int sequences (lists / tensors) of unit ids; spkrs: list of speaker ids (or None for a
+        single-speaker generator).  Returns a list aligned with ``codes`` (``None`` for utterances outside ``indices``):
+        int16 PCM (``pcm16``), float32 peak-normalised audio (``normalize``: librosa.util.normalize of the int16 audio, as
+        the reference writes it), or the raw float32 waveform; numpy arrays when ``to_host`` else device tensors."""
+        if normalize and not pcm16:
+            raise ValueError("normalize=True normalises the int16 audio (as the reference does): it needs pcm16=True")
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("BatchSynthesizer needs a generator on a CUDA device (there is no CPU path)")
+        hop = self.generator.hop
+        codes = [torch.as_tensor(c, dtype=torch.long).reshape(-1) for c in codes]
+        lengths = [int(c.numel()) for c in codes]
+        batches, long_form, empty = plan_batches(lengths, self.max_batch, self.max_pad_ratio, self.long_form_units, indices)
+        self.last_plan = {"batches": batches, "long_form": long_form, "empty": empty,
+                          "units": sum(lengths[i] for b in batches for i in b),
+                          "padded_units": sum(len(b) * lengths[b[0]] for b in batches)}
+        out = [None] * len(codes)
+
+        def finish(wav):                               # f32 [n] on the device -> requested format
+            if not pcm16:
+                return wav
+            pcm = ops.wav_to_pcm16(wav.contiguous())
+            return ops.peak_normalize(pcm) if normalize else pcm
+
+        def spk(i):
+            return 0 if spkrs is None else int(spkrs[i])
+
+        for b in batches:
+            Lmax = lengths[b[0]]
+            host = torch.zeros(len(b), Lmax, dtype=torch.long).pin_memory()
+            for r, i in enumerate(b):
+                host[r, :lengths[i]] = codes[i]
+            kw = {"code": host.to(dev, non_blocking=True),
+                  "lens": torch.tensor([lengths[i] for i in b], dtype=torch.int32).to(dev, non_blocking=True)}
+            if spkrs is not None:
+                kw["spkr"] = torch.tensor([[spk(i)] for i in b], dtype=torch.long).to(dev, non_blocking=True)
+            wav = self.generator(**kw)                 # [len(b), 1, hop * Lmax], zero beyond each item's end
+            for r, i in enumerate(b):
+                out[i] = finish(wav[r, 0, :lengths[i] * hop])
+        for i in long_form:                            # streamed: chunks of one utterance, each with its halo
+            code = codes[i].to(dev).unsqueeze(0)
+            sp = torch.tensor([[spk(i)]], dtype=torch.long, device=dev) if spkrs is not None else None
+            parts = [w[0] for _, w in stream_generate(self.generator, code, sp, self.chunk_units, self.halo_units)]
+            out[i] = finish(torch.cat(parts))
+        for i in empty:
+            out[i] = finish(torch.zeros(0, device=dev))
+        if to_host:
+            out = [None if o is None else o.cpu().numpy() for o in out]
+        return out

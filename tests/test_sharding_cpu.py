@@ -96,3 +96,26 @@ def test_stream_chunks_cover_the_utterance():
             assert lo == max(a - halo, 0) and hi == min(b + halo, T)
             if nxt is not None:
                 assert nxt[2] == b
+
+
+def test_serving_plan_is_a_partition_with_bounded_padding():
+    """Batching front door (parrot_tts_b200.serving): every utterance lands in exactly one place, batches respect the
+    size and padding bounds, long utterances are streamed, and the ranks' shares partition the request."""
+    import numpy as np
+    from parrot_tts_b200 import serving
+    lengths = np.random.default_rng(0).integers(0, 12000, 300).tolist()
+    lengths[5] = 0
+    batches, long_form, empty = serving.plan_batches(lengths, max_batch=8, max_pad_ratio=1.25, long_form_units=8192)
+    seen = sorted([i for b in batches for i in b] + long_form + empty)
+    assert seen == list(range(len(lengths)))
+    assert all(lengths[i] > 8192 for i in long_form) and all(lengths[i] == 0 for i in empty)
+    for b in batches:
+        assert 1 <= len(b) <= 8
+        assert lengths[b[0]] == max(lengths[i] for i in b)
+        assert lengths[b[0]] <= 1.25 * min(lengths[i] for i in b)
+    shares = [serving.rank_share(lengths, 4, r) for r in range(4)]
+    assert sorted(i for s in shares for i in s) == list(range(len(lengths)))
+    loads = [sum(lengths[i] for i in s) for s in shares]
+    assert max(loads) <= 1.02 * (sum(loads) / 4) + max(lengths)          # LPT: balanced to within one utterance
+    sub_batches, sub_long, sub_empty = serving.plan_batches(lengths, indices=shares[1], long_form_units=8192)
+    assert sorted([i for b in sub_batches for i in b] + sub_long + sub_empty) == shares[1]

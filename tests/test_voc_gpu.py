@@ -298,3 +298,33 @@ assert e1 < 1e-4 and e2 < 2e-5, (e1, e2)
     env = dict(os.environ, PB_TC_CLUSTER="0", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_batch_synthesizer_equals_per_utterance_generate():
+    """Batching front door: ragged length-bucketed batches, device-side PCM and peak normalisation, long-form
+    streaming - every utterance equals the reference-style one-at-a-time `generate()` result (bit-exact int16)."""
+    from parrot_tts_b200.serving import BatchSynthesizer
+    from parrot_tts_b200.vocoder import generate, normalize
+    h, sd, gen = _code_generator(0)
+    g = _gen(11)
+    lengths = [40, 37, 36, 12, 0, 150, 33, 9]
+    codes = [torch.randint(0, 1000, (n,), generator=g) for n in lengths]
+    spk = [int(torch.randint(0, 10, (1,), generator=g)) for _ in lengths]
+    synth = BatchSynthesizer(gen, max_batch=3, max_pad_ratio=1.25, long_form_units=100, chunk_units=64, halo_units=32)
+    got = synth(codes, spk)
+    assert synth.last_plan["long_form"] == [5] and synth.last_plan["empty"] == [4]
+    assert all(len(b) <= 3 for b in synth.last_plan["batches"])
+    got_n = synth(codes, spk, normalize=True)
+    for i, n in enumerate(lengths):
+        assert got[i].dtype == np.int16 and got[i].shape == (n * 320,)
+        if n == 0:
+            continue
+        ref, _ = generate(h, gen, dict(code=codes[i].view(1, -1).to(DEV), spkr=torch.tensor([[spk[i]]], device=DEV)))
+        if i == 5:      # streamed in chunks: the unchunked values up to fp32 round-off (waveform within 2e-4 -> a few LSB at most)
+            assert np.abs(got[i].astype(np.int32) - ref.astype(np.int32)).max() <= 2
+        else:
+            assert np.array_equal(got[i], ref), i
+        assert np.array_equal(got_n[i], normalize(got[i]))
+    part = synth(codes, spk, indices=[0, 3])
+    assert [p is not None for p in part] == [True, False, False, True, False, False, False, False]
+    assert np.array_equal(part[3], got[3])

@@ -1,6 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for m in 0 1; do
-PB_TC_TMA_OUT=$m timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-    --log-file gpurun_out/launches_tma$m.csv python tools/prof_voc.py 8 1024 1 0 > gpurun_out/ncu_voc.log 2>&1; echo "ncu rc=$?"
-done
+timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q -k "synthesizer or peak or pcm or stream" 2>&1 | tail -15
