@@ -414,6 +414,30 @@ def run_ours(args):
                     "tte_ms": ms3_tte, "value": world * t3["n"] / (ms3 * 1e-3), "unit": "samples/s",
                     "rtf_16k": t3["n"] / (ms3 * 1e-3) / 16000.0, "gpu_launches_per_step": t3["launch"]}
 
+    # ---- supplementary: configs[0] single-utterance latency: 64 chars -> 512 units -> int16 PCM on the host ---------
+    latency = None
+    if S == 0 and not args.no_text2wav:
+        from parrot_tts_b200 import ops as _ops
+        ph1_h = torch.randint(2, 150, (1, 64), generator=g).pin_memory()
+        sp1 = torch.zeros(1, 1, dtype=torch.long, device=dev)
+        spk1 = torch.zeros(1, dtype=torch.long, device=dev)
+
+        def run1():
+            ph = ph1_h.to(dev, non_blocking=True)
+            ids, _ = tte.infer_device({"phones": ph, "src_mask": ph != 0, "speaker": spk1})
+            return _ops.wav_to_pcm16(voc(code=ids, spkr=sp1)).cpu().numel()
+
+        for _ in range(3):
+            run1()
+        ts = []
+        for _ in range(20):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); n1 = run1(); ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        latency = {"workload": "cfg1: 1 utterance, 64 chars -> TTE -> 512 units -> CodeGenerator -> int16 PCM on host (wall clock)",
+                   "median_ms": ts[len(ts) // 2], "min_ms": ts[0], "samples": n1, "rtf_16k": n1 / (ts[len(ts) // 2] * 1e-3) / 16000.0,
+                   "gpu_launches": tte.last_launches + voc.last_launches + 1}
+
     # ---- supplementary: configs[4] long-form streaming: 16 384 units in 1024-unit chunks with a 32-unit halo -------
     streaming = None
     if S == 0 and not args.no_streaming:
@@ -468,7 +492,7 @@ def run_ours(args):
             "rtf_16k": value / 16000.0, "rtf_22k05": value / 22050.0,
             "vocoder_algorithmic_tflops": VOC_FLOP_PER_UNIT * units * world / (ms_step * 1e-3) / 1e12 if S == 0 else None,
             "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "text2wav": text2wav, "streaming": streaming,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "text2wav": text2wav, "latency": latency, "streaming": streaming,
         }
         if quiet is not None:
             quiet.restore()

@@ -1,3 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q -k "synthesizer or peak or pcm or stream" 2>&1 | tail -15
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_quick.json'))
+print('ms_per_step',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'])
+print(d['latency']); print(d['streaming'])
+PY
+tail -3 gpurun_out/bench_quick.err
