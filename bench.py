@@ -422,21 +422,35 @@ def run_ours(args):
         sp1 = torch.zeros(1, 1, dtype=torch.long, device=dev)
         spk1 = torch.zeros(1, dtype=torch.long, device=dev)
 
-        def run1():
+        from parrot_tts_b200.vocoder import GraphedGenerator
+        voc_graphs = {}
+
+        def run1(graphed=False):
             ph = ph1_h.to(dev, non_blocking=True)
             ids, _ = tte.infer_device({"phones": ph, "src_mask": ph != 0, "speaker": spk1})
-            return _ops.wav_to_pcm16(voc(code=ids, spkr=sp1)).cpu().numel()
+            if not graphed:
+                return _ops.wav_to_pcm16(voc(code=ids, spkr=sp1)).cpu().numel()
+            T1 = int(ids.shape[1])
+            if T1 not in voc_graphs:      # the vocoder forward + PCM cast of this length as one CUDA graph
+                voc_graphs[T1] = GraphedGenerator(voc, 1, T1, pcm16=True)
+            return voc_graphs[T1](ids, sp1).cpu().numel()
 
-        for _ in range(3):
-            run1()
-        ts = []
-        for _ in range(20):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter(); n1 = run1(); ts.append((time.perf_counter() - t0) * 1e3)
-        ts.sort()
+        def wall(fn):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(20):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter(); n = fn(); ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            return ts, n
+
+        ts, n1 = wall(run1)
+        tg, _ = wall(lambda: run1(True))
         latency = {"workload": "cfg1: 1 utterance, 64 chars -> TTE -> 512 units -> CodeGenerator -> int16 PCM on host (wall clock)",
                    "median_ms": ts[len(ts) // 2], "min_ms": ts[0], "samples": n1, "rtf_16k": n1 / (ts[len(ts) // 2] * 1e-3) / 16000.0,
-                   "gpu_launches": tte.last_launches + voc.last_launches + 1}
+                   "gpu_launches": tte.last_launches + voc.last_launches + 1,
+                   "vocoder_cuda_graph": {"median_ms": tg[len(tg) // 2], "min_ms": tg[0]}}
 
     # ---- supplementary: configs[4] long-form streaming: 16 384 units in 1024-unit chunks with a 32-unit halo -------
     streaming = None
@@ -445,10 +459,12 @@ def run_ours(args):
         code5_h = torch.randint(0, 1000, (1, 16384), generator=g).pin_memory()
         spk5 = torch.zeros(1, 1, dtype=torch.long, device=dev)
 
-        def run_stream(first_only):
+        stream_graphs = {}
+
+        def run_stream(first_only, graphs=None):
             c5 = code5_h.to(dev, non_blocking=True)
             n = 0
-            for _, pcm in stream_generate(voc, c5, spk5, chunk_units=1024, halo_units=32, pcm16=True):
+            for _, pcm in stream_generate(voc, c5, spk5, chunk_units=1024, halo_units=32, pcm16=True, graphs=graphs):
                 n += pcm.cpu().numel()       # int16 PCM of the chunk on the host
                 if first_only:
                     break
@@ -461,6 +477,11 @@ def run_ours(args):
         streaming = {"workload": "cfg5: 16 384 units streamed as 16 chunks of 1024 units (+32-unit halo), host codes -> int16 PCM on host",
                      "time_to_first_chunk_ms": first_ms, "steady_samples_per_s": n5 / all_s, "rtf_16k": n5 / all_s / 16000.0,
                      "total_ms": all_s * 1e3}
+        run_stream(False, stream_graphs)               # captures one CUDA graph per window length (3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); run_stream(True, stream_graphs); first_g = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); n5g = run_stream(False, stream_graphs); all_g = time.perf_counter() - t0
+        streaming["cuda_graphs"] = {"time_to_first_chunk_ms": first_g, "steady_samples_per_s": n5g / all_g, "total_ms": all_g * 1e3}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -----------------------------
     cpu = None

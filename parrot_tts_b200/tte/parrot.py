@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ._engine import TteEngine, need_cuda
+from .._weights import WeightStamp
 from .duration import DurationPredictor
 from .fft import FFTBlock, SinusoidalPosEmb
 
@@ -50,6 +51,7 @@ class Parrot(nn.Module):
         self.decoder_layers = stack("decoder")
         self.head = nn.Linear(self.d_model, self.n_codes)
         self._eng = TteEngine()
+        self._wstamp = WeightStamp(self)
         self.last_launches = 0
 
     # ------------------------------------------------------------------ engine
@@ -64,7 +66,7 @@ class Parrot(nn.Module):
                    conv_k2=tr["conv_kernel_sizes"][1], dp_n_filter=dp["n_filter"], dp_kernel=dp["kernel_size"],
                    n_codes=self.n_codes, max_len=self.max_len, fold_projections=int(self.fold_projections),
                    gemm_mode=int(self.gemm_mode) if self.fold_projections else 0)   # the unfolded reference mode is fp32 SIMT
-        return self._eng.get(cfg, dict(self.state_dict(keep_vars=True)), device)
+        return self._eng.get(cfg, self._wstamp, device)
 
     def _encode(self, batch, dur_in=None):
         phones = batch["phones"]

@@ -43,6 +43,56 @@ def normalize(audio, device="cuda"):
     return ops.peak_normalize(torch.from_numpy(a).to(device)).cpu().numpy()
 
 
+class GraphedGenerator:
+    """CUDA-graph replay of ``generator(code=, spkr=, lens=)`` for one fixed ``[B, T]`` shape: the ~80 launches of a forward are
+    captured once (stream capture keeps the programmatic-dependent-launch edges and the cluster launches) and replayed with
+    one driver call, which is what bounds the small, latency-critical calls (a single utterance, the chunks of a stream).
+    Inputs are copied into static buffers; the returned waveform (or int16 PCM with ``pcm16=True``) is a static buffer too,
+    valid until the next call.  Capture the LARGEST shape you will use first: a later, larger forward of the same generator
+    regrows its workspace and invalidates graphs captured before it."""
+
+    def __init__(self, generator, B, T, pcm16=False):
+        dev = next(generator.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedGenerator needs a generator on a CUDA device")
+        self.generator, self.B, self.T, self.pcm16 = generator, int(B), int(T), bool(pcm16)
+        self.code = torch.zeros(B, T, dtype=torch.long, device=dev)
+        self.spkr = torch.zeros(B, 1, dtype=torch.long, device=dev) if getattr(generator, "multispkr", None) else None
+        self.lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+
+        def run():
+            kw = {"code": self.code, "lens": self.lens}
+            if self.spkr is not None:
+                kw["spkr"] = self.spkr
+            wav = generator(**kw)
+            return ops.wav_to_pcm16(wav) if self.pcm16 else wav
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                  # warm-up off the capture: engine, workspace, function attributes
+            run(); run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+
+    def __call__(self, code, spkr=None, lens=None):
+        if tuple(code.shape) != (self.B, self.T):
+            raise ValueError(f"GraphedGenerator captured for {(self.B, self.T)}, got {tuple(code.shape)}")
+        self.code.copy_(code, non_blocking=True)
+        if self.spkr is not None:
+            if spkr is None:
+                raise KeyError("spkr")
+            self.spkr.copy_(spkr.reshape(self.B, 1), non_blocking=True)
+        if lens is None:
+            self.lens.fill_(self.T)
+        else:
+            self.lens.copy_(torch.as_tensor(lens).to(torch.int32), non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def stream_chunks(n_units, chunk_units=1024, halo_units=32):
     """[(lo, hi, a, b)]: chunk i synthesises units [a, b) from the window [lo, hi) = [a - halo, b + halo) clipped to the
     utterance.  The generator is purely convolutional with a receptive-field radius of ~23 units,
@@ -54,15 +104,24 @@ def stream_chunks(n_units, chunk_units=1024, halo_units=32):
     return out
 
 
-def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32, pcm16=False):
+def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32, pcm16=False, graphs=None):
     """Long-form synthesis in chunks (BASELINE configs[4]): yields (first_sample, audio) per chunk, audio f32 [B, n] on the
     device (or int16 with ``pcm16=True``), n = hop * (b - a).  ``code`` i64 [B, T] on the device.  Each chunk is one
-    ``generator(code=window, spkr=spkr)`` call on the window of units it needs; nothing is recomputed beyond the two halos."""
+    ``generator(code=window, spkr=spkr)`` call on the window of units it needs; nothing is recomputed beyond the two halos.
+    ``graphs={}`` replays one CUDA graph per distinct window length instead (the dict can be kept for the next stream)."""
     T = code.shape[1]
     hop = generator.hop
-    for lo, hi, a, b in stream_chunks(T, chunk_units, halo_units):
-        kw = {"code": code[:, lo:hi].contiguous()}
-        if spkr is not None:
-            kw["spkr"] = spkr
-        wav = generator(**kw)[:, 0, (a - lo) * hop:(b - lo) * hop]
+    chunks = stream_chunks(T, chunk_units, halo_units)
+    if graphs is not None:      # dict {window length: GraphedGenerator}, filled here (largest window first) and reusable across streams
+        for n in sorted({hi - lo for lo, hi, _, _ in chunks}, reverse=True):
+            if n not in graphs:
+                graphs[n] = GraphedGenerator(generator, code.shape[0], n)
+    for lo, hi, a, b in chunks:
+        if graphs is not None:
+            wav = graphs[hi - lo](code[:, lo:hi], spkr)[:, 0, (a - lo) * hop:(b - lo) * hop]
+        else:
+            kw = {"code": code[:, lo:hi].contiguous()}
+            if spkr is not None:
+                kw["spkr"] = spkr
+            wav = generator(**kw)[:, 0, (a - lo) * hop:(b - lo) * hop]
         yield a * hop, (ops.wav_to_pcm16(wav.contiguous()) if pcm16 else wav)

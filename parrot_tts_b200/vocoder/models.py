@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from .._weights import WeightStamp
 from .utils import get_padding, init_weights
 
 LRELU_SLOPE = 0.1
@@ -111,6 +112,7 @@ class Generator(nn.Module):
         self.ups.apply(init_weights)
         self.conv_post.apply(init_weights)
         self._eng = _Engine()
+        self._wstamp = None
         self.hop = 1
         for u in h.upsample_rates:
             self.hop *= int(u)
@@ -144,7 +146,9 @@ class Generator(nn.Module):
         return cfg
 
     def _stamp(self, device):
-        return (str(device), int(self.conv_mode)) + tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        if self._wstamp is None:
+            self._wstamp = WeightStamp(self)
+        return (str(device), int(self.conv_mode)) + self._wstamp.stamp()
 
     def _engine(self, device):
         """pb_voc handle holding the folded + packed copy of the current parameters."""
