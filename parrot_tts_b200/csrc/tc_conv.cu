@@ -58,7 +58,8 @@ struct TcParams {
     int cluster;                         // 1: CTA pairs (cta_group::2): M = 256 per pair, each CTA streams half of the weight rows
     int fmt;                             // split storage / MMA operand type: 0 bf16, 1 fp16
     int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
-    int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads
+    int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads,
+                  // 16 = skip the accumulator reads, 32 = skip the epilogue arithmetic
 };
 
 }  // namespace
