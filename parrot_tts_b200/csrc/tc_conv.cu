@@ -737,7 +737,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     // stay resident for the whole launch, the rest stream through a ring of sub-blocks once per tile.
     //  - everything resident + >= 3 activation stages in HALF an SM: two CTAs per SM (narrow layers are latency bound per tile)
     //  - everything resident + >= 2 stages in a whole SM: one CTA per SM
-    //  - otherwise 2 activation stages, a 4-deep ring, and as many resident blocks as still fit - kept only when they
+    //  - otherwise 2 activation stages, a 3-deep ring, and as many resident blocks as still fit - kept only when they
     //    cover at least a quarter of the operand (else the space buys more pipeline depth instead)
     int ctas_per_sm = 1;
     uint32_t b_res_bytes = 0, ring_bytes = 0;
@@ -784,8 +784,11 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
                    "tc_conv: tile does not fit in shared memory (Cin=%d N=%d K=%d D=%d)", a.Cin, a.N, a.K, a.D);
         p.n_a_stages = 2;
         uint32_t left = bud - 2u * (uint32_t)p.a_stage_bytes;
+        // ring depth vs resident blocks (PB_TC_RING, dev switch): measured on the 64-channel k = 11 layers, 2 / 3 / 4 / 6 slots ->
+        // 161 / 161 / 165 / 179 us - the ring hides L2 latency with 2-3 slots already, every further slot costs a resident block
+        static const int ring_max = getenv("PB_TC_RING") ? atoi(getenv("PB_TC_RING")) : 3;
         p.n_b_stages = (int)(left / (uint32_t)p.b_sub_bytes);
-        if (p.n_b_stages > 4) p.n_b_stages = 4;
+        if (p.n_b_stages > ring_max) p.n_b_stages = ring_max;
         left -= (uint32_t)p.n_b_stages * (uint32_t)p.b_sub_bytes;
         p.res_blocks = (int)(left / (uint32_t)p.b_block_bytes);
         if (p.res_blocks * 4 < p.total_blocks) {

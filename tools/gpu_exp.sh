@@ -1,11 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_quick.json'))
-print('ms_per_step',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'])
-print(d['latency']); print(d['streaming']); print(d['text2wav'])
-PY
-tail -5 gpurun_out/bench_quick.err
+for m in 2 3 4 6; do
+PB_TC_RING=$m timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file gpurun_out/launches_ring$m.csv python tools/prof_voc.py 8 1024 1 0 > gpurun_out/ncu_voc.log 2>&1; echo "ncu rc=$?"
+done
