@@ -90,6 +90,18 @@ def wav_to_pcm16(wav):
     return pcm
 
 
+def to_host(t):
+    """Device tensor -> numpy through a pinned staging tensor from torch's caching host allocator: a D2H copy into pageable
+    memory (``.cpu()``) runs at ~10 GB/s, into pinned memory at PCIe speed - 0.3 ms of the 5 MB of PCM an 8 x 1024-unit batch
+    produces.  The array keeps the pinned block alive; it returns to the cache when the array is dropped."""
+    _need_cuda(t)
+    t = t.contiguous()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
 def peak_normalize(pcm):
     """`librosa.util.normalize(audio.astype(np.float32))` on the device (utils/vocoder/inference.py:169, demo cell 13):
     int16 PCM [n] or [B, n] -> float32 of the same shape, every utterance divided by its own max |sample|

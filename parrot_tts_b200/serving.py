@@ -99,5 +99,5 @@ class BatchSynthesizer:
         for i in empty:
             out[i] = finish(torch.zeros(0, device=dev))
         if to_host:
-            out = [None if o is None else o.cpu().numpy() for o in out]
+            out = [None if o is None else (ops.to_host(o) if o.numel() else o.cpu().numpy()) for o in out]
         return out

@@ -25,7 +25,7 @@ def generate(h, generator, code):
     y_g_hat = generator(**code)
     if type(y_g_hat) is tuple:
         y_g_hat = y_g_hat[0]
-    audio = ops.wav_to_pcm16(y_g_hat.squeeze()).cpu().numpy()
+    audio = ops.to_host(ops.wav_to_pcm16(y_g_hat.squeeze()))
     rtf = (time.time() - start) / (y_g_hat.shape[-1] / h.sampling_rate)
     return audio, rtf
 
@@ -40,7 +40,7 @@ def normalize(audio, device="cuda"):
     a = np.ascontiguousarray(audio)
     if a.dtype != np.int16:
         raise TypeError("normalize expects the int16 audio that generate() returns")
-    return ops.peak_normalize(torch.from_numpy(a).to(device)).cpu().numpy()
+    return ops.to_host(ops.peak_normalize(torch.from_numpy(a).to(device)))
 
 
 class GraphedGenerator:
