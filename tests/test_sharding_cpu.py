@@ -119,3 +119,44 @@ def test_serving_plan_is_a_partition_with_bounded_padding():
     assert max(loads) <= 1.02 * (sum(loads) / 4) + max(lengths)          # LPT: balanced to within one utterance
     sub_batches, sub_long, sub_empty = serving.plan_batches(lengths, indices=shares[1], long_form_units=8192)
     assert sorted([i for b in sub_batches for i in b] + sub_long + sub_empty) == shares[1]
+
+
+def test_scheduling_invariants_property_based():
+    """Property tests (hypothesis) of the host scheduling logic: LPT shares partition the request and are balanced to within
+    the largest item; length buckets respect the size / padding bounds; stream chunks tile the utterance exactly once and
+    every window carries the requested halo (clipped at the ends)."""
+    from hypothesis import given, settings, strategies as st
+    from parrot_tts_b200 import serving, sharding
+    from parrot_tts_b200.vocoder import stream_chunks
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(0, 5000), min_size=0, max_size=80), st.integers(1, 8), st.integers(1, 9),
+           st.floats(1.0, 2.0))
+    def sched(lengths, world, max_batch, ratio):
+        costs = [sharding.utterance_cost(n, with_tte=False) for n in lengths]
+        bins = sharding.lpt_assign(costs, world)
+        assert sorted(i for b in bins for i in b) == list(range(len(lengths)))
+        if lengths:
+            loads = [sum(costs[i] for i in b) for b in bins]
+            assert max(loads) - min(loads) <= max(costs) + 1e-6
+        for r in range(world):
+            batches, long_form, empty = serving.plan_batches(lengths, max_batch, ratio, 4096, indices=bins[r])
+            assert sorted([i for b in batches for i in b] + long_form + empty) == sorted(bins[r])
+            for b in batches:
+                assert 1 <= len(b) <= max_batch
+                assert all(0 < lengths[i] <= 4096 for i in b)
+                assert lengths[b[0]] <= ratio * min(lengths[i] for i in b) + 1e-9
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 20000), st.integers(1, 2048), st.integers(0, 64))
+    def chunks(n, chunk, halo):
+        cs = stream_chunks(n, chunk, halo)
+        assert cs[0][2] == 0 and cs[-1][3] == n
+        for (lo, hi, a, b), nxt in zip(cs, cs[1:] + [None]):
+            assert 0 <= lo <= a < b <= hi <= n and b - a <= chunk
+            assert lo == max(a - halo, 0) and hi == min(b + halo, n)
+            if nxt is not None:
+                assert nxt[2] == b
+
+    sched()
+    chunks()
