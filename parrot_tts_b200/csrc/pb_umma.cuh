@@ -47,6 +47,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2): one instruction per two lanes of a thread's row, IEEE round-to-nearest per lane - the
+// same results as the scalar operations, half the issue slots in the epilogues.
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb;\n mov.b64 ra, {%0, %1};\n mov.b64 rb, {%2, %3};\n add.rn.f32x2 ra, ra, rb;\n mov.b64 {%0, %1}, ra; }"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float& a0, float& a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb;\n mov.b64 ra, {%0, %1};\n mov.b64 rb, {%2, %3};\n sub.rn.f32x2 ra, ra, rb;\n mov.b64 {%0, %1}, ra; }"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb;\n mov.b64 ra, {%0, %1};\n mov.b64 rb, {%2, %3};\n mul.rn.f32x2 ra, ra, rb;\n mov.b64 {%0, %1}, ra; }"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+
 // two 16-column blocks of the same lanes, summed (the hi.hi + lo.hi block and the hi.lo block of a stacked accumulator)
 __device__ __forceinline__ void tmem_ld16x2_sum(uint32_t t0, uint32_t t1, float* v) {
     uint32_t r[16], u[16];
@@ -64,7 +79,10 @@ __device__ __forceinline__ void tmem_ld16x2_sum(uint32_t t0, uint32_t t1, float*
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(u[i]);
+    for (int i = 0; i < 8; ++i) {
+        v[2 * i] = __uint_as_float(r[2 * i]); v[2 * i + 1] = __uint_as_float(r[2 * i + 1]);
+        add2(v[2 * i], v[2 * i + 1], __uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+    }
 }
 
 // shared-memory matrix descriptor (sm_100 "version 1"): start address, leading / stride byte offsets in 16-byte units
@@ -232,7 +250,8 @@ __device__ __forceinline__ void split2(float a, float b, int fmt, uint32_t& hw, 
     if (fmt == 0) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
         hw = *reinterpret_cast<const uint32_t*>(&h2);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - bf16lo(hw), b - bf16hi(hw));
+        sub2(a, b, bf16lo(hw), bf16hi(hw));
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a, b);
         lw = *reinterpret_cast<const uint32_t*>(&l2);
     } else {
         a = fminf(fmaxf(a, -65504.f), 65504.f);      // saturate instead of overflowing to inf
@@ -240,15 +259,21 @@ __device__ __forceinline__ void split2(float a, float b, int fmt, uint32_t& hw, 
         const __half2 h2 = __floats2half2_rn(a, b);
         hw = *reinterpret_cast<const uint32_t*>(&h2);
         const float2 hf = __half22float2(h2);
-        const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+        sub2(a, b, hf.x, hf.y);
+        const __half2 l2 = __floats2half2_rn(a, b);
         lw = *reinterpret_cast<const uint32_t*>(&l2);
     }
 }
 __device__ __forceinline__ float2 join2(uint32_t hw, uint32_t lw, int fmt) {
-    if (fmt == 0) return make_float2(bf16lo(hw) + bf16lo(lw), bf16hi(hw) + bf16hi(lw));
-    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+    if (fmt == 0) {
+        float2 r = make_float2(bf16lo(hw), bf16hi(hw));
+        add2(r.x, r.y, bf16lo(lw), bf16hi(lw));
+        return r;
+    }
+    float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw));
     const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lw));
-    return make_float2(h.x + l.x, h.y + l.y);
+    add2(h.x, h.y, l.x, l.y);
+    return h;
 }
 __device__ __forceinline__ void split1(float v, int fmt, uint16_t& hi, uint16_t& lo) {
     if (fmt == 0) {

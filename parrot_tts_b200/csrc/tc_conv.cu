@@ -506,7 +506,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 bv = bv4[i];
-                    v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
+                    add2(v[4 * i], v[4 * i + 1], bv.x, bv.y);
+                    add2(v[4 * i + 2], v[4 * i + 3], bv.z, bv.w);
                 }
                 if (RES) {
                     const uint32_t hh[8] = {R[0].x, R[0].y, R[0].z, R[0].w, R[1].x, R[1].y, R[1].z, R[1].w};
@@ -514,8 +515,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float2 r = join2(hh[i], ll[i], p.fmt);
-                        v[2 * i] += fminf(r.x, r.x * p.res_unslope);       // undo the stored leaky relu (1/slope >= 1)
-                        v[2 * i + 1] += fminf(r.y, r.y * p.res_unslope);
+                        float tx = r.x, ty = r.y;
+                        mul2(tx, ty, p.res_unslope, p.res_unslope);
+                        add2(v[2 * i], v[2 * i + 1], fminf(r.x, tx), fminf(r.y, ty));      // undo the stored leaky relu (1/slope >= 1)
                     }
                 }
                 if (ACC) {
@@ -524,8 +526,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float2 r = join2(hh[i], ll[i], p.fmt);
-                        v[2 * i] = r.x + v[2 * i];
-                        v[2 * i + 1] = r.y + v[2 * i + 1];
+                        add2(v[2 * i], v[2 * i + 1], r.x, r.y);
                     }
                 }
             }
@@ -545,9 +546,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 }
                 const float sc = live ? p.scale : 0.f;      // rows past the valid length are written as zeros
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float u = v[i] * sc;
-                    v[i] = fmaxf(u, u * p.post_slope);      // leaky relu for slope in [0,1]; slope 1 = identity
+                for (int i = 0; i < 8; ++i) {
+                    mul2(v[2 * i], v[2 * i + 1], sc, sc);
+                    float tx = v[2 * i], ty = v[2 * i + 1];
+                    mul2(tx, ty, p.post_slope, p.post_slope);
+                    v[2 * i] = fmaxf(v[2 * i], tx);         // leaky relu for slope in [0,1]; slope 1 = identity
+                    v[2 * i + 1] = fmaxf(v[2 * i + 1], ty);
                 }
                 if (p.tanh_out) {
 #pragma unroll
