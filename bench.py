@@ -46,12 +46,36 @@ def parse():
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, source).  The driver-written file is read tolerantly (keys may sit one
+    level down, a value may be missing): a malformed file must not take the bench line with it."""
+    fb_hbm, fb_tf = 6650.0, 1400.0
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(p):
+    if not os.path.isfile(p):
+        return fb_hbm, fb_tf, "fallback (B200_PROFILING.md)"
+
+    def find(d, key):
+        if isinstance(d, dict):
+            if isinstance(d.get(key), (int, float)) and d[key] > 0:
+                return float(d[key])
+            for v in d.values():
+                r = find(v, key)
+                if r is not None:
+                    return r
+        return None
+
+    try:
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+    except (OSError, ValueError):
+        return fb_hbm, fb_tf, "fallback (MEASURED_PEAKS.json unreadable)"
+    hbm = find(d, "hbm_gbs")
+    tf = find(d, "bf16_tflops_sustained") or find(d, "bf16_tflops")
+    if hbm is None and tf is None:
+        return fb_hbm, fb_tf, "fallback (MEASURED_PEAKS.json holds neither hbm_gbs nor bf16_tflops)"
+    src = "measured (MEASURED_PEAKS.json)"
+    if hbm is None or tf is None:
+        src += "; fallback for " + ("hbm_gbs" if hbm is None else "bf16_tflops")
+    return hbm or fb_hbm, tf or fb_tf, src
 
 
 def workload_shape(name):

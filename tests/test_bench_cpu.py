@@ -32,3 +32,21 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_peaks_reader_tolerates_the_driver_file(tmp_path, monkeypatch):
+    """roofline denominators: flat keys, nested keys, a missing value and a broken file all give numbers."""
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.peaks() == (6650.0, 1400.0, "fallback (B200_PROFILING.md)")
+    f = tmp_path / "MEASURED_PEAKS.json"
+    f.write_text(json.dumps({"hbm_gbs": 7000.5, "bf16_tflops": 1600, "bf16_tflops_sustained": 1390}))
+    assert bench.peaks()[:2] == (7000.5, 1390.0) and bench.peaks()[2].startswith("measured")
+    f.write_text(json.dumps({"b200": {"hbm_gbs": 6900, "bf16_tflops": 1500}, "clocks": {"sm_mhz": 1965}}))
+    assert bench.peaks()[:2] == (6900.0, 1500.0)
+    f.write_text(json.dumps({"hbm_gbs": 6900}))
+    hbm, tf, src = bench.peaks()
+    assert (hbm, tf) == (6900.0, 1400.0) and "fallback for bf16_tflops" in src
+    f.write_text("{not json")
+    assert bench.peaks()[:2] == (6650.0, 1400.0)
