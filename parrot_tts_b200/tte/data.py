@@ -38,7 +38,8 @@ class DFATokenizer:
             symbols = list(table)
         else:
             raise TypeError(f"symbols.pkl holds a {type(table).__name__}, expected dict or list")
-        symbols = ["sil" if s == " " else s for s in symbols] if " " in symbols else symbols
+        if " " in symbols:                        # the blank is the aligner's silence token (first occurrence, as in the reference)
+            symbols[symbols.index(" ")] = "sil"
         self.symbols = [self.pad, self.sep] + symbols
         self.stoi = {s: i for i, s in enumerate(self.symbols)}
         self.itos = dict(enumerate(self.symbols))
