@@ -160,3 +160,54 @@ def test_scheduling_invariants_property_based():
 
     sched()
     chunks()
+
+
+def test_chunk_halo_is_sufficient_on_the_oracle():
+    """The claim the streaming path rests on, checked on the CPU oracle (the reference graph): synthesising the windows of
+    ``stream_chunks`` and keeping each chunk's own samples equals the unchunked waveform when halo >= the receptive-field radius
+    (~23 units) - and does not with a short halo, so the test can see a broken plan."""
+    import torch
+    from oracle import voc_oracle
+    from parrot_tts_b200 import configs, synth
+    from parrot_tts_b200.vocoder.inference import stream_chunks
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=0)
+    g = torch.Generator().manual_seed(3)
+    T, hop = 150, 320
+    code = torch.randint(0, 1000, (1, T), generator=g)
+    spkr = torch.tensor([[4]])
+    with torch.no_grad():
+        full = voc_oracle.code_generator_forward(sd, h, code, spkr)[0, 0]
+
+        def chunked(halo):
+            parts = []
+            for lo, hi, a, b in stream_chunks(T, 50, halo):
+                w = voc_oracle.code_generator_forward(sd, h, code[:, lo:hi], spkr)[0, 0]
+                parts.append(w[(a - lo) * hop:(b - lo) * hop])
+            return torch.cat(parts)
+
+        ok, short = chunked(24), chunked(6)
+    assert ok.shape == full.shape == (T * hop,)
+    assert float((ok - full).abs().max()) < 1e-5          # same arithmetic, another summation order inside the CPU conv (~1e-6)
+    assert float((short - full).abs().max()) > 1e-4
+
+
+def test_receptive_field_radius_on_the_oracle():
+    """One changed unit moves the waveform only within +-24 units of it (what `halo_units` has to cover)."""
+    import torch
+    from oracle import voc_oracle
+    from parrot_tts_b200 import configs, synth
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=0)
+    g = torch.Generator().manual_seed(5)
+    T, hop, mid = 96, 320, 48
+    code = torch.randint(0, 1000, (1, T), generator=g)
+    other = code.clone()
+    other[0, mid] = (other[0, mid] + 500) % 1000
+    spkr = torch.tensor([[0]])
+    with torch.no_grad():
+        d = (voc_oracle.code_generator_forward(sd, h, code, spkr) - voc_oracle.code_generator_forward(sd, h, other, spkr))[0, 0].abs()
+    touched = torch.nonzero(d > 1e-7).flatten()
+    lo_u, hi_u = int(touched.min()) // hop, int(touched.max()) // hop
+    assert mid - 24 <= lo_u <= mid and mid <= hi_u <= mid + 24, (lo_u, hi_u)
+    assert hi_u - lo_u >= 20                               # and it really is that wide: a halo of a few units would not do
