@@ -58,3 +58,62 @@ def test_voc_oracle_vs_reference(seed, B, T):
     assert "conv_pre.weight" in sd_plain
     wav2 = voc_oracle.code_generator_forward(sd_plain, h, code, spkr)
     np.testing.assert_allclose(wav2.numpy(), ref.numpy(), atol=2e-5, rtol=0)
+
+
+def test_tte_oracle_vs_reference_single_speaker():
+    # speakers.json with one entry: the reference builds no speaker_emb (modules/parrot.py:28-32) and adds nothing (:98-99)
+    cfg = configs.default_tte_config()
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 1, seed=5)
+    assert "speaker_emb.weight" not in sd
+    ref = ref_shim.load_reference_parrot(cfg, 150, 0, 1)
+    ref.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(5)
+    phones = torch.randint(2, 150, (2, 11), generator=g)
+    phones[0, 7:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.zeros(2, dtype=torch.long)}
+    with torch.no_grad():
+        ids_ref = ref.infer(batch)
+    ids, _ = tte_oracle.parrot_infer(sd, batch)
+    assert ids == ids_ref
+
+
+def test_tte_oracle_vs_reference_teacher_forced_and_zero_durations():
+    # Parrot.forward(batch) with batch['duration'] (modules/parrot.py:101-103): includes zero-length characters and an item
+    # whose total is far below the batch maximum (rows of zeros + pe row, still live keys up to len + 1)
+    cfg = configs.default_tte_config()
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=6)
+    ref = ref_shim.load_reference_parrot(cfg, 150, 0, 10)
+    ref.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    phones = torch.randint(2, 150, (3, 8), generator=g)
+    phones[2, 3:] = 0
+    dur = torch.randint(0, 5, (3, 8), generator=g)
+    dur[1] = 0
+    dur[1, 4] = 2
+    dur[2, 3:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([1, 0, 9]), "duration": dur,
+             "tgt_mask": None}              # the reference indexes batch['tgt_mask'] on this path; None = derive it from the durations
+    with torch.no_grad():
+        logits, _, tgt_mask, log_dur = ref(batch)
+    r = tte_oracle.parrot_forward(sd, batch, dur_override=dur)
+    assert torch.equal(r["tgt_mask"], tgt_mask) and r["logits"].shape == logits.shape
+    assert [int(n) for n in r["out_lens"]] == dur.sum(1).tolist()
+    np.testing.assert_allclose(r["logits"].numpy(), logits.numpy(), atol=5e-4, rtol=0)
+    np.testing.assert_allclose(r["log_dur"].numpy(), log_dur.numpy(), atol=2e-5, rtol=0)
+
+
+def test_generator_oracle_vs_reference_feature_input():
+    # Generator.forward on features (utils/vocoder/models.py:95-111) through the reference CodeGenerator's parent class
+    h = configs.default_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=8, weight_norm=True)
+    gen = ref_shim.load_reference_vocoder(h)
+    gen.load_state_dict(sd, strict=True)
+    x = torch.randn(2, h.model_in_dim, 9, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        ref = type(gen).__mro__[1].forward(gen, x)
+    wav = voc_oracle.generator_forward(sd, h, x)
+    np.testing.assert_allclose(wav.numpy(), ref.numpy(), atol=2e-5, rtol=0)
+    # the reference's own int16 expression (utils/vocoder/inference.py:71-73), including a sample that wraps
+    y = torch.tensor([[0.5, -0.25, 0.99999, -1.0, 1.0, 3.0517578125e-05 * 1.5]])
+    want = (y.squeeze() * 32768.0).cpu().numpy().astype("int16")
+    assert np.array_equal(voc_oracle.to_int16(y), want)
