@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libparrot_b200.so")
+# PB_LIB_VARIANT=NAME loads an experiment build (python -m parrot_tts_b200.build --variant NAME --define ...) instead of the product
+_VARIANT = os.environ.get("PB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "lib", f"libparrot_b200_{_VARIANT}.so" if _VARIANT else "libparrot_b200.so")
 
 PB_OK, PB_ERR_INVALID, PB_ERR_INDEX, PB_ERR_CUDA, PB_ERR_STATE, PB_ERR_NCCL = 0, -1, -2, -3, -4, -5
 

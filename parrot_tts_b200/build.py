@@ -1,9 +1,13 @@
 """Build libparrot_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m parrot_tts_b200.build [--force] [--verbose]
+    python -m parrot_tts_b200.build [--force] [--verbose] [--variant NAME --define MACRO ...]
 
 Objects go to parrot_tts_b200/build/ (git-ignored); the shared library to parrot_tts_b200/lib/.
 The library is rebuilt only when a source is newer than it.
+
+``--variant NAME --define MACRO`` builds an EXPERIMENT beside the product: objects in build/NAME/, library
+lib/libparrot_b200_NAME.so, loaded instead of the product only when ``PB_LIB_VARIANT=NAME`` is set (``_lib.py``) - so an
+A/B run needs no rebuild and the product library is never overwritten by an experiment.
 """
 import os
 import shutil
@@ -43,12 +47,21 @@ def _deps_mtime():
     return m
 
 
-def needs_build():
-    return not os.path.isfile(LIB) or os.path.getmtime(LIB) < _deps_mtime()
+def needs_build(lib=LIB):
+    return not os.path.isfile(lib) or os.path.getmtime(lib) < _deps_mtime()
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def variant_lib(variant):
+    return os.path.join(LIBDIR, f"libparrot_b200_{variant}.so") if variant else LIB
+
+
+def build(force=False, verbose=False, defines=(), variant=""):
+    if defines and not variant:
+        raise ValueError("a build with extra macros is an experiment: give it a --variant name (the product library keeps its flags)")
+    LIB = variant_lib(variant)
+    OBJ = os.path.join(HERE, "build", variant) if variant else os.path.join(HERE, "build")
+    NVCC_FLAGS = globals()["NVCC_FLAGS"] + [f"-D{d}" for d in defines]
+    if not force and not needs_build(LIB):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
@@ -80,4 +93,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    def _values(flag):
+        return [sys.argv[i + 1] for i, a in enumerate(sys.argv[:-1]) if a == flag]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=_values("--define"),
+                variant=(_values("--variant") or [""])[0]))

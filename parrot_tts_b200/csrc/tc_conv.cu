@@ -60,6 +60,11 @@ struct TcParams {
     int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
     int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads,
                   // 16 = skip the accumulator reads, 32 = skip the epilogue arithmetic
+#ifdef PB_TC_EPI_SPLIT
+    int epi_split;  // EXPERIMENTAL build (-DPB_TC_EPI_SPLIT; written in round 1 without GPU access, NOT yet run): every epilogue group works on
+                    // EVERY tile and takes the 16-column items grp, grp + n_groups, ... - a tile's epilogue latency drops from
+                    // (NT/16 items) to (NT/16 / n_groups) and n_groups is no longer capped by the number of accumulators
+#endif
 };
 
 }  // namespace
@@ -243,6 +248,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     const int cta0 = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int nctas = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int ROWS_PER_TILE = CL ? 2 * TC_M : TC_M;
+#ifdef PB_TC_EPI_SPLIT
+    const bool EPI_SPLIT = p.epi_split != 0;        // column-split epilogue groups (see TcParams::epi_split)
+#else
+    constexpr bool EPI_SPLIT = false;
+#endif
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
@@ -254,7 +264,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             mbar_init(&peer_a[s], 1); mbar_init(&peer_b[s], 1);
         }
         // accumulator release: 4 epilogue warps per CTA; the leader of a pair also collects the peer's 4
-        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CL ? 8 : 4); }
+        for (int s = 0; s < TC_MAX_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (CL ? 8 : 4) * (EPI_SPLIT ? p.n_groups : 1)); }
         mbar_init(b_res_full, 1);
         fence_mbar_init();
     }
@@ -373,7 +383,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         asm volatile("griddepcontrol.wait;" ::: "memory");   // residual / running-sum reads and the output stores depend on the previous kernel
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int grp = (warp - 4) >> 2;              // epilogue group: takes this CTA's tiles grp, grp + n_groups, ...
-        const int tile_stride = nctas * p.n_groups;
+        const int tile_stride = EPI_SPLIT ? nctas : nctas * p.n_groups;
+        const int n0_first = EPI_SPLIT ? 16 * grp : 0;            // (column split: items grp, grp + n_groups, ... of every tile)
+        const int n0_step = EPI_SPLIT ? 16 * p.n_groups : 16;
         const int row = q * 32 + lane;
         const int Lout = p.L * p.U;
         const size_t out_pitch = (size_t)2 * p.out_C;
@@ -439,26 +451,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             }
         };
 
-        int tile = cta0 + grp * nctas, n0 = 0;
-        uint32_t acc_i = (uint32_t)grp;                   // local tile counter: this group sees i = grp + k*n_groups
+        int tile = EPI_SPLIT ? cta0 : cta0 + grp * nctas, n0 = n0_first;
+        uint32_t acc_i = EPI_SPLIT ? 0u : (uint32_t)grp;  // local tile counter: this group sees i = grp + k*n_groups
         const uint32_t acc_mask = (uint32_t)p.n_acc - 1u, acc_shift = (uint32_t)__ffs(p.n_acc) - 1u;   // n_acc is a power of two
         TileCtx cur;
         locate_first(tile, cur);
         size_t off = 0; int co = 0; bool live = false;
-        if (cur.ok) item(cur, 0, off, co, live);
+        if (cur.ok) item(cur, n0_first, off, co, live);
         uint4 R[4], A[4];
         request(cur.ok && cur.row_ok, off, R, A);
         while (cur.ok) {
             // next item
             TileCtx nxt = cur;
-            int tile_n = tile, n0n = n0 + 16;
+            int tile_n = tile, n0n = n0 + n0_step;
             if (n0n >= p.NT) {
-                n0n = 0; tile_n += tile_stride; locate_next(tile_n, nxt);
+                n0n = n0_first; tile_n += tile_stride; locate_next(tile_n, nxt);
             }
             size_t offn = 0; int con = 0; bool liven = false;
             if (nxt.ok) item(nxt, n0n, offn, con, liven);
 
-            if ((RES || ACC) && n0 == 0 && p.U == 1) {
+            if ((RES || ACC) && n0 == n0_first && p.U == 1 && (!EPI_SPLIT || grp == 0)) {
                 // residual / running-sum rows of this group's NEXT tile: pull this N tile's columns into L2 now, a whole
                 // tile period ahead of their use (the loads then see L2 latency, not DRAM latency under load)
                 TileCtx pf = cur;
@@ -476,7 +488,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 }
             }
             const uint32_t as = acc_i & acc_mask;
-            if (n0 == 0) {
+            if (n0 == n0_first) {
                 mbar_wait(&acc_full[as], (acc_i >> acc_shift) & 1u);
                 tc_fence_after();
             }
@@ -495,7 +507,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 } else if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
                 else tmem_ld16(taddr, v);
             }
-            if (n0n == 0) {                            // accumulator fully read: hand it back before the arithmetic
+            if (n0n == n0_first) {                     // accumulator fully read: hand it back before the arithmetic
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {                              // one arrival per epilogue warp, at the MMA issuer's CTA
@@ -596,7 +608,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     bulk_commit_group();
                 }
             }
-            if (n0n == 0) acc_i += (uint32_t)p.n_groups;
+            if (n0n == n0_first) acc_i += EPI_SPLIT ? 1u : (uint32_t)p.n_groups;
             cur = nxt; tile = tile_n; n0 = n0n; off = offn; co = con; live = liven;
         }
     }
@@ -836,6 +848,14 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     // several warpgroups take alternate tiles so that those chains overlap.
     static const int env_groups = getenv("PB_TC_GROUPS") ? atoi(getenv("PB_TC_GROUPS")) : 0;
     p.n_groups = a.n_groups > 0 ? a.n_groups : (env_groups > 0 ? env_groups : (ctas_per_sm == 2 ? 1 : 3));
+#ifdef PB_TC_EPI_SPLIT
+    // EXPERIMENTAL (see TcParams::epi_split).  PB_TC_EPI_SPLIT: 0 = off, 1 = the CTA-pair layers (default of this build), 2 = every one-CTA-per-SM layer
+    static const int epi_split_env = getenv("PB_TC_EPI_SPLIT") ? atoi(getenv("PB_TC_EPI_SPLIT")) : 1;
+    p.epi_split = (ctas_per_sm == 1 && (epi_split_env >= 2 || (epi_split_env == 1 && p.cluster))) ? 1 : 0;
+    if (p.epi_split) {
+        if (p.n_groups > NT / 16) p.n_groups = NT / 16;       // every group needs an item in every tile
+    } else
+#endif
     if (p.n_groups > p.n_acc) p.n_groups = p.n_acc;
     if (p.n_groups > 3) p.n_groups = 3;
     const int threads = 128 + 128 * p.n_groups;

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round-2 experiment, written in round 1 without GPU access: column-split epilogue groups in tc_conv (TcParams::epi_split).
+# HERE, before gpurun (the .so travels):   python -m parrot_tts_b200.build --variant episplit --define PB_TC_EPI_SPLIT
+# ON THE BOX:                              bash tools/gpu_exp_episplit.sh
+# PB_TC_EPI_SPLIT: 0 = off (the variant build then behaves like the product), 1 = CTA-pair layers, 2 = every one-CTA-per-SM layer
+mkdir -p gpurun_out
+export PB_LIB_VARIANT=episplit
+for m in 1 2; do
+  PB_TC_EPI_SPLIT=$m timeout 900 python -m pytest tests/test_voc_gpu.py tests/test_tte_gpu.py -m gpu -x -q > gpurun_out/episplit_pytest_$m.log 2>&1
+  echo "mode $m pytest rc=$?"; tail -2 gpurun_out/episplit_pytest_$m.log
+done
+for m in 0 1 2; do
+  echo "== PB_TC_EPI_SPLIT=$m"
+  PB_TC_EPI_SPLIT=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1
+  PB_TC_EPI_SPLIT=$m timeout 300 python tools/dev_tte_time.py | tail -1
+done
+# per-launch view of the winner (compare with profiles/r01_model_vs_measured.txt):
+#   PB_TC_EPI_SPLIT=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+#       --log-file gpurun_out/launches_episplit.csv python tools/prof_voc.py 8 1024 1 0 && python tools/roofline_model.py gpurun_out/launches_episplit.csv
