@@ -759,13 +759,16 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     uint32_t b_res_bytes = 0, ring_bytes = 0;
     const uint32_t w_all = (uint32_t)round_up(p.w_total_bytes, 1024);
     // TMA-store epilogue (U == 1, split output): 2 KB of staging per epilogue warp, up to 3 groups of 4 warps.
-    // PB_TC_TMA_OUT: 0 = never, 1 = layers that run one CTA per SM without CTA pairs (default), 2 = every eligible layer (dev switch)
+    // PB_TC_TMA_OUT: 0 = never, 1 = layers that run one CTA per SM without CTA pairs (default), 2 = every eligible layer (dev switch),
+    // 3 = as 1 plus the CTA-pair layers with K <= 3 (not yet measured: those launches are epilogue-bound, profiles/r01_model_vs_measured.txt,
+    //     so the ring slot the staging tiles cost should matter less there than on the k = 7 / 11 layers mode 2 was measured on)
     static const int tma_out_mode = getenv("PB_TC_TMA_OUT") ? atoi(getenv("PB_TC_TMA_OUT")) : 1;
     // two CTAs per SM (two producers, two MMA issuers, one epilogue group each) measured best for the 16-channel layers;
     // wider layers run one CTA per SM with up to 3 epilogue groups (PB_TC_2CTA=0/1 forces either, dev switch)
     static const int force_2cta = getenv("PB_TC_2CTA") ? atoi(getenv("PB_TC_2CTA")) : -1;
     const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
-    p.tma_out = (a.out != nullptr && a.U == 1 && tma_out_mode > 0 && !want_2cta && (tma_out_mode > 1 || !p.cluster)) ? 1 : 0;
+    p.tma_out = (a.out != nullptr && a.U == 1 && tma_out_mode > 0 && !want_2cta &&
+                 (tma_out_mode == 2 || !p.cluster || (tma_out_mode == 3 && a.K <= 3))) ? 1 : 0;
     uint32_t stage_bytes = p.tma_out ? 3u * 4u * 2048u : 0u;
     auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off - stage_bytes; };   // barriers + bias + alignment slack
     if (p.tma_out && !p.cluster && budget(TC_SMEM_LIMIT) < w_all + 2u * (uint32_t)p.a_stage_bytes) {

@@ -14,6 +14,10 @@ for m in 0 1 2; do
   PB_TC_EPI_SPLIT=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1
   PB_TC_EPI_SPLIT=$m timeout 300 python tools/dev_tte_time.py | tail -1
 done
+# second prepared switch (product library, host-side only): TMA-store epilogue on the CTA-pair layers with k <= 3
+unset PB_LIB_VARIANT
+for m in 1 3; do echo "== PB_TC_TMA_OUT=$m"; PB_TC_TMA_OUT=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
+PB_TC_TMA_OUT=3 timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q 2>&1 | tail -1
 # per-launch view of the winner (compare with profiles/r01_model_vs_measured.txt):
 #   PB_TC_EPI_SPLIT=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
 #       --log-file gpurun_out/launches_episplit.csv python tools/prof_voc.py 8 1024 1 0 && python tools/roofline_model.py gpurun_out/launches_episplit.csv
