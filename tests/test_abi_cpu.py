@@ -89,3 +89,35 @@ def test_state_dict_layouts_match_reference_names():
     assert tuple(sd["conv_post.weight_v"].shape) == (1, 16, 7)
     assert tuple(sd["dict.weight"].shape) == (1000, 128) and tuple(sd["spkr.weight"].shape) == (10, 128)
     assert set(sd) == set(synth.synth_vocoder_state_dict(h, seed=0))
+
+
+def test_checkpoint_files_load_like_the_reference(tmp_path):
+    """The two checkpoint files of the demo: a Lightning .ckpt dict (extra trainer keys ignored, `parrot.`
+    prefix) through LitParrot.load_from_checkpoint(path, weights_only=True), and torch.load(path)['generator'] for the vocoder."""
+    import json
+    import torch
+    from parrot_tts_b200.tte import LitParrot
+    from parrot_tts_b200.vocoder import CodeGenerator, load_checkpoint
+    with open(tmp_path / "speakers.json", "w") as f:
+        json.dump({f"s{i}": i for i in range(3)}, f)
+    cfg = configs.default_tte_config(root_path=str(tmp_path))
+    sd = synth.synth_tte_state_dict(cfg, 40, 0, 3, seed=2)
+    ckpt = {"epoch": 7, "global_step": 1234, "pytorch-lightning_version": "2.4.0", "optimizer_states": [{"state": {}}], "lr_schedulers": [],
+            "hyper_parameters": {"data_config": cfg, "src_vocab_size": 40, "src_pad_idx": 0},
+            "state_dict": {"parrot." + k: v for k, v in sd.items()}}
+    torch.save(ckpt, tmp_path / "tte.ckpt")
+    model = LitParrot.load_from_checkpoint(str(tmp_path / "tte.ckpt"), weights_only=True)
+    assert not model.training and model.parrot.src_vocab_size == 40
+    got = model.parrot.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    with pytest.raises(Exception):                       # no silent CPU execution of the loaded model
+        model.infer({"phones": torch.ones(1, 4, dtype=torch.long), "src_mask": torch.ones(1, 4, dtype=torch.bool),
+                     "speaker": torch.zeros(1, dtype=torch.long)})
+
+    h = configs.default_vocoder_config()
+    sd_v = synth.synth_vocoder_state_dict(h, seed=2)
+    torch.save({"generator": sd_v}, tmp_path / "g_00000001")
+    gen = CodeGenerator(h)
+    gen.load_state_dict(load_checkpoint(str(tmp_path / "g_00000001"))["generator"])
+    got = gen.state_dict()
+    assert all(torch.equal(got[k], sd_v[k]) for k in sd_v)

@@ -117,3 +117,36 @@ def test_generator_oracle_vs_reference_feature_input():
     y = torch.tensor([[0.5, -0.25, 0.99999, -1.0, 1.0, 3.0517578125e-05 * 1.5]])
     want = (y.squeeze() * 32768.0).cpu().numpy().astype("int16")
     assert np.array_equal(voc_oracle.to_int16(y), want)
+
+
+def test_checkpoint_layouts_are_interchangeable_with_the_reference():
+    """Drop-in boundary: the mirror classes' state_dict() has exactly the reference modules' keys and
+    shapes, each loads the other's with strict=True - with weight norm attached and after remove_weight_norm()."""
+    from parrot_tts_b200.tte import Parrot
+    from parrot_tts_b200.vocoder import CodeGenerator
+    import json, os, tempfile
+    d = tempfile.mkdtemp(prefix="parrot_ckpt_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({f"s{i}": i for i in range(10)}, f)
+    cfg = configs.default_tte_config(root_path=d)
+    ours_t, ref_t = Parrot(cfg, 150, 0), ref_shim.load_reference_parrot(cfg, 150, 0, 10)
+    a, b = ours_t.state_dict(), ref_t.state_dict()
+    assert {k: tuple(v.shape) for k, v in a.items()} == {k: tuple(v.shape) for k, v in b.items()}
+    ours_t.load_state_dict(b, strict=True)
+    ref_t.load_state_dict(a, strict=True)
+
+    h = configs.default_vocoder_config()
+    ours_v, ref_v = CodeGenerator(h), ref_shim.load_reference_vocoder(h)
+    a, b = ours_v.state_dict(), ref_v.state_dict()
+    assert {k: tuple(v.shape) for k, v in a.items()} == {k: tuple(v.shape) for k, v in b.items()}
+    assert "conv_pre.weight_g" in a and "conv_pre.weight_v" in a
+    ours_v.load_state_dict(b, strict=True)
+    ref_v.load_state_dict(a, strict=True)
+    ours_v.remove_weight_norm()
+    ref_v.remove_weight_norm()
+    a, b = ours_v.state_dict(), ref_v.state_dict()
+    assert {k: tuple(v.shape) for k, v in a.items()} == {k: tuple(v.shape) for k, v in b.items()}
+    assert "conv_pre.weight" in a and "conv_pre.weight_g" not in a
+    ours_v.load_state_dict(b, strict=True)
+    for k in b:                                      # and the folded weights really are the reference's g * v / ||v||
+        assert torch.equal(ours_v.state_dict()[k], b[k])
