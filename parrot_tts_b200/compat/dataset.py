@@ -1,0 +1,2 @@
+"""script-mode ``from dataset import MAX_WAV_VALUE`` (reference utils/vocoder/inference.py:24-25); the dataset classes are training-side"""
+from parrot_tts_b200.vocoder import MAX_WAV_VALUE  # noqa: F401

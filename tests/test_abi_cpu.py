@@ -121,3 +121,35 @@ def test_checkpoint_files_load_like_the_reference(tmp_path):
     gen.load_state_dict(load_checkpoint(str(tmp_path / "g_00000001"))["generator"])
     got = gen.state_dict()
     assert all(torch.equal(got[k], sd_v[k]) for k in sd_v)
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    """demo.ipynb cell 0 / utils/vocoder/inference.py:24-27 import lines, unchanged, after compat.install() (fresh interpreter)."""
+    import subprocess
+    import sys
+    code = """
+import parrot_tts_b200.compat as compat
+compat.install(); compat.install()
+from modules.data import DFATokenizer, get_mask_from_batch
+from utils.aligner.cleaners import english_cleaners, nonenglish_cleaners, nonenglish_cleaners_no_transliteration
+from inference import LitParrot
+from utils.vocoder.utils import AttrDict
+from utils.vocoder.models import CodeGenerator
+from utils.vocoder.dataset import MAX_WAV_VALUE
+from modules.parrot import Parrot
+from modules.fft import FFTBlock, SinusoidalPosEmb
+from modules.duration import DurationPredictor, length_regulator
+from modules import Parrot as P2
+from utils import init_weights, get_padding, AttrDict as A2      # script mode of utils/vocoder/models.py:8
+from models import CodeGenerator as C2                            # script mode of utils/vocoder/inference.py:27
+from dataset import MAX_WAV_VALUE as M2
+from utils.vocoder.inference import generate
+import parrot_tts_b200.tte, parrot_tts_b200.vocoder, parrot_tts_b200.text
+assert CodeGenerator is C2 is parrot_tts_b200.vocoder.CodeGenerator and LitParrot is parrot_tts_b200.tte.LitParrot
+assert Parrot is P2 is parrot_tts_b200.tte.Parrot and AttrDict is A2 and MAX_WAV_VALUE == M2 == 32768.0
+assert english_cleaners is parrot_tts_b200.text.english_cleaners and english_cleaners('Dr. No 2') == 'doctor no two'
+assert get_padding(7, 3) == 9 and AttrDict(a=1).a == 1
+print('ok')
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
