@@ -153,3 +153,38 @@ print('ok')
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, lib_path):
+    """The boundary is a C ABI: include/parrot_b200.h compiles as C99 (pedantic), and a C program linked against the library gets
+    the version, a thread-local error message and error codes - no GPU, no Python, no C++ in between."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "parrot_b200.h"
+int main(void) {
+    pb_voc* v = NULL;
+    pb_voc_cfg cfg;
+    memset(&cfg, 0, sizeof cfg);
+    if (pb_version() != PB_ABI_VERSION) return 1;
+    if (pb_voc_forward(NULL, NULL, NULL, NULL, NULL, 1, 1, NULL, NULL) >= 0) return 2;      /* null handle */
+    if (strlen(pb_last_error()) == 0) return 3;
+    if (pb_voc_create(&cfg, &v) >= 0) return 4;                                              /* an all-zero config is rejected */
+    if (pb_wav_to_pcm16(NULL, 4, NULL, NULL) >= 0) return 5;
+    printf("%d %s\n", pb_version(), pb_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(lib_path)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lparrot_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("2 ")
