@@ -1,7 +1,7 @@
-"""CPU experiment (no GPU needed): what would cheaper operand formats cost in waveform error?
+"""ORACLE-side experiment (test infrastructure, not product code; CPU only): what would cheaper operand formats cost in waveform error?
 
 The vocoder convolutions run today as 3 tensor passes per product (split bf16: x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, ~2^-16 per product).
-This script replays the ORACLE graph (test infrastructure; this is a dev tool, not product code) with the operands of every
+This script replays the oracle graph with the operands of every
 convolution rounded the way a cheaper tcgen05 scheme would see them, and reports max |wav - wav_fp32| against the 1e-3 abs bar:
 
   tf32_trunc   kind::tf32, activations fed as raw fp32 (the MMA ignores the low 13 mantissa bits), weights rounded to tf32 (RNE)
@@ -10,7 +10,7 @@ convolution rounded the way a cheaper tcgen05 scheme would see them, and reports
   x16_w16      today's 3-pass split bf16 (x and w to 16 mantissa bits, the lo.lo term dropped)
   bf16         1 pass plain bf16
 
-    python tools/dev_precision_emul.py [--units 48] [--batch 2] [--gain 1.0 6.0]
+    python oracle/precision_emulation.py [--units 48] [--batch 2] [--gain 1.0 6.0]
 """
 import argparse
 import os
