@@ -6,11 +6,12 @@ states the two floors of every launch of one `CodeGenerator` forward and puts th
   hbm floor     bytes the launch has to move as implemented (split 16-bit activations = 4 B per element: conv1 reads x and writes xt;
                 conv2 reads xt and the residual and writes; the ResBlock-closing conv2 also reads / writes the running sum; a fused pair
                 reads x (with its halo) and writes once; weights once) / the copy roofline
-  tensor floor  tcgen05 cycles of the launch from the measured cost of one MMA (profiles/r01_mma_probe.txt: M = 128, K = 16 costs
+  pipe floor    tcgen05 cycles of the launch from the measured cost of one MMA (profiles/r01_mma_probe.txt: M = 128, K = 16 costs
                 max(N/2, 32 + N/4) cycles), two MMAs per k-step (x_hi against the stacked [w_hi; w_lo], x_lo against w_hi), spread over
                 148 SMs at the SM clock
 
     python tools/roofline_model.py profiles/r01_launches_voc_cfg2.csv [--B 8 --T 1024] [--hbm 6650] [--mhz 1965]
+    python tools/roofline_model.py profiles/r01_launches_tte_cfg3.csv --tte [--B 32 --S 256 --T 2048]
 
 The launch order is the library's (voc_api.cu: embed, conv_pre, then per stage ups[i] and the ResBlocks k = 3, 7, 11, each (conv1, conv2) x 3
 dilations - one fused launch per pair at C <= 32 - and conv_post).
@@ -69,6 +70,49 @@ def expected(B, T):
     return out
 
 
+def expected_tte(B, S, T, d=256, ff=1024, k1=9, heads=2, n_layers=4, n_codes=1000):
+    """TTE forward (cfg3 by default) in launch order (tte_api.cu): embed, 4 encoder FFT blocks, speaker row, duration predictor,
+    length regulator, 4 decoder FFT blocks, head, argmax.  GEMM inputs are split-fp16 rows (4 B per element), the residual
+    stream is fp32; attention: Q.K^T is evaluated in both softmax passes, every product three times (split operands)."""
+    F32 = 4
+    out = [dict(name="embed + pe row", bytes=B * S * (8 + d * F32), cycles=0)]
+
+    def gemm(name, M, K, taps, N, res):
+        n_pad = -(-N // 128) * 128
+        cyc = -(-M // 128) * (n_pad // 128) * taps * (K // 16) * kstep_cycles(128)
+        byt = M * K * EL + M * N * F32 * (2 if res else 1) + K * taps * n_pad * 6
+        return dict(name=name, bytes=byt, cycles=cyc)
+
+    def block(tag, M, L):
+        rows = []
+        rows.append(dict(name=f"{tag} layernorm+split", bytes=M * d * (F32 + EL), cycles=0))
+        rows.append(gemm(f"{tag} qkv {d}->{3 * d}", M, d, 1, 3 * d, False))
+        att_flop = 9.0 * 2 * L * L * (d // heads) * heads * (M // L)              # (2 passes x 3 + 3) products
+        rows.append(dict(name=f"{tag} attention L={L}", bytes=M * 3 * d * EL + M * d * EL, cycles=att_flop / 8192.0))
+        rows.append(gemm(f"{tag} out-proj + res", M, d, 1, d, True))
+        rows.append(dict(name=f"{tag} layernorm+split", bytes=M * d * (F32 + EL), cycles=0))
+        rows.append(gemm(f"{tag} ffn k{k1} {d}->{ff} relu", M, d, k1, ff, False))
+        rows.append(gemm(f"{tag} ffn k1 {ff}->{d} + res", M, ff, 1, d, True))
+        return rows
+
+    for i in range(n_layers):
+        out += block(f"enc{i}", B * S, S)
+    M = B * S
+    out.append(dict(name="speaker row add", bytes=2 * M * d * F32, cycles=0))
+    fp32_fma_per_clk = 128.0                                                     # per SM
+    dp = dict(name="duration conv k3 (fp32 SIMT)", bytes=2 * M * d * F32, cycles=M * d * d * 3 / fp32_fma_per_clk * 1.0)
+    out += [dp, dict(name="duration layernorm", bytes=2 * M * d * F32, cycles=0), dict(dp),
+            dict(name="duration LN + head + round", bytes=M * d * F32, cycles=0), dict(name="duration scan", bytes=M * 16, cycles=0)]
+    Md = B * T
+    out.append(dict(name="length regulator + pe row", bytes=Md * d * F32 + M * d * F32, cycles=0))
+    for i in range(n_layers):
+        out += block(f"dec{i}", Md, T)
+    out.append(dict(name="rows -> split", bytes=Md * d * (F32 + EL), cycles=0))
+    out.append(gemm(f"head {d}->{n_codes}", Md, d, 1, n_codes, False))
+    out.append(dict(name="argmax", bytes=Md * n_codes * F32 + Md * 8, cycles=0))
+    return out
+
+
 def read_launches(path, first="voc_embed"):
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
     h = rows[0]
@@ -89,11 +133,18 @@ def main():
     ap.add_argument("--T", type=int, default=1024)
     ap.add_argument("--hbm", type=float, default=6650.0, help="GB/s")
     ap.add_argument("--mhz", type=float, default=1965.0)
+    ap.add_argument("--tte", action="store_true", help="TTE forward (defaults B=32 S=256 T=2048) instead of the vocoder")
+    ap.add_argument("--S", type=int, default=256)
     a = ap.parse_args()
-    exp = expected(a.B, a.T)
-    got = [d for d in read_launches(a.launches) if not d["name"].startswith("void at::") and "at::" not in d["name"]]
+    if a.tte:
+        B = 32 if a.B == 8 else a.B
+        T = 2048 if a.T == 1024 else a.T
+        exp = expected_tte(B, a.S, T)
+    else:
+        exp = expected(a.B, a.T)
+    got = [d for d in read_launches(a.launches, "embed_pos" if a.tte else "voc_embed") if "at::" not in d["name"]]
     assert len(got) >= len(exp), (len(got), len(exp))
-    print(f"{'launch':34s} {'meas us':>8s} {'hbm us':>7s} {'tens us':>8s} {'bound':>6s} {'floor/meas':>10s} {'dram MB':>8s} {'model MB':>8s}")
+    print(f"{'launch':34s} {'meas us':>8s} {'hbm us':>7s} {'pipe us':>8s} {'bound':>6s} {'floor/meas':>10s} {'dram MB':>8s} {'model MB':>8s}")
     stage = collections.OrderedDict()
     for e, g in zip(exp, got):
         us = g["gpu__time_duration.sum"] / 1e3
@@ -101,15 +152,20 @@ def main():
         t_t = e["cycles"] / SMS / a.mhz
         floor = max(t_h, t_t)
         dram = (g.get("dram__bytes_read.sum", 0) + g.get("dram__bytes_write.sum", 0)) / 1e6
-        print(f"{e['name']:34s} {us:8.1f} {t_h:7.1f} {t_t:8.1f} {'hbm' if t_h >= t_t else 'tensor':>6s} {floor / us:10.2f} {dram:8.1f} {e['bytes'] / 1e6:8.1f}")
+        print(f"{e['name']:34s} {us:8.1f} {t_h:7.1f} {t_t:8.1f} {'hbm' if t_h >= t_t else 'pipe':>6s} {floor / us:10.2f} {dram:8.1f} {e['bytes'] / 1e6:8.1f}")
         key = e["name"].split()[0]
-        key = key if key[0] == "s" and key[1:].isdigit() else "other"
+        if a.tte:
+            key = key[:3] if key[:3] in ("enc", "dec") else "other"
+            if key != "other":
+                key += " attention" if "attention" in e["name"] else (" gemm" if ("->" in e["name"] or "proj" in e["name"]) else " layernorm")
+        else:
+            key = key if key[0] == "s" and key[1:].isdigit() else "other"
         s = stage.setdefault(key, [0.0, 0.0, 0.0, 0.0])
         s[0] += us; s[1] += t_h; s[2] += t_t; s[3] += floor
     print()
-    print(f"{'section':10s} {'meas us':>9s} {'hbm us':>9s} {'tens us':>9s} {'floor us':>9s} {'floor/meas':>10s}")
+    print(f"{'section':14s} {'meas us':>9s} {'hbm us':>9s} {'pipe us':>9s} {'floor us':>9s} {'floor/meas':>10s}")
     for k, s in list(stage.items()) + [("total", [sum(v[i] for v in stage.values()) for i in range(4)])]:
-        print(f"{k:10s} {s[0]:9.1f} {s[1]:9.1f} {s[2]:9.1f} {s[3]:9.1f} {s[3] / s[0]:10.2f}")
+        print(f"{k:14s} {s[0]:9.1f} {s[1]:9.1f} {s[2]:9.1f} {s[3]:9.1f} {s[3] / s[0]:10.2f}")
 
 
 if __name__ == "__main__":
