@@ -39,6 +39,11 @@ struct pb_voc {
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     bool ev_valid = false;
+    // PB_VOC_CHAINS=1 (experimental, off by default): the num_kernels ResBlock chains of a stage are independent until their
+    // outputs are summed, so each runs on its own stream and one chain's launch tails overlap the next chain's kernels
+    cudaStream_t chain_st[PB_VOC_MAX_RESK] = {};
+    cudaEvent_t ev_fork = nullptr, ev_last[PB_VOC_MAX_RESK] = {};
+    bool chains_ready = false;
     float* A(size_t off) const { return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(arena.ptr) + off); }
 };
 
@@ -120,6 +125,13 @@ extern "C" void pb_voc_destroy(pb_voc* h) {
     if (!h) return;
     for (auto& kv : h->staged) if (kv.second.ptr) cudaFree(kv.second.ptr);
     for (auto e : h->ev) cudaEventDestroy(e);
+    if (h->chains_ready) {
+        cudaEventDestroy(h->ev_fork);
+        for (int j = 0; j < PB_VOC_MAX_RESK; ++j) {
+            if (h->ev_last[j]) cudaEventDestroy(h->ev_last[j]);
+            if (h->chain_st[j]) cudaStreamDestroy(h->chain_st[j]);
+        }
+    }
     h->arena.release();
     h->work.release();
     delete h;
@@ -273,16 +285,31 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
             slot_elems = std::max(slot_elems, (size_t)B * (size_t)L * 2 * (c0 >> (i + 1)));
         }
     }
+    // PB_VOC_CHAINS=1: chain j (ResBlock kernel size j) of every stage runs on its own stream with its own XT / XA / XB buffers
+    // (the last chain stays on the caller's stream); the running sum keeps its order k3 -> k7 -> k11, so results are bit-identical.
+    // Written in round 1 after the GPU budget was spent: NOT yet run on a GPU, hence off unless asked for.
+    static const bool chains_env = getenv("PB_VOC_CHAINS") != nullptr && atoi(getenv("PB_VOC_CHAINS")) != 0;
+    const bool chains = chains_env && c.num_kernels > 1 && c.num_kernels <= PB_VOC_MAX_RESK;
+    constexpr int MAX_SLOTS = 4 + 3 * PB_VOC_MAX_RESK;
+    const int n_slots = chains ? 4 + 3 * c.num_kernels : 7;        // X, XS, Y + the previous stage's Y, and (XT, XA, XB) per chain
+    if (chains && !h->chains_ready) {
+        PB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        for (int j = 0; j + 1 < c.num_kernels; ++j) {
+            PB_CUDA(cudaStreamCreateWithFlags(&h->chain_st[j], cudaStreamNonBlocking));
+            PB_CUDA(cudaEventCreateWithFlags(&h->ev_last[j], cudaEventDisableTiming));
+        }
+        h->chains_ready = true;
+    }
     Carver plan(nullptr);
     plan.take<bf>((size_t)B * T * 2 * c.model_in_dim);
     plan.take<bf>((size_t)B * T * 2 * c0);
-    for (int s = 0; s < 7; ++s) plan.take<bf>(slot_elems);
+    for (int s = 0; s < n_slots; ++s) plan.take<bf>(slot_elems);
     PB_TRY(h->work.reserve(plan.off));
     Carver cv(h->work.ptr);
     bf* x0 = cv.take<bf>((size_t)B * T * 2 * c.model_in_dim);
     bf* h0 = cv.take<bf>((size_t)B * T * 2 * c0);
-    bf* slot[7];
-    for (int s = 0; s < 7; ++s) slot[s] = cv.take<bf>(slot_elems);
+    bf* slot[MAX_SLOTS];
+    for (int s = 0; s < n_slots; ++s) slot[s] = cv.take<bf>(slot_elems);
 
     int ev_i = 0;
     h->ev_valid = false;
@@ -312,11 +339,11 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
         const int u = c.upsample_rates[i];
         const int64_t Lo = L * u;
         mul *= u;
-        bf* buf[6];
-        for (int s = 0, n = 0; s < 7 && n < 6; ++s) if (s != in_slot) buf[n++] = slot[s];
-        bf *X = buf[0], *XT = buf[1], *XA = buf[2], *XB = buf[3], *XS = buf[4], *Y = buf[5];
+        bf* buf[MAX_SLOTS];
+        for (int s = 0, n = 0; s < n_slots && n < n_slots - 1; ++s) if (s != in_slot) buf[n++] = slot[s];
+        bf *X = buf[0], *XS = buf[4], *Y = buf[5];
         int y_slot = 0;
-        for (int s = 0; s < 7; ++s) if (slot[s] == Y) y_slot = s;
+        for (int s = 0; s < n_slots; ++s) if (slot[s] == Y) y_slot = s;
         {   // ups[i] as a 3-tap polyphase implicit GEMM; X is stored leaky-relu'd (the resblocks' first activation)
             const ConvSlot& s = h->ups[i];
             TcConvArgs a;
@@ -326,8 +353,18 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
             PB_TRY(launch_tc_conv(a, st));
         }
         PB_MARK();
+        if (chains) {       // fork: the side chains start once ups[i] (X) is complete
+            PB_CUDA(cudaEventRecord(h->ev_fork, st));
+            for (int j = 0; j + 1 < c.num_kernels; ++j) PB_CUDA(cudaStreamWaitEvent(h->chain_st[j], h->ev_fork, 0));
+        }
         for (int j = 0; j < c.num_kernels; ++j) {
             const bf* cur = X;
+            bf *XT = buf[1], *XA = buf[2], *XB = buf[3];
+            cudaStream_t sj = st;
+            if (chains) {
+                if (j > 0) { XT = buf[6 + 3 * (j - 1)]; XA = buf[7 + 3 * (j - 1)]; XB = buf[8 + 3 * (j - 1)]; }
+                if (j + 1 < c.num_kernels) sj = h->chain_st[j];      // the last chain (it writes Y) stays on the caller's stream
+            }
             for (int m = 0; m < c.num_dilations; ++m) {
                 const int idx = (i * c.num_kernels + j) * c.num_dilations + m;
                 const ConvSlot& s1 = h->rb1[idx];
@@ -341,7 +378,7 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                     if (m + 1 < c.num_dilations) {
                         bf* dst = (cur == XA) ? XB : XA;
                         f.out = dst; f.post_slope = 0.1f;
-                        PB_TRY(launch_tc_pair(f, st));
+                        PB_TRY(launch_tc_pair(f, sj));
                         cur = dst;
                     } else {
                         if (j > 0) f.accin = XS;
@@ -352,7 +389,10 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                             f.scale = 1.0f / (float)c.num_kernels;
                             f.post_slope = (i + 1 < c.num_upsamples) ? 0.1f : 0.01f;
                         }
-                        PB_TRY(launch_tc_pair(f, st));
+                        // the chain-closing kernel adds into the running sum the previous chain has written: order k3 -> k7 -> k11 kept
+                        if (chains && j > 0) PB_CUDA(cudaStreamWaitEvent(sj, h->ev_last[j - 1], 0));
+                        PB_TRY(launch_tc_pair(f, sj));
+                        if (chains && j + 1 < c.num_kernels) PB_CUDA(cudaEventRecord(h->ev_last[j], sj));
                     }
                     continue;
                 }
@@ -360,7 +400,7 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                 a.x = cur; a.w = W(s1); a.bias = h->A(s1.b_off); a.out = XT; a.lens = lens; a.len_mul = mul;
                 a.B = B; a.L = (int)Lo; a.Cin = C; a.N = C; a.out_C = C; a.U = 1; a.K = s1.K; a.D = s1.D;
                 a.post_slope = 0.1f; a.single_pass = single;
-                PB_TRY(launch_tc_conv(a, st));
+                PB_TRY(launch_tc_conv(a, sj));
                 TcConvArgs b2;
                 b2.x = XT; b2.w = W(s2); b2.bias = h->A(s2.b_off); b2.res = cur; b2.res_unslope = 10.f;
                 b2.lens = lens; b2.len_mul = mul; b2.B = B; b2.L = (int)Lo; b2.Cin = C; b2.N = C; b2.out_C = C; b2.U = 1;
@@ -368,7 +408,7 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                 if (m + 1 < c.num_dilations) {
                     bf* dst = (cur == XA) ? XB : XA;
                     b2.out = dst; b2.post_slope = 0.1f;
-                    PB_TRY(launch_tc_conv(b2, st));
+                    PB_TRY(launch_tc_conv(b2, sj));
                     cur = dst;
                 } else {
                     if (j > 0) b2.accin = XS;
@@ -379,7 +419,9 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                         b2.scale = 1.0f / (float)c.num_kernels;
                         b2.post_slope = (i + 1 < c.num_upsamples) ? 0.1f : 0.01f;
                     }
-                    PB_TRY(launch_tc_conv(b2, st));
+                    if (chains && j > 0) PB_CUDA(cudaStreamWaitEvent(sj, h->ev_last[j - 1], 0));      // (as above)
+                    PB_TRY(launch_tc_conv(b2, sj));
+                    if (chains && j + 1 < c.num_kernels) PB_CUDA(cudaEventRecord(h->ev_last[j], sj));
                 }
             }
         }

@@ -1,7 +1,10 @@
 #!/bin/bash
-# Round-2 experiment, written in round 1 without GPU access: column-split epilogue groups in tc_conv (TcParams::epi_split).
+# Round-2 experiments, written in round 1 after the GPU budget was spent (none has run on a GPU yet):
+#  (1) column-split epilogue groups in tc_conv (TcParams::epi_split; variant build)
+#  (2) PB_TC_TMA_OUT=3: TMA-store epilogue on the CTA-pair layers with k <= 3 (product library, host-side switch)
+#  (3) PB_VOC_CHAINS=1: the three ResBlock chains of a stage on three streams (product library, host-side switch)
 # HERE, before gpurun (the .so travels):   python -m parrot_tts_b200.build --variant episplit --define PB_TC_EPI_SPLIT
-# ON THE BOX:                              bash tools/gpu_exp_episplit.sh
+# ON THE BOX:                              bash tools/gpu_exp_r2.sh
 # PB_TC_EPI_SPLIT: 0 = off (the variant build then behaves like the product), 1 = CTA-pair layers, 2 = every one-CTA-per-SM layer
 mkdir -p gpurun_out
 export PB_LIB_VARIANT=episplit
@@ -18,6 +21,10 @@ done
 unset PB_LIB_VARIANT
 for m in 1 3; do echo "== PB_TC_TMA_OUT=$m"; PB_TC_TMA_OUT=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
 PB_TC_TMA_OUT=3 timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q 2>&1 | tail -1
+# (3) chain streams: parity (bit-identical by construction: the running sum keeps its order), CUDA-graph capture, timing
+for m in 0 1; do echo "== PB_VOC_CHAINS=$m"; PB_VOC_CHAINS=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
+PB_VOC_CHAINS=1 timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q 2>&1 | tail -1
+PB_VOC_CHAINS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-text2wav > gpurun_out/bench_chains.json 2> gpurun_out/bench_chains.err; echo "bench rc=$?"
 # per-launch view of the winner (compare with profiles/r01_model_vs_measured.txt):
 #   PB_TC_EPI_SPLIT=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
 #       --log-file gpurun_out/launches_episplit.csv python tools/prof_voc.py 8 1024 1 0 && python tools/roofline_model.py gpurun_out/launches_episplit.csv
