@@ -698,8 +698,13 @@ __global__ void __launch_bounds__(256)
 conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ wav, const int32_t* __restrict__ lens, int len_mul, int L) {
     constexpr int ROWS = POST_T + K - 1;
+#ifdef PB_POST_TILE4
+    constexpr int PITCH = (ROWS + 3 + 3) / 4 * 4;     // rows o .. o + 9 of a 4-sample tile stay inside the pitch; multiple of 4 floats
+    __shared__ __align__(16) float xs[CIN * PITCH];
+#else
     constexpr int PITCH = ROWS + 1;
     __shared__ float xs[CIN * PITCH];
+#endif
     __shared__ float ws[CIN * K];
     for (int i = threadIdx.x; i < CIN * K; i += blockDim.x) ws[i] = w[i];
     const int b = blockIdx.y;
@@ -727,6 +732,35 @@ conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
     }
     __syncthreads();
     const float bv = bias[0];
+#ifdef PB_POST_TILE4
+    // EXPERIMENTAL build (-DPB_POST_TILE4; written in round 1 without GPU access, NOT yet run): the loop below issues 2 shared-memory
+    // loads per FMA (91 us per 8 x 1024 units against a 27 us HBM floor, profiles/r01_model_vs_measured.txt).  Here a thread owns 4
+    // consecutive samples: 10 inputs (two 128-bit loads and a 64-bit one) and the 7 weights of a channel serve 28 FMAs.  The order of
+    // the FMAs of one sample is unchanged (channel outer, tap inner), so the waveform is bit-identical.
+    static_assert(POST_T % 4 == 0 && PITCH % 4 == 0 && K <= 7, "4-sample tiles read xs[o .. o + 9] with aligned vector loads");
+    for (int o = 4 * threadIdx.x; o < POST_T; o += 4 * blockDim.x) {
+        if (t0 + o >= L) break;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float* xr = xs + c * PITCH + o;
+            const float4 a = *reinterpret_cast<const float4*>(xr), bq = *reinterpret_cast<const float4*>(xr + 4);
+            const float2 cq = *reinterpret_cast<const float2*>(xr + 8);
+            const float in[10] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, cq.x, cq.y};
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float wj = ws[c * K + j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = fmaf(wj, in[q + j], acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = t0 + o + q;
+            if (t < L) wav[(size_t)b * L + t] = t < valid ? tanhf(acc[q] + bv) : 0.f;
+        }
+    }
+#else
     for (int o = threadIdx.x; o < POST_T; o += blockDim.x) {
         const int t = t0 + o;
         if (t >= L) break;
@@ -740,13 +774,19 @@ conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
         }
         wav[(size_t)b * L + t] = acc;
     }
+#endif
 }
 
 int launch_conv_post_split(const __nv_bfloat16* x, const float* w, const float* bias, float* wav, const int32_t* lens, int len_mul,
                            int B, int Cin, int L, int K, cudaStream_t st) {
     PB_REQUIRE(K == 7, PB_ERR_INVALID, "conv_post: kernel size %d unsupported (7 expected)", K);
     dim3 grid((unsigned)ceil_div(L, POST_T), (unsigned)B);
-    if (Cin == 16) conv_post_split_kernel<16, 7><<<grid, 256, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
+#ifdef PB_POST_TILE4
+    constexpr int POST_THREADS = POST_T / 4;      // one 4-sample tile per thread
+#else
+    constexpr int POST_THREADS = 256;
+#endif
+    if (Cin == 16) conv_post_split_kernel<16, 7><<<grid, POST_THREADS, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
     else { set_error("conv_post: Cin=%d unsupported on the tensor-core path (16 expected)", Cin); return PB_ERR_INVALID; }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());

@@ -1,9 +1,9 @@
 #!/bin/bash
 # Round-2 experiments, written in round 1 after the GPU budget was spent (none has run on a GPU yet):
-#  (1) column-split epilogue groups in tc_conv (TcParams::epi_split; variant build)
+#  (1) column-split epilogue groups in tc_conv (TcParams::epi_split; variant build) + 4-sample register tiles in conv_post (PB_POST_TILE4, same variant)
 #  (2) PB_TC_TMA_OUT=3: TMA-store epilogue on the CTA-pair layers with k <= 3 (product library, host-side switch)
 #  (3) PB_VOC_CHAINS=1: the three ResBlock chains of a stage on three streams (product library, host-side switch)
-# HERE, before gpurun (the .so travels):   python -m parrot_tts_b200.build --variant episplit --define PB_TC_EPI_SPLIT
+# HERE, before gpurun (the .so travels):   python -m parrot_tts_b200.build --variant episplit --define PB_TC_EPI_SPLIT --define PB_POST_TILE4
 # ON THE BOX:                              bash tools/gpu_exp_r2.sh
 # PB_TC_EPI_SPLIT: 0 = off (the variant build then behaves like the product), 1 = CTA-pair layers, 2 = every one-CTA-per-SM layer
 mkdir -p gpurun_out
