@@ -7,6 +7,8 @@
 # ON THE BOX:                              bash tools/gpu_exp_r2.sh
 # PB_TC_EPI_SPLIT: 0 = off (the variant build then behaves like the product), 1 = CTA-pair layers, 2 = every one-CTA-per-SM layer
 mkdir -p gpurun_out
+# bitwise parity of every prepared switch against the default path (fresh interpreter per case)
+PB_TEST_EXPERIMENTS=1 timeout 1800 python -m pytest tests/test_experiments_gpu.py -m gpu -q 2>&1 | tail -3
 export PB_LIB_VARIANT=episplit
 for m in 1 2; do
   PB_TC_EPI_SPLIT=$m timeout 900 python -m pytest tests/test_voc_gpu.py tests/test_tte_gpu.py -m gpu -x -q > gpurun_out/episplit_pytest_$m.log 2>&1
