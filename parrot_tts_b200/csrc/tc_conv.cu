@@ -21,6 +21,28 @@
 #include "pb_tc.cuh"
 #include "pb_umma.cuh"
 
+// EXPERIMENTAL build switch -DPB_TC_FAMILY (written in round 1 without GPU access, NOT yet run): a fourth template parameter VOC
+// instantiates the kernel for the vocoder's layer family - split-bf16 in and out, no tanh, no fp32 residual / output, no ablation -
+// so the per-item flag tests of the epilogue (a uniform branch per element pair in split2 / join2, the tanh / fp32 blocks) fold
+// away.  Without the switch the macros below expand to the plain parameter reads: the product's device code does not change.
+#ifdef PB_TC_FAMILY
+#define TC_KERNEL_TEMPLATE template <bool RES, bool ACC, bool CL, bool VOC>
+#define EP_FMT (VOC ? 0 : p.fmt)
+#define EP_ABL(x) (!VOC && (p.ablate & (x)))
+#define EP_TANH (!VOC && p.tanh_out)
+#define EP_RES_F32 (VOC ? static_cast<const float*>(nullptr) : p.res_f32)
+#define EP_OUT_F32 (VOC ? static_cast<float*>(nullptr) : p.out_f32)
+#define EP_HAS_OUT (VOC || p.out)
+#else
+#define TC_KERNEL_TEMPLATE template <bool RES, bool ACC, bool CL>
+#define EP_FMT p.fmt
+#define EP_ABL(x) (p.ablate & (x))
+#define EP_TANH p.tanh_out
+#define EP_RES_F32 p.res_f32
+#define EP_OUT_F32 p.out_f32
+#define EP_HAS_OUT p.out
+#endif
+
 namespace pb {
 
 namespace {
@@ -223,7 +245,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-template <bool RES, bool ACC, bool CL>
+TC_KERNEL_TEMPLATE
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap omap,
                const TcParams p) {
@@ -312,7 +334,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&empty_a[a_s], a_ph ^ 1);
                 if (elect_one()) {
-                    if (p.ablate & 8) {
+                    if (EP_ABL(8)) {
                         mbar_arrive(&full_a[a_s]);
                     } else if (CL) {
                         // both CTAs load their own 128 rows; both signal the LEADER's barrier, which expects both halves
@@ -440,7 +462,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             }
         };
         auto request = [&](bool ok, size_t off, uint4 (&r)[4], uint4 (&a)[4]) {
-            if (!ok || (p.ablate & 4)) return;
+            if (!ok || EP_ABL(4)) return;
             if (RES) {
                 ld_global_nc_v8(p.res + off, r[0], r[1]);
                 ld_global_nc_v8(p.res + off + p.out_C, r[2], r[3]);
@@ -501,7 +523,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             float v[16];
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_cols + (uint32_t)n0;
-                if (p.ablate & 16) {
+                if (EP_ABL(16)) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 } else if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
@@ -514,7 +536,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     if (CL && rank != 0) mbar_arrive_remote(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
                 }
             }
-            if (cur.row_ok && !(p.ablate & 32)) {
+            if (cur.row_ok && !EP_ABL(32)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 bv = bv4[i];
@@ -526,7 +548,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     const uint32_t ll[8] = {R[2].x, R[2].y, R[2].z, R[2].w, R[3].x, R[3].y, R[3].z, R[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float2 r = join2(hh[i], ll[i], p.fmt);
+                        const float2 r = join2(hh[i], ll[i], EP_FMT);
                         float tx = r.x, ty = r.y;
                         mul2(tx, ty, p.res_unslope, p.res_unslope);
                         add2(v[2 * i], v[2 * i + 1], fminf(r.x, tx), fminf(r.y, ty));      // undo the stored leaky relu (1/slope >= 1)
@@ -537,7 +559,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     const uint32_t ll[8] = {A[2].x, A[2].y, A[2].z, A[2].w, A[3].x, A[3].y, A[3].z, A[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float2 r = join2(hh[i], ll[i], p.fmt);
+                        const float2 r = join2(hh[i], ll[i], EP_FMT);
                         add2(v[2 * i], v[2 * i + 1], r.x, r.y);
                     }
                 }
@@ -547,9 +569,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             // have the rest of this item plus the next accumulator read to arrive
             request(nxt.ok && nxt.row_ok, offn, R, A);
             uint32_t hw[8], lw[8];
-            if (cur.row_ok && !(p.ablate & 32)) {
-                if (p.res_f32) {      // fp32 residual stream [B][Lout][out_C] (TTE)
-                    const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + (off - (size_t)co) / 2 + co);
+            if (cur.row_ok && !EP_ABL(32)) {
+                if (EP_RES_F32) {      // fp32 residual stream [B][Lout][out_C] (TTE)
+                    const float4* rp = reinterpret_cast<const float4*>(EP_RES_F32 + (off - (size_t)co) / 2 + co);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 rv = __ldg(rp + i);
@@ -565,13 +587,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     v[2 * i] = fmaxf(v[2 * i], tx);         // leaky relu for slope in [0,1]; slope 1 = identity
                     v[2 * i + 1] = fmaxf(v[2 * i + 1], ty);
                 }
-                if (p.tanh_out) {
+                if (EP_TANH) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
                 }
-                if (p.out && !(p.ablate & 2)) {
+                if (EP_HAS_OUT && !EP_ABL(2)) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], p.fmt, hw[i], lw[i]);
+                    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], EP_FMT, hw[i], lw[i]);
                     if (!p.tma_out) {
                         __nv_bfloat16* oh = p.out + off;
                         __nv_bfloat16* ol = oh + p.out_C;
@@ -579,14 +601,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                         st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
                     }
                 }
-                if (p.out_f32) {
-                    float* of = p.out_f32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch
+                if (EP_OUT_F32) {
+                    float* of = EP_OUT_F32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<float4*>(of + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
-            if (p.tma_out && !(p.ablate & 2)) {
+            if (p.tma_out && !EP_ABL(2)) {
                 // Row-per-thread 32-byte global stores cost ~50 L1 wavefronts per instruction (every lane its own line); instead the
                 // warp parks its [32 rows x 16 ch] hi and lo tiles in shared memory (32B-swizzled: conflict-free 16-byte stores) and
                 // one lane hands them to the TMA unit.  Rows past the end of the sequence are clipped by the tensor map.
@@ -896,14 +918,17 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         int dev = 0;
         PB_CUDA(cudaGetDevice(&dev));
         PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+#ifdef PB_TC_FAMILY
+#define TC_SET_ATTR(R, A, C) \
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<R, A, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT)); \
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<R, A, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT))
+#else
+#define TC_SET_ATTR(R, A, C) \
+        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<R, A, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT))
+#endif
+        TC_SET_ATTR(false, false, false); TC_SET_ATTR(true, false, false); TC_SET_ATTR(true, true, false); TC_SET_ATTR(false, true, false);
+        TC_SET_ATTR(false, false, true); TC_SET_ATTR(true, false, true); TC_SET_ATTR(true, true, true); TC_SET_ATTR(false, true, true);
+#undef TC_SET_ATTR
         attr_set = true;
     }
     int grid = p.total_tiles < n_sm * ctas_per_sm ? p.total_tiles : n_sm * ctas_per_sm;
@@ -931,17 +956,27 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
+#ifdef PB_TC_FAMILY
+    // the vocoder's layer family (see the top of the file): everything the VOC instantiation assumes is checked here
+    const bool voc = a.fmt == 0 && !a.tanh_out && a.res_f32 == nullptr && a.out_f32 == nullptr && a.out != nullptr && p.ablate == 0;
+#define TC_LAUNCH(R, A, C) \
+    do { if (voc) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<R, A, C, true>, xmap, wmap, omap, p)); \
+         else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<R, A, C, false>, xmap, wmap, omap, p)); } while (0)
+#else
+#define TC_LAUNCH(R, A, C) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<R, A, C>, xmap, wmap, omap, p))
+#endif
     if (p.cluster) {
-        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, true>, xmap, wmap, omap, p));
-        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, true>, xmap, wmap, omap, p));
-        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, true>, xmap, wmap, omap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, true>, xmap, wmap, omap, p));
+        if (a.res && a.accin) TC_LAUNCH(true, true, true);
+        else if (a.res) TC_LAUNCH(true, false, true);
+        else if (a.accin) TC_LAUNCH(false, true, true);
+        else TC_LAUNCH(false, false, true);
     } else {
-        if (a.res && a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, true, false>, xmap, wmap, omap, p));
-        else if (a.res) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<true, false, false>, xmap, wmap, omap, p));
-        else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, true, false>, xmap, wmap, omap, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<false, false, false>, xmap, wmap, omap, p));
+        if (a.res && a.accin) TC_LAUNCH(true, true, false);
+        else if (a.res) TC_LAUNCH(true, false, false);
+        else if (a.accin) TC_LAUNCH(false, true, false);
+        else TC_LAUNCH(false, false, false);
     }
+#undef TC_LAUNCH
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;

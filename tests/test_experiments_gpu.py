@@ -70,9 +70,18 @@ def test_tma_store_on_k3_pair_layers_is_bit_identical(tmp_path, baseline):
     _same(baseline, _run(tmp_path, "tma3", {"PB_TC_TMA_OUT": "3"}))
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_column_split_epilogue_is_bit_identical(tmp_path, baseline, mode):
-    lib = os.path.join(ROOT, "parrot_tts_b200", "lib", "libparrot_b200_episplit.so")
+VARIANTS = {   # name -> (build flags, environment); build each with `python -m parrot_tts_b200.build --variant NAME --define ...`
+    "episplit": ("--define PB_TC_EPI_SPLIT --define PB_POST_TILE4", [{"PB_TC_EPI_SPLIT": "1"}, {"PB_TC_EPI_SPLIT": "2"}]),
+    "family": ("--define PB_TC_FAMILY", [{}]),
+    "r2all": ("--define PB_TC_EPI_SPLIT --define PB_POST_TILE4 --define PB_TC_FAMILY", [{"PB_TC_EPI_SPLIT": "1", "PB_VOC_CHAINS": "1"}]),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_variant_builds_are_bit_identical(tmp_path, baseline, variant):
+    flags, envs = VARIANTS[variant]
+    lib = os.path.join(ROOT, "parrot_tts_b200", "lib", f"libparrot_b200_{variant}.so")
     if not os.path.isfile(lib):
-        pytest.skip("build it first: python -m parrot_tts_b200.build --variant episplit --define PB_TC_EPI_SPLIT --define PB_POST_TILE4")
-    _same(baseline, _run(tmp_path, f"episplit{mode}", {"PB_LIB_VARIANT": "episplit", "PB_TC_EPI_SPLIT": mode}))
+        pytest.skip(f"build it first: python -m parrot_tts_b200.build --variant {variant} {flags}")
+    for n, env in enumerate(envs):
+        _same(baseline, _run(tmp_path, f"{variant}{n}", dict(env, PB_LIB_VARIANT=variant)))
