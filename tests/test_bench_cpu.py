@@ -72,3 +72,12 @@ def test_roofline_model_reproduces_the_committed_table():
 def test_chain_schedule_is_hazard_free():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_chain_schedule.py")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_cpu_baseline_sample_is_bounded():
+    sys.path.insert(0, ROOT)
+    import bench
+    shape = dict(workload="tiny", B=2, T=24, S=0)
+    d = bench.cpu_baseline_sample(shape, budget_s=0.5, max_steps=3)
+    assert d["kind"] == "port" and d["unit"] == "samples/s" and d["cores"] >= 1 and d["value"] > 0 and d["best_step"] >= d["value"] * 0.999
+    assert "1 utterance x 24 units" in d["sample"] and "step(s)" in d["sample"]
