@@ -465,7 +465,8 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("PB_TC_NO_PDL") != nullptr;      // dev switch, as in tc_conv.cu
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
     if (p.ksteps == 1) {
         if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 1>, xmap, omap, omap_tail, p));
         else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 1>, xmap, omap, omap_tail, p));

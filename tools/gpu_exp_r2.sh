@@ -31,6 +31,9 @@ for m in 1 3; do echo "== PB_TC_TMA_OUT=$m"; PB_TC_TMA_OUT=$m timeout 300 python
 PB_TC_TMA_OUT=3 timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q 2>&1 | tail -1
 # (3) chain streams: parity (bit-identical by construction: the running sum keeps its order), CUDA-graph capture, timing
 for m in 0 1; do echo "== PB_VOC_CHAINS=$m"; PB_VOC_CHAINS=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
+# with programmatic dependent launch the NEXT kernel of the same chain becomes resident early and idles in griddepcontrol.wait on the SMs
+# another chain's kernel could use: try the chains without it as well
+for m in 0 1; do echo "== PB_TC_NO_PDL=1 PB_VOC_CHAINS=$m"; PB_TC_NO_PDL=1 PB_VOC_CHAINS=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
 PB_VOC_CHAINS=1 timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q 2>&1 | tail -1
 PB_VOC_CHAINS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-text2wav > gpurun_out/bench_chains.json 2> gpurun_out/bench_chains.err; echo "bench rc=$?"
 # per-launch view of the winner (compare with profiles/r01_model_vs_measured.txt):
