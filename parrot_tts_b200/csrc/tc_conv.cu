@@ -47,7 +47,30 @@ namespace pb {
 
 namespace {
 
-constexpr int TC_MAX_THREADS = 512;         // 4 service warps + up to 3 epilogue groups of 4 warps (128 registers per thread)
+#ifdef PB_TC_GROUPS4
+// EXPERIMENTAL build (-DPB_TC_GROUPS4; written in round 1 without GPU access, NOT yet run): a FOURTH epilogue warpgroup.  640 threads
+// leave 102 registers per thread at launch, which spilled when it was tried - here the service warpgroup hands
+// registers back (setmaxnreg.dec) and the epilogue warpgroups grow (setmaxnreg.inc).
+constexpr int TC_MAX_GROUPS = 4;
+#ifndef PB_TC_REGS_SERVICE
+#define PB_TC_REGS_SERVICE 56
+#endif
+#ifndef PB_TC_REGS_EPI
+#define PB_TC_REGS_EPI 112          // 128 x 56 + 512 x 112 = 64 512 of 65 536 registers; ptxas spills least at this split (40/112, 48/112,
+                                    // 56/104, 64/104, 72/96, 88/88 tried: 688 bytes of spill stores over the 16 instantiations here, 1 280+ elsewhere)
+#endif
+#define TC_STR2(x) #x
+#define TC_STR(x) TC_STR2(x)
+// The register hand-over must DOMINATE the code it governs (ptxas allocates per region) and all four warps of a warpgroup must
+// execute the same instruction: the service warpgroup shrinks at the top of its branch, the epilogue warpgroups grow at the top of theirs.
+#define TC_SERVICE_BEGIN if (warp < 4) { asm volatile("setmaxnreg.dec.sync.aligned.u32 " TC_STR(PB_TC_REGS_SERVICE) ";" ::: "memory");
+#define TC_EPILOGUE_BEGIN } else { asm volatile("setmaxnreg.inc.sync.aligned.u32 " TC_STR(PB_TC_REGS_EPI) ";" ::: "memory");
+#else
+#define TC_SERVICE_BEGIN
+#define TC_EPILOGUE_BEGIN else if (warp >= 4) {
+constexpr int TC_MAX_GROUPS = 3;
+#endif
+constexpr int TC_MAX_THREADS = 128 + 128 * TC_MAX_GROUPS;   // 4 service warps + up to 3 epilogue groups of 4 warps (128 registers per thread)
 constexpr int TC_M = 128;                 // time rows per tile (UMMA M, cta_group::1)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_ACC = 8;                // accumulator stages in TMEM
@@ -310,6 +333,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     // phases live in uniform registers; only the asynchronous instructions themselves are issued by one elected lane.
     // (Measured: running the loops inside `if (lane == 0)` costs ~25 dependent R2UR/ELECT instructions per tcgen05.mma
     // and left the tensor pipe 57-80 % idle.)
+    TC_SERVICE_BEGIN
     if (warp == 0) {
         // =========================== producer ===========================
         if (p.res_blocks > 0) {
@@ -397,7 +421,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 default: mma_issuer<4, 0>(p, mc); break;
             }
         }
-    } else if (warp >= 4) {
+    }
+    TC_EPILOGUE_BEGIN
         // =========================== epilogue ===========================
         // Work items are (tile, 16-column chunk) in order; the residual / running-sum rows of item k+1 are requested as soon
         // as item k has consumed its own, so their latency hides behind the rest of item k and the next accumulator read.
@@ -791,7 +816,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
     p.tma_out = (a.out != nullptr && a.U == 1 && tma_out_mode > 0 && !want_2cta &&
                  (tma_out_mode == 2 || !p.cluster || (tma_out_mode == 3 && a.K <= 3))) ? 1 : 0;
-    uint32_t stage_bytes = p.tma_out ? 3u * 4u * 2048u : 0u;
+    uint32_t stage_bytes = p.tma_out ? (uint32_t)TC_MAX_GROUPS * 4u * 2048u : 0u;
     auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off - stage_bytes; };   // barriers + bias + alignment slack
     if (p.tma_out && !p.cluster && budget(TC_SMEM_LIMIT) < w_all + 2u * (uint32_t)p.a_stage_bytes) {
         // the staging tiles would cost weight residency: every resident block counts (measured ~6 us per block on the 64-channel
@@ -872,7 +897,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     // The epilogue of a narrow tile is a short latency-bound chain (accumulator wait, TMEM load, arithmetic, stores):
     // several warpgroups take alternate tiles so that those chains overlap.
     static const int env_groups = getenv("PB_TC_GROUPS") ? atoi(getenv("PB_TC_GROUPS")) : 0;
-    p.n_groups = a.n_groups > 0 ? a.n_groups : (env_groups > 0 ? env_groups : (ctas_per_sm == 2 ? 1 : 3));
+    p.n_groups = a.n_groups > 0 ? a.n_groups : (env_groups > 0 ? env_groups : (ctas_per_sm == 2 ? 1 : TC_MAX_GROUPS));
 #ifdef PB_TC_EPI_SPLIT
     // EXPERIMENTAL (see TcParams::epi_split).  PB_TC_EPI_SPLIT: 0 = off, 1 = the CTA-pair layers (default of this build), 2 = every one-CTA-per-SM layer
     static const int epi_split_env = getenv("PB_TC_EPI_SPLIT") ? atoi(getenv("PB_TC_EPI_SPLIT")) : 1;
@@ -882,7 +907,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     } else
 #endif
     if (p.n_groups > p.n_acc) p.n_groups = p.n_acc;
-    if (p.n_groups > 3) p.n_groups = 3;
+    if (p.n_groups > TC_MAX_GROUPS) p.n_groups = TC_MAX_GROUPS;
     const int threads = 128 + 128 * p.n_groups;
     int cols = 32;
     while (cols < p.n_acc * p.acc_cols) cols *= 2;

@@ -73,7 +73,8 @@ def test_tma_store_on_k3_pair_layers_is_bit_identical(tmp_path, baseline):
 VARIANTS = {   # name -> (build flags, environment); build each with `python -m parrot_tts_b200.build --variant NAME --define ...`
     "episplit": ("--define PB_TC_EPI_SPLIT --define PB_POST_TILE4", [{"PB_TC_EPI_SPLIT": "1"}, {"PB_TC_EPI_SPLIT": "2"}]),
     "family": ("--define PB_TC_FAMILY", [{}]),
-    "r2all": ("--define PB_TC_EPI_SPLIT --define PB_POST_TILE4 --define PB_TC_FAMILY", [{"PB_TC_EPI_SPLIT": "1", "PB_VOC_CHAINS": "1"}]),
+    "groups4": ("--define PB_TC_GROUPS4 --define PB_TC_EPI_SPLIT", [{"PB_TC_EPI_SPLIT": "1"}, {"PB_TC_EPI_SPLIT": "0"}]),
+    "r2all": ("--define PB_TC_EPI_SPLIT --define PB_POST_TILE4 --define PB_TC_FAMILY --define PB_TC_GROUPS4", [{"PB_TC_EPI_SPLIT": "1", "PB_VOC_CHAINS": "1"}]),
 }
 
 

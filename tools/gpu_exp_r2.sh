@@ -3,11 +3,13 @@
 #  (1) column-split epilogue groups in tc_conv (TcParams::epi_split; variant build) + 4-sample register tiles in conv_post (PB_POST_TILE4, same variant)
 #  (2) PB_TC_TMA_OUT=3: TMA-store epilogue on the CTA-pair layers with k <= 3 (product library, host-side switch)
 #  (3) PB_VOC_CHAINS=1: the three ResBlock chains of a stage on three streams (product library, host-side switch)
+#  (5) -DPB_TC_GROUPS4: a fourth epilogue warpgroup, registers handed over with setmaxnreg (variant build; with PB_TC_EPI_SPLIT=1 also on the wide layers)
 #  (4) -DPB_TC_FAMILY: tc_conv instantiated for the vocoder's layer family (flag tests of the epilogue folded away; variant build)
 # HERE, before gpurun (the .so files travel):
 #   python -m parrot_tts_b200.build --variant episplit --define PB_TC_EPI_SPLIT --define PB_POST_TILE4
 #   python -m parrot_tts_b200.build --variant family --define PB_TC_FAMILY
-#   python -m parrot_tts_b200.build --variant r2all --define PB_TC_EPI_SPLIT --define PB_POST_TILE4 --define PB_TC_FAMILY
+#   python -m parrot_tts_b200.build --variant groups4 --define PB_TC_GROUPS4 --define PB_TC_EPI_SPLIT
+#   python -m parrot_tts_b200.build --variant r2all --define PB_TC_EPI_SPLIT --define PB_POST_TILE4 --define PB_TC_FAMILY --define PB_TC_GROUPS4
 # ON THE BOX:                              bash tools/gpu_exp_r2.sh
 # PB_TC_EPI_SPLIT: 0 = off (the variant build then behaves like the product), 1 = CTA-pair layers, 2 = every one-CTA-per-SM layer
 mkdir -p gpurun_out
@@ -24,6 +26,7 @@ for m in 0 1 2; do
   PB_TC_EPI_SPLIT=$m timeout 300 python tools/dev_tte_time.py | tail -1
 done
 echo "== family"; PB_LIB_VARIANT=family timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1
+for m in 0 1; do echo "== groups4 PB_TC_EPI_SPLIT=$m"; PB_LIB_VARIANT=groups4 PB_TC_EPI_SPLIT=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
 echo "== r2all + chains"; PB_LIB_VARIANT=r2all PB_TC_EPI_SPLIT=1 PB_VOC_CHAINS=1 timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1
 # second prepared switch (product library, host-side only): TMA-store epilogue on the CTA-pair layers with k <= 3
 unset PB_LIB_VARIANT
