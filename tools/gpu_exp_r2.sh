@@ -38,6 +38,8 @@ for m in 0 1; do echo "== PB_VOC_CHAINS=$m"; PB_VOC_CHAINS=$m timeout 300 python
 # another chain's kernel could use: try the chains without it as well
 for m in 0 1; do echo "== PB_TC_NO_PDL=1 PB_VOC_CHAINS=$m"; PB_TC_NO_PDL=1 PB_VOC_CHAINS=$m timeout 300 python tools/dev_voc_time.py 8 1024 | tail -1; done
 PB_VOC_CHAINS=1 timeout 900 python -m pytest tests/test_voc_gpu.py -m gpu -x -q 2>&1 | tail -1
+# the single-utterance path (cfg1) is where independent chains can really run side by side: stages 1-2 are under one wave there
+for m in 0 1; do echo "== latency PB_VOC_CHAINS=$m"; PB_VOC_CHAINS=$m timeout 300 python tools/dev_latency.py | tail -3; done
 PB_VOC_CHAINS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-text2wav > gpurun_out/bench_chains.json 2> gpurun_out/bench_chains.err; echo "bench rc=$?"
 # per-launch view of the winner (compare with profiles/r01_model_vs_measured.txt):
 #   PB_TC_EPI_SPLIT=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
