@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """bench.py - throughput of the Parrot-TTS inference hot path on B200 (contract: see DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|cfg2|cfg3|cfg4]
 
-Workload (default, BASELINE.json configs[1]): batch = 8 utterances x 1024 HuBERT units through the HiFi-GAN
-CodeGenerator -> 8 x 327 680 samples per step per GPU.  `--workload cfg3` is configs[2]: 32 x 256 chars ->
-TTE -> 32 x 2048 units -> CodeGenerator (text -> wav); the default run also reports it under "text2wav".
+Workloads (BASELINE.json configs):
+  cfg3 (default at N = 1)  configs[2]: 32 x 256 chars -> TTE -> 32 x 2048 units -> CodeGenerator -> 20 971 520 samples per step
+                           (text -> wav, the configuration the metric is worded on)
+  cfg4 (default at N > 1)  configs[3]: a pool of 256 utterances of 256..4096 units (32..512 chars), text -> wav, sharded over the
+                           ranks by longest-processing-time-first, length-bucketed ragged vocoder batches, no collective on the
+                           data path - "scaling": "strong" (the pool is fixed, every rank takes its share)
+  cfg2                     configs[1]: 8 x 1024 units, CodeGenerator only (also reported as a supplementary block of the default run)
 
-One JSON line on stdout (rank 0).  `value` = audio samples/s with the inputs resident in HBM; `e2e` = the same
-metric through the public API (vocoder.generate(): pinned host codes -> H2D -> forward -> int16 PCM -> D2H);
-`roofline` = the ResBlock conv1d kernel family (90 launches/step) against the measured HBM copy bandwidth;
-`cpu_baseline` = the torch-CPU oracle port of the reference on this box's host cores (bounded sample).
-`--impl reference` times only that CPU port (the reference is pure PyTorch; its modules cannot travel to the
-GPU box, the oracle restates them and is pinned to them by tests/golden).
+One JSON line on stdout (rank 0).  `value` = audio samples/s with the inputs resident in HBM; `e2e` = the same metric through the
+public API from pinned HOST inputs to int16 PCM on the HOST; `roofline` = the ResBlock conv kernel family, timed live through the
+library's section events, against the measured HBM copy bandwidth (with the ncu-measured DRAM traffic of the same launches beside
+the layer-wise algorithmic bytes); `cpu_baseline` = the torch-CPU oracle port of the reference on this box's host cores (bounded
+sample).  `--impl reference` times only that CPU port on the same workload (one utterance of it per step).
 """
 import argparse
 import json
@@ -29,20 +32,29 @@ VOC_FLOP_PER_UNIT = 321656832.0
 # algorithmic fp32 bytes per unit of the 90 ResBlock convs, by stage
 RESBLOCK_BYTES_PER_UNIT = [230400.0, 460800.0, 921600.0, 921600.0, 921600.0]
 VOC_BYTES_PER_UNIT = 3616000.0
+N_RB_LAUNCH = 72      # 18 x 3 tc_conv launches (stages 1-3) + 9 x 2 fused tc_pair launches (stages 4-5) for the 90 ResBlock convs
 METRIC = "audio samples/s (22.05 kHz) end-to-end text->wav; RTF at 1/2/4/8 GPU"
+DTYPE = "f32 (split 16-bit x3 products on tcgen05, fp32 accumulation in TMEM)"
+CFG4_POOL = 256
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-text2wav", action="store_true")
-    ap.add_argument("--no-streaming", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the supplementary blocks (cfg2 / cfg1 latency / cfg5 streaming)")
+    return ap.parse_args(argv)
+
+
+def resolve_workload(name, world):
+    """auto: the single-GPU text -> wav configuration at N = 1, the sharded pool at N > 1."""
+    if name != "auto":
+        return name
+    return "cfg3" if world <= 1 else "cfg4"
 
 
 def peaks():
@@ -81,7 +93,31 @@ def peaks():
 def workload_shape(name):
     if name == "cfg2":
         return dict(workload="cfg2: batch=8 utterances x 1024 units, HiFi-GAN CodeGenerator only", B=8, T=1024, S=0)
-    return dict(workload="cfg3: batch=32, 256 chars -> 2048 units, TTE + CodeGenerator", B=32, T=2048, S=256)
+    if name == "cfg4":
+        return dict(workload=f"cfg4: {CFG4_POOL} utterances, 256..4096 units each (numpy default_rng(0)), chars = ceil(units / 8), "
+                             "TTE + CodeGenerator, LPT-sharded over the ranks", B=CFG4_POOL, T=0, S=-1)
+    return dict(workload="cfg3: batch=32, 256 chars -> 2048 units, TTE + CodeGenerator (text -> wav)", B=32, T=2048, S=256)
+
+
+def cfg4_lengths():
+    import numpy as np
+    return [int(v) for v in np.random.default_rng(0).integers(256, 4097, CFG4_POOL)]
+
+
+def config_block(name, world):
+    """The `config` object - identical in the GPU arm and the reference arm (same workload, same metric)."""
+    shape = workload_shape(name)
+    cfg = {"workload": shape["workload"], "n_ranks": world,
+           "l2": "GPU arm: 256 MB flush write before every timed step; the per-step activation working set (> 5 GB) exceeds the 126 MB L2",
+           "sharding": ("one batch of the workload per rank (weak scaling)" if name != "cfg4" else
+                        "the pool is split over the ranks by longest-processing-time-first on the utterance cost (strong scaling)") +
+                       ", weights broadcast once at init, no per-step collective",
+           "reference_arm_sample": "one utterance of the workload per step (the reference's own batch-of-1 inference mode), all host threads"}
+    if name == "cfg4":
+        cfg["pool_units"] = sum(cfg4_lengths())
+    else:
+        cfg["units_per_rank_per_step"] = shape["B"] * shape["T"]
+    return cfg
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -163,10 +199,13 @@ def cpu_models():
             folded[base + ".weight"] = voc_oracle.folded_weight(sd_v, base)
         elif not k.endswith(".weight_g"):
             folded[k] = sd_v[k]
-    cfg = configs.default_tte_config()
+    cfg = configs.default_tte_config(max_len=TTE_MAX_LEN)
     sd_t = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=0, dur_mode="const8")
     torch.set_num_threads(os.cpu_count() or 1)
     return h, folded, sd_t
+
+
+TTE_MAX_LEN = 4200      # cfg4 reaches 4096 units: the reference's table ends at 3500 rows (fft.py:18), the synthetic config raises it
 
 
 def cpu_step(h, sd_v, sd_t, S, B, T, seed):
@@ -188,54 +227,67 @@ def cpu_step(h, sd_v, sd_t, S, B, T, seed):
     return int(pcm.size), time.perf_counter() - t0
 
 
-def cpu_sample_shape(shape):
-    # bounded sample of the same workload: one utterance of the workload's length
-    if shape["S"] > 0:
-        return dict(B=1, S=shape["S"], T=shape["T"])
-    return dict(B=1, S=0, T=shape["T"])
+def cpu_sample_plan(name, n_steps):
+    """[(S, T)] per step: one utterance of the workload per step (cfg4: utterances of the pool, spread over its lengths)."""
+    shape = workload_shape(name)
+    if name == "cfg4":
+        L = sorted(cfg4_lengths())
+        pick = [L[(2 * i + 1) * len(L) // (2 * n_steps)] for i in range(n_steps)]      # evenly spaced quantiles of the pool
+        return [((n + 7) // 8, n) for n in pick]
+    return [(shape["S"], shape["T"])] * n_steps
 
 
-def cpu_baseline_sample(shape, budget_s=10.0, max_steps=64):
+def cpu_baseline_sample(name, budget_s=12.0, max_steps=48, plan=None):
     """The `cpu_baseline` object: the oracle port on this box's host cores over a bounded sample of the workload - one-utterance
-    steps of the workload's length until ~``budget_s`` seconds of CPU work have been timed (mean over all of them)."""
+    steps until ~``budget_s`` seconds of CPU work have been timed (mean over all of them).  ``plan`` overrides the (chars, units)
+    list of the workload (tests)."""
     import torch
-    smp = cpu_sample_shape(shape)
     hh, sd_v, sd_t = cpu_models()
-    cpu_step(hh, sd_v, sd_t, smp["S"], 1, min(smp["T"], 64), 99)  # warm-up
+    if plan is None:
+        plan = cpu_sample_plan(name, 12 if name == "cfg4" else max_steps)
+    cpu_step(hh, sd_v, sd_t, min(plan[0][0], 8), 1, 64, 99)  # warm-up
     tot_n, tot_s, best, done = 0, 0.0, None, 0
-    while done < max_steps and tot_s < budget_s:
-        n, sec = cpu_step(hh, sd_v, sd_t, smp["S"], smp["B"], smp["T"], done)
+    for S, T in plan:
+        if done and tot_s >= budget_s:
+            break
+        n, sec = cpu_step(hh, sd_v, sd_t, S, 1, T, done)
         tot_n += n
         tot_s += sec
         best = n / sec if best is None else max(best, n / sec)
         done += 1
+    units = sorted({T for _, T in plan[:done]})
+    what = f"{units[0]} units" if len(units) == 1 else f"{units[0]}..{units[-1]} units"
     return {"value": tot_n / tot_s, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "best_step": best,
-            "sample": f"{done} step(s) of {smp['B']} utterance x {smp['T']} units ({'TTE+' if smp['S'] else ''}CodeGenerator) = "
-                      f"{tot_s:.1f} s of CPU work, mean; torch CPU fp32 oracle port"}
+            "sample": f"{done} step(s) of 1 utterance x {what} of the workload ({'TTE + ' if plan[0][0] else ''}CodeGenerator -> int16) = "
+                      f"{tot_s:.1f} s of CPU work, mean; torch {torch.__version__} CPU fp32 oracle port"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
     import torch
-    shape = workload_shape(args.workload)
-    smp = cpu_sample_shape(shape)
+    name = resolve_workload(args.workload, world)
     h, sd_v, sd_t = cpu_models()
+    plan = cpu_sample_plan(name, args.steps)
     for i in range(max(args.warmup, 1)):
-        cpu_step(h, sd_v, sd_t, smp["S"], 1, min(smp["T"], 64) if i == 0 else smp["T"], 100 + i)
+        S, T = plan[i % len(plan)]
+        cpu_step(h, sd_v, sd_t, min(S, 8) if i == 0 else S, 1, 64 if i == 0 else T, 100 + i)
     tot_s, tot_n = 0.0, 0
-    for i in range(args.steps):
-        n, s = cpu_step(h, sd_v, sd_t, smp["S"], smp["B"], smp["T"], i)
+    for i, (S, T) in enumerate(plan):
+        n, s = cpu_step(h, sd_v, sd_t, S, 1, T, i)
         tot_n += n
         tot_s += s
     v = tot_n / tot_s
-    sample = f"per step: {smp['B']} utterance x {smp['T']} units of the workload ({'TTE+' if smp['S'] else ''}CodeGenerator, fp32, torch {torch.__version__} CPU)"
+    sample = (f"per step: 1 utterance of the workload ({'TTE + ' if plan[0][0] else ''}CodeGenerator -> int16, fp32, torch "
+              f"{torch.__version__} CPU, {torch.get_num_threads()} threads); {args.steps} steps = {tot_n} samples")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded random weights and unit codes)",
-        "config": {"workload": shape["workload"], "sample": sample},
+        "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if name == "cfg4" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded random weights, random char tokens / unit codes)",
+        "config": config_block(name, world),
         "rtf_16k": v / 16000.0, "rtf_22k05": v / 22050.0,
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,85 +299,148 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import tempfile
+class Bench:
+    """Process-wide state of the GPU arm: device, process group, models (weights broadcast once), timing helpers."""
 
-    import torch
-    import torch.distributed as dist
+    def __init__(self):
+        import tempfile
 
-    from parrot_tts_b200 import _lib, configs, sharding, synth
-    from parrot_tts_b200.tte import Parrot
-    from parrot_tts_b200.vocoder import CodeGenerator, generate
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
-    _lib.load()  # fails loudly if the extension is missing
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    quiet = _StdoutToStderr() if world > 1 else None     # NCCL prints its version banner to stdout
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    steps, warmup = args.steps, max(args.warmup, 3)
-    shape = workload_shape(args.workload)
-    B, T, S = shape["B"], shape["T"], shape["S"]
-    hbm_peak, tf_peak, peak_src = peaks()
+        from parrot_tts_b200 import _lib, configs, sharding, synth
+        from parrot_tts_b200.tte import Parrot
+        from parrot_tts_b200.vocoder import CodeGenerator
 
-    # ---- weights: rank 0 builds them, ONE broadcast at init, no collective afterwards ---------------------
-    h = configs.default_vocoder_config()
-    d = tempfile.mkdtemp(prefix="parrot_bench_")
-    with open(os.path.join(d, "speakers.json"), "w") as f:
-        json.dump({f"s{i}": i for i in range(10)}, f)
-    max_len = 3500
-    cfg = configs.default_tte_config(root_path=d, max_len=max_len)
-    sd = None
-    if rank == 0:
-        sd = {"voc." + k: v for k, v in synth.synth_vocoder_state_dict(h, seed=0).items()}
-        sd.update({"tte." + k: v for k, v in synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=0, dur_mode="const8").items()})
-    if world > 1:
-        sd = sharding.broadcast_state_dict(sd, src=0, device=dev)
-    voc = CodeGenerator(h)
-    voc.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("voc.")})
-    voc = voc.to(dev)
-    tte = Parrot(cfg, 150, 0)
-    tte.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("tte.")})
-    tte = tte.eval().to(dev)
-    del sd
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
+        _lib.load()  # fails loudly if the extension is missing
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.quiet = _StdoutToStderr() if self.world > 1 else None     # NCCL prints its version banner to stdout
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.hbm_peak, self.tf_peak, self.peak_src = peaks()
+        # ---- weights: rank 0 builds them, ONE broadcast at init, no collective afterwards ---------------------
+        self.h = configs.default_vocoder_config()
+        d = tempfile.mkdtemp(prefix="parrot_bench_")
+        with open(os.path.join(d, "speakers.json"), "w") as f:
+            json.dump({f"s{i}": i for i in range(10)}, f)
+        cfg = configs.default_tte_config(root_path=d, max_len=TTE_MAX_LEN)
+        self.voc = CodeGenerator(self.h)
+        self.tte = Parrot(cfg, 150, 0)
+        if self.rank == 0:      # only rank 0 "loads the checkpoint"
+            self.voc.load_state_dict(synth.synth_vocoder_state_dict(self.h, seed=0))
+            self.tte.load_state_dict(synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=0, dur_mode="const8"))
+        self.voc = self.voc.to(self.dev)
+        self.tte = self.tte.eval().to(self.dev)
+        self.broadcast_bytes = 0
+        if self.world > 1:      # the folded + packed weight arenas, once; nothing else is ever exchanged
+            self.broadcast_bytes = sharding.broadcast_engines([self.voc, self.tte], src=0, device=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
 
-    g = torch.Generator().manual_seed(1000 + rank)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, n_warm, n_steps, sampler=None):
-        """n_steps calls of fn, each between its own CUDA events on the current stream, L2 flushed before each
-        (outside the events); returns mean ms per step, max over ranks."""
+    def timed(self, fn, n_warm, n_steps, sampler=None, after=None):
+        """n_steps calls of fn, each between its own CUDA events on the current stream, L2 flushed before each (outside the
+        events); ``after`` (optional) runs after each step's end event (it may synchronise: every step has its own event pair).
+        Returns mean ms per step, max over ranks."""
+        torch = self.torch
         for _ in range(n_warm):
             fn()
-        barrier()
+        self.barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
-        ctx = sampler if sampler is not None else _Null()
-        with ctx:
+        with (sampler if sampler is not None else _Null()):
             for a, b in evs:
-                flush.fill_(1)
+                self.flush.fill_(1)
                 a.record()
                 fn()
                 b.record()
-            barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs) / n_steps
-        return max_over_ranks(ms)
+                if after is not None:
+                    after()
+            self.barrier()
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / n_steps)
+
+    def finish(self, line):
+        if self.rank == 0:
+            if self.quiet is not None:
+                self.quiet.restore()
+            print(json.dumps(line), flush=True)
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measured_traffic(workload):
+    """DRAM bytes per launch of the ResBlock conv family from the committed ncu capture of this bench's own step (profiles/
+    traffic.json, written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` - a profiler pass,
+    never a timed one).  None when the workload was not captured."""
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(tr) as f:
+            d = json.load(f)
+        v = d.get(workload)
+        return (float(v), d.get("source")) if isinstance(v, (int, float)) else (None, None)
+    except Exception:
+        return None, None
+
+
+def resblock_roofline(b, sec_ms, units, ms_step, workload):
+    """`roofline` of the dominant kernel family (the 72 ResBlock launches of a CodeGenerator forward) from live section times."""
+    rb_ms = sum(sec_ms[f"resblocks{i}"] for i in range(5))
+    rb_bytes = sum(RESBLOCK_BYTES_PER_UNIT) * units
+    achieved = rb_bytes / (rb_ms * 1e-3) / 1e9
+    # per-unit MMACs of the 90 ResBlock convs (SURVEY.md section 8d): 3 products per MAC on the tensor pipe
+    rb_mmac_per_unit = 41.288e6 * 3 + 20.644e6 + 10.322e6
+    traffic, traffic_src = measured_traffic(workload)
+    r = {
+        "bound": "hbm",
+        "kernel": "tc_conv_kernel + tc_pair_kernel (the 90 ResBlock1 dilated convs as tcgen05 implicit GEMMs on split-bf16 operands; "
+                  "lrelu + bias + residual + resblock mean fused in the epilogues)",
+        "achieved": achieved, "peak": b.hbm_peak, "unit": "GB/s", "frac": achieved / b.hbm_peak,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": b.peak_src,
+        "bytes_per_launch_avg": rb_bytes / N_RB_LAUNCH, "ms_per_launch_avg": rb_ms / N_RB_LAUNCH,
+        "share_of_step": rb_ms / ms_step,
+        "algorithmic_tflops": 2 * rb_mmac_per_unit * units / (rb_ms * 1e-3) / 1e12,
+        "tensor_pipe_tflops_3pass": 2 * 3 * rb_mmac_per_unit * units / (rb_ms * 1e-3) / 1e12,
+        "tensor_pipe_frac_of_bf16_peak": 2 * 3 * rb_mmac_per_unit * units / (rb_ms * 1e-3) / 1e12 / b.tf_peak,
+        "per_stage": {f"stage{i + 1}": {"ms": sec_ms[f"resblocks{i}"],
+                                        "GB/s": RESBLOCK_BYTES_PER_UNIT[i] * units / (sec_ms[f"resblocks{i}"] * 1e-3) / 1e9,
+                                        "frac": RESBLOCK_BYTES_PER_UNIT[i] * units / (sec_ms[f"resblocks{i}"] * 1e-3) / 1e9 / b.hbm_peak}
+                      for i in range(5)},
+        "section_ms": sec_ms,
+    }
+    if traffic:
+        # what the launches really pull from DRAM (fused pairs never write the conv1 output; stage-1 tensors partly hit L2)
+        r["dram_GB/s"] = traffic * N_RB_LAUNCH / (rb_ms * 1e-3) / 1e9
+        r["dram_frac"] = r["dram_GB/s"] / b.hbm_peak
+    return r
+
+
+def run_rect(args, name):
+    """cfg2 / cfg3: one rectangular batch of the workload per rank and step."""
+    b = Bench()
+    torch, dev, voc, tte, h = b.torch, b.dev, b.voc, b.tte, b.h
+    from parrot_tts_b200.vocoder import generate
+    steps, warmup = args.steps, max(args.warmup, 3)
+    shape = workload_shape(name)
+    B, T, S = shape["B"], shape["T"], shape["S"]
+    g = torch.Generator().manual_seed(1000 + b.rank)
 
     # ---- device-resident inputs ------------------------------------------------------------------------
     code = torch.randint(0, 1000, (B, T), generator=g).to(dev)
@@ -333,12 +448,15 @@ def run_ours(args):
     phones = torch.randint(2, 150, (B, max(S, 1)), generator=g).to(dev)
     tbatch = {"phones": phones, "src_mask": phones != 0, "speaker": (torch.arange(B) % 10).to(dev)}
     out = {}
+    tte_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
 
     def step_voc():
         out["wav"] = voc(code=code, spkr=spkr)
 
     def step_full():
+        tte_ev[0].record()
         ids, _ = tte.infer_device(tbatch)
+        tte_ev[1].record()
         out["wav"] = voc(code=ids, spkr=spkr)
         out["T"] = ids.shape[1]
 
@@ -349,65 +467,31 @@ def run_ours(args):
     samples_per_step = out["wav"].numel()
     assert samples_per_step == B * T * HOP, (samples_per_step, B, T)
 
-    # section events on for the timed run (13 cudaEventRecord per forward)
+    # section events on for the timed run (13 cudaEventRecord per forward); they are reused by every forward, so they are read
+    # right after each step's end event (reading synchronises; each step is timed by its own event pair)
     voc.set_timing(True, dev)
-    sampler = ClockSampler(local)
-    # the section events are reused by every forward, so they are read right after each step's end event
-    # (reading synchronises; each step is timed by its own event pair, so this does not enter the timing)
+    sampler = ClockSampler(b.local)
     sec_acc = {}
-    for _ in range(warmup):
-        step()
-    barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    with sampler:
-        for a, b in evs:
-            flush.fill_(1)
-            a.record()
-            step()
-            b.record()
-            for k, v in voc.section_ms().items():
-                sec_acc[k] = sec_acc.get(k, 0.0) + v
-        barrier()
-    ms_step = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / steps)
+
+    def read_sections():
+        for k, v in voc.section_ms().items():
+            sec_acc[k] = sec_acc.get(k, 0.0) + v
+        if S > 0:
+            sec_acc["tte"] = sec_acc.get("tte", 0.0) + tte_ev[0].elapsed_time(tte_ev[1])
+
+    ms_step = b.timed(step, warmup, steps, sampler, after=read_sections)
     voc.set_timing(False, dev)
-    value = world * samples_per_step / (ms_step * 1e-3)
+    value = b.world * samples_per_step / (ms_step * 1e-3)
     sec_ms = {k: v / steps for k, v in sec_acc.items()}
-
-    # ---- roofline of the dominant kernel family: conv1d_kernel on the ResBlock path ------------------------
     units = B * T
-    rb_ms = sum(sec_ms[f"resblocks{i}"] for i in range(5))
-    rb_bytes = sum(RESBLOCK_BYTES_PER_UNIT) * units
-    n_rb_launch = 72      # 18 x 3 tc_conv launches (stages 1-3) + 9 x 2 fused tc_pair launches (stages 4-5) for the 90 ResBlock convs
-    achieved = rb_bytes / (rb_ms * 1e-3) / 1e9
-    # per-unit MMACs of the 90 ResBlock convs: 3 products per MAC on the tensor pipe (split-bf16, 2 MMAs
-    # per k-step with the stacked operand for N <= 128, 3 for N = 256)
-    rb_mmac_per_unit = 41.288e6 * 3 + 20.644e6 + 10.322e6
-    roofline = {
-        "bound": "hbm",
-        "kernel": "tc_conv_kernel + tc_pair_kernel (the 90 ResBlock1 dilated convs as tcgen05 implicit GEMMs on split-bf16 operands: "
-                  "54 single-conv launches for C >= 64, 18 fused conv1->conv2 launches for C = 32 / 16; lrelu + bias + residual + "
-                  "resblock mean fused in the epilogues)",
-        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-        "peak_source": peak_src,
-        "bytes_per_launch_avg": rb_bytes / n_rb_launch, "ms_per_launch_avg": rb_ms / n_rb_launch,
-        "share_of_step": rb_ms / ms_step,
-        "algorithmic_tflops": 2 * rb_mmac_per_unit * units / (rb_ms * 1e-3) / 1e12,
-        "tensor_pipe_tflops_3pass": 2 * 3 * rb_mmac_per_unit * units / (rb_ms * 1e-3) / 1e12,
-        "tensor_pipe_frac_of_bf16_peak": 2 * 3 * rb_mmac_per_unit * units / (rb_ms * 1e-3) / 1e12 / tf_peak,
-        "per_stage": {f"stage{i + 1}": {"ms": sec_ms[f"resblocks{i}"], "GB/s": RESBLOCK_BYTES_PER_UNIT[i] * units / (sec_ms[f"resblocks{i}"] * 1e-3) / 1e9,
-                                        "frac": RESBLOCK_BYTES_PER_UNIT[i] * units / (sec_ms[f"resblocks{i}"] * 1e-3) / 1e9 / hbm_peak}
-                      for i in range(5)},
-        "section_ms": sec_ms,
-    }
-    tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tr):
-        try:
-            with open(tr) as f:
-                roofline["traffic"] = json.load(f).get(args.workload)
-        except Exception:
-            pass
+    roofline = resblock_roofline(b, sec_ms, units, ms_step, name)
+    if S > 0:
+        # 2.45 TFLOP of algorithmic TTE work at cfg3 (projections folded: 1.73 TFLOP of GEMMs + attention)
+        roofline["tte"] = {"ms": sec_ms["tte"], "share_of_step": sec_ms["tte"] / ms_step, "launches": tte.last_launches,
+                           "algorithmic_tflops": 2.45e12 / (sec_ms["tte"] * 1e-3) / 1e12,
+                           "tensor_pipe_frac_of_bf16_peak_3pass": 3 * 2.45e12 / (sec_ms["tte"] * 1e-3) / 1e12 / b.tf_peak}
 
-    # ---- e2e through the public API: pinned host codes -> H2D -> generate() -> int16 PCM on the host ------
+    # ---- e2e through the public API: pinned host inputs -> H2D -> (Parrot.infer_device ->) generate() -> int16 PCM on the host ------
     code_h = code.cpu().pin_memory()
     spkr_h = spkr.cpu().pin_memory()
     phones_h = phones.cpu().pin_memory()
@@ -417,28 +501,56 @@ def run_ours(args):
     def step_e2e():
         if S > 0:
             ph = phones_h.to(dev, non_blocking=True)
-            b = {"phones": ph, "src_mask": ph != 0, "speaker": spk_ids_h.to(dev, non_blocking=True)}
-            ids, _ = tte.infer_device(b)
+            bt = {"phones": ph, "src_mask": ph != 0, "speaker": spk_ids_h.to(dev, non_blocking=True)}
+            ids, _ = tte.infer_device(bt)
             c = {"code": ids, "spkr": spkr_h.to(dev, non_blocking=True)}
         else:
             c = {"code": code_h.to(dev, non_blocking=True), "spkr": spkr_h.to(dev, non_blocking=True)}
         audio, _ = generate(h, voc, c)      # int16 numpy on the host
         res["pcm"] = audio
 
-    e2e_ms = timed(step_e2e, warmup, steps)
+    e2e_ms = b.timed(step_e2e, warmup, steps)
     h2d = (phones_h.numel() * 8 + spk_ids_h.numel() * 8 if S > 0 else code_h.numel() * 8) + spkr_h.numel() * 8
     d2h = res["pcm"].size * 2
-    e2e = {"value": world * samples_per_step / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+    e2e = {"value": b.world * samples_per_step / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-           "api": "parrot_tts_b200.vocoder.generate(h, CodeGenerator, code) -> int16 PCM on host"}
+           "api": ("Parrot.infer_device(batch) -> " if S > 0 else "") + "parrot_tts_b200.vocoder.generate(h, CodeGenerator, code) -> int16 PCM on host"}
 
-    # ---- supplementary: configs[2] text -> wav (TTE + vocoder) ----------------------------------------------
-    text2wav = None
-    if S == 0 and not args.no_text2wav:
-        B3, S3 = 32, 256
-        ph3 = torch.randint(2, 150, (B3, S3), generator=g).to(dev)
-        b3 = {"phones": ph3, "src_mask": ph3 != 0, "speaker": (torch.arange(B3) % 10).to(dev)}
-        sp3 = (torch.arange(B3) % 10).view(B3, 1).to(dev)
+    extras = {} if args.no_extras else supplementary(b, skip=name)
+    cpu = None
+    if b.rank == 0 and b.world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(name)
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": b.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic (seeded random weights, random char tokens / unit codes)",
+        "config": config_block(name, b.world),
+        "rtf_16k": value / 16000.0, "rtf_22k05": value / 22050.0, "timed_region_s": ms_step * steps * 1e-3,
+        "vocoder_algorithmic_tflops": VOC_FLOP_PER_UNIT * units * b.world / ((ms_step - sec_ms.get("tte", 0.0)) * 1e-3) / 1e12,
+        "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+    }
+    line.update(extras)
+    b.finish(line)
+
+
+def supplementary(b, skip):
+    """Blocks beside the headline: configs[1] (vocoder only), configs[0] (single-utterance latency), configs[4] (streaming)."""
+    torch, dev, voc, tte = b.torch, b.dev, b.voc, b.tte
+    g = torch.Generator().manual_seed(2000 + b.rank)
+    out = {}
+    if skip != "cfg2":
+        code = torch.randint(0, 1000, (8, 1024), generator=g).to(dev)
+        spkr = torch.randint(0, 10, (8, 1), generator=g).to(dev)
+        ms2 = b.timed(lambda: voc(code=code, spkr=spkr), 2, 5)
+        out["vocoder_cfg2"] = {"workload": workload_shape("cfg2")["workload"], "ms_per_step": ms2,
+                               "value": b.world * 8 * 1024 * HOP / (ms2 * 1e-3), "unit": "samples/s",
+                               "hbm_algorithmic_frac": VOC_BYTES_PER_UNIT * 8192 / (ms2 * 1e-3) / 1e9 / b.hbm_peak,
+                               "gpu_launches_per_step": voc.last_launches}
+    if skip != "cfg3":
+        ph3 = torch.randint(2, 150, (32, 256), generator=g).to(dev)
+        b3 = {"phones": ph3, "src_mask": ph3 != 0, "speaker": (torch.arange(32) % 10).to(dev)}
+        sp3 = (torch.arange(32) % 10).view(32, 1).to(dev)
         t3 = {}
 
         def step3():
@@ -446,118 +558,81 @@ def run_ours(args):
             t3["n"] = voc(code=ids, spkr=sp3).numel()
             t3["launch"] = tte.last_launches + voc.last_launches
 
-        def step3_tte():
-            tte.infer_device(b3)
+        ms3 = b.timed(step3, 2, 3)
+        ms3_tte = b.timed(lambda: tte.infer_device(b3), 1, 3)
+        out["text2wav_cfg3"] = {"workload": workload_shape("cfg3")["workload"], "ms_per_step": ms3, "tte_ms": ms3_tte,
+                                "value": b.world * t3["n"] / (ms3 * 1e-3), "unit": "samples/s", "gpu_launches_per_step": t3["launch"]}
 
-        ms3 = timed(step3, 2, 3)
-        ms3_tte = timed(step3_tte, 1, 3)
-        tte_flop = 2.45e12   # TTE at cfg3
-        text2wav = {"workload": "cfg3: batch=32, 256 chars -> 2048 units, TTE (tcgen05 split-fp16 GEMMs + fused attention) + CodeGenerator",
-                    "ms_per_step": ms3, "tte_algorithmic_tflops": tte_flop / (ms3_tte * 1e-3) / 1e12,
-                    "tte_ms": ms3_tte, "value": world * t3["n"] / (ms3 * 1e-3), "unit": "samples/s",
-                    "rtf_16k": t3["n"] / (ms3 * 1e-3) / 16000.0, "gpu_launches_per_step": t3["launch"]}
+    # ---- configs[0] single-utterance latency: 64 chars -> 512 units -> int16 PCM on the host (wall clock) ---------
+    from parrot_tts_b200 import ops as _ops
+    from parrot_tts_b200.vocoder import GraphedGenerator, stream_generate
+    ph1_h = torch.randint(2, 150, (1, 64), generator=g).pin_memory()
+    sp1 = torch.zeros(1, 1, dtype=torch.long, device=dev)
+    spk1 = torch.zeros(1, dtype=torch.long, device=dev)
+    voc_graphs = {}
 
-    # ---- supplementary: configs[0] single-utterance latency: 64 chars -> 512 units -> int16 PCM on the host ---------
-    latency = None
-    if S == 0 and not args.no_text2wav:
-        from parrot_tts_b200 import ops as _ops
-        ph1_h = torch.randint(2, 150, (1, 64), generator=g).pin_memory()
-        sp1 = torch.zeros(1, 1, dtype=torch.long, device=dev)
-        spk1 = torch.zeros(1, dtype=torch.long, device=dev)
+    def run1(graphed=False):
+        ph = ph1_h.to(dev, non_blocking=True)
+        ids, _ = tte.infer_device({"phones": ph, "src_mask": ph != 0, "speaker": spk1})
+        if not graphed:
+            return _ops.to_host(voc.forward_pcm16(code=ids, spkr=sp1)).size
+        T1 = int(ids.shape[1])
+        if T1 not in voc_graphs:      # the vocoder forward + PCM cast of this length as one CUDA graph
+            voc_graphs[T1] = GraphedGenerator(voc, 1, T1, pcm16=True)
+        return _ops.to_host(voc_graphs[T1](ids, sp1)).size
 
-        from parrot_tts_b200.vocoder import GraphedGenerator
-        voc_graphs = {}
-
-        def run1(graphed=False):
-            ph = ph1_h.to(dev, non_blocking=True)
-            ids, _ = tte.infer_device({"phones": ph, "src_mask": ph != 0, "speaker": spk1})
-            if not graphed:
-                return _ops.wav_to_pcm16(voc(code=ids, spkr=sp1)).cpu().numel()
-            T1 = int(ids.shape[1])
-            if T1 not in voc_graphs:      # the vocoder forward + PCM cast of this length as one CUDA graph
-                voc_graphs[T1] = GraphedGenerator(voc, 1, T1, pcm16=True)
-            return voc_graphs[T1](ids, sp1).cpu().numel()
-
-        def wall(fn):
-            for _ in range(3):
-                fn()
-            ts = []
-            for _ in range(20):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter(); n = fn(); ts.append((time.perf_counter() - t0) * 1e3)
-            ts.sort()
-            return ts, n
-
-        ts, n1 = wall(run1)
-        latency = {"workload": "cfg1: 1 utterance, 64 chars -> TTE -> 512 units -> CodeGenerator -> int16 PCM on host (wall clock)",
-                   "median_ms": ts[len(ts) // 2], "min_ms": ts[0], "samples": n1, "rtf_16k": n1 / (ts[len(ts) // 2] * 1e-3) / 16000.0,
-                   "gpu_launches": tte.last_launches + voc.last_launches + 1}
-        try:      # supplementary: never let a capture problem take the headline line down
-            tg, _ = wall(lambda: run1(True))
-            latency["vocoder_cuda_graph"] = {"median_ms": tg[len(tg) // 2], "min_ms": tg[0]}
-        except Exception as e:  # noqa: BLE001
-            latency["vocoder_cuda_graph"] = {"error": str(e)[:200]}
-
-    # ---- supplementary: configs[4] long-form streaming: 16 384 units in 1024-unit chunks with a 32-unit halo -------
-    streaming = None
-    if S == 0 and not args.no_streaming:
-        from parrot_tts_b200.vocoder import stream_generate
-        code5_h = torch.randint(0, 1000, (1, 16384), generator=g).pin_memory()
-        spk5 = torch.zeros(1, 1, dtype=torch.long, device=dev)
-
-        stream_graphs = {}
-
-        def run_stream(first_only, graphs=None):
-            c5 = code5_h.to(dev, non_blocking=True)
-            n = 0
-            for _, pcm in stream_generate(voc, c5, spk5, chunk_units=1024, halo_units=32, pcm16=True, graphs=graphs):
-                n += pcm.cpu().numel()       # int16 PCM of the chunk on the host
-                if first_only:
-                    break
-            return n
-
-        run_stream(False)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter(); run_stream(True); first_ms = (time.perf_counter() - t0) * 1e3
-        t0 = time.perf_counter(); n5 = run_stream(False); all_s = time.perf_counter() - t0
-        streaming = {"workload": "cfg5: 16 384 units streamed as 16 chunks of 1024 units (+32-unit halo), host codes -> int16 PCM on host",
-                     "time_to_first_chunk_ms": first_ms, "steady_samples_per_s": n5 / all_s, "rtf_16k": n5 / all_s / 16000.0,
-                     "total_ms": all_s * 1e3}
-        try:
-            run_stream(False, stream_graphs)           # captures one CUDA graph per window length (3)
+    def wall(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(20):
             torch.cuda.synchronize()
-            t0 = time.perf_counter(); run_stream(True, stream_graphs); first_g = (time.perf_counter() - t0) * 1e3
-            t0 = time.perf_counter(); n5g = run_stream(False, stream_graphs); all_g = time.perf_counter() - t0
-            streaming["cuda_graphs"] = {"time_to_first_chunk_ms": first_g, "steady_samples_per_s": n5g / all_g, "total_ms": all_g * 1e3}
-        except Exception as e:  # noqa: BLE001
-            streaming["cuda_graphs"] = {"error": str(e)[:200]}
+            t0 = time.perf_counter(); n = fn(); ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        return ts, n
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -----------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_sample(shape)
+    ts, n1 = wall(run1)
+    latency = {"workload": "cfg1: 1 utterance, 64 chars -> TTE -> 512 units -> CodeGenerator -> int16 PCM on host (wall clock)",
+               "median_ms": ts[len(ts) // 2], "min_ms": ts[0], "samples": n1, "rtf_16k": n1 / (ts[len(ts) // 2] * 1e-3) / 16000.0,
+               "gpu_launches": tte.last_launches + voc.last_launches + 1}
+    try:      # supplementary: never let a capture problem take the headline line down
+        tg, _ = wall(lambda: run1(True))
+        latency["vocoder_cuda_graph"] = {"median_ms": tg[len(tg) // 2], "min_ms": tg[0]}
+    except Exception as e:  # noqa: BLE001
+        latency["vocoder_cuda_graph"] = {"error": str(e)[:200]}
+    out["latency"] = latency
 
-    if rank == 0:
-        clocks = sampler.summary()
-        line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (split-bf16 x3 products on tcgen05, fp32 accumulation in TMEM)",
-            "data": "synthetic (seeded random weights, random unit codes / char tokens)",
-            "config": {"workload": shape["workload"], "units_per_gpu_per_step": units, "samples_per_gpu_per_step": samples_per_step,
-                       "l2": "256 MB flush write before every timed step; per-step activation working set (>5 GB) exceeds the 126 MB L2",
-                       "sharding": f"{world} rank(s), one utterance batch per rank, weights broadcast once at init, no per-step collective"},
-            "rtf_16k": value / 16000.0, "rtf_22k05": value / 22050.0,
-            "vocoder_algorithmic_tflops": VOC_FLOP_PER_UNIT * units * world / (ms_step * 1e-3) / 1e12 if S == 0 else None,
-            "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "text2wav": text2wav, "latency": latency, "streaming": streaming,
-        }
-        if quiet is not None:
-            quiet.restore()
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # ---- configs[4] long-form streaming: 16 384 units in 1024-unit chunks with a 32-unit halo -------
+    code5_h = torch.randint(0, 1000, (1, 16384), generator=g).pin_memory()
+    spk5 = torch.zeros(1, 1, dtype=torch.long, device=dev)
+    stream_graphs = {}
+
+    def run_stream(first_only, graphs=None):
+        c5 = code5_h.to(dev, non_blocking=True)
+        n = 0
+        for _, pcm in stream_generate(voc, c5, spk5, chunk_units=1024, halo_units=32, pcm16=True, graphs=graphs):
+            n += _ops.to_host(pcm).size       # int16 PCM of the chunk on the host
+            if first_only:
+                break
+        return n
+
+    run_stream(False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); run_stream(True); first_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); n5 = run_stream(False); all_s = time.perf_counter() - t0
+    streaming = {"workload": "cfg5: 16 384 units streamed as 16 chunks of 1024 units (+32-unit halo), host codes -> int16 PCM on host",
+                 "time_to_first_chunk_ms": first_ms, "steady_samples_per_s": n5 / all_s, "rtf_16k": n5 / all_s / 16000.0,
+                 "total_ms": all_s * 1e3}
+    try:
+        run_stream(False, stream_graphs)           # captures one CUDA graph per window length (3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); run_stream(True, stream_graphs); first_g = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); n5g = run_stream(False, stream_graphs); all_g = time.perf_counter() - t0
+        streaming["cuda_graphs"] = {"time_to_first_chunk_ms": first_g, "steady_samples_per_s": n5g / all_g, "total_ms": all_g * 1e3}
+    except Exception as e:  # noqa: BLE001
+        streaming["cuda_graphs"] = {"error": str(e)[:200]}
+    out["streaming"] = streaming
+    return out
 
 
 class _StdoutToStderr:
@@ -584,88 +659,129 @@ class _Null:
         return False
 
 
-def run_cfg4(args):
-    """BASELINE configs[3]: 256 utterances of 256..4096 units, sharded data-parallel by longest-processing-time-first on
-    their length, batched in length buckets (each item masked to its own length = its batch-of-1 result); no collective on
-    the data path.  value = true (unpadded) samples of all ranks / slowest rank's time."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    from parrot_tts_b200 import _lib, configs, sharding, synth
-    from parrot_tts_b200.vocoder import CodeGenerator
-
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device")
-    _lib.load()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    quiet = _StdoutToStderr() if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    h = configs.default_vocoder_config()
-    sd = synth.synth_vocoder_state_dict(h, seed=0) if rank == 0 else None
-    if world > 1:
-        sd = sharding.broadcast_state_dict(sd, src=0, device=dev)
-    voc = CodeGenerator(h); voc.load_state_dict(sd); voc = voc.to(dev)
-    lengths = np.random.default_rng(0).integers(256, 4097, 256).tolist()
-    bins = sharding.lpt_assign([sharding.utterance_cost(n, with_tte=False) for n in lengths], world)
-    batches = sharding.length_buckets(bins[rank], lengths, max_batch=8)
+def cfg4_pool(torch):
+    """The pool: (unit lengths, char-token sequences on the host, TTE speaker ids, vocoder voices) - identical on every rank."""
+    lengths = cfg4_lengths()
     g = torch.Generator().manual_seed(7)
-    work = []
-    for idx in batches:
-        Lmax = max(lengths[i] for i in idx)
-        code = torch.randint(0, 1000, (len(idx), Lmax), generator=g).to(dev)
-        lens = torch.tensor([lengths[i] for i in idx], dtype=torch.int32, device=dev)
-        spk = torch.randint(0, 10, (len(idx), 1), generator=g).to(dev)
-        work.append((code, spk, lens))
-    my_units = sum(lengths[i] for i in bins[rank]); padded = sum(c.numel() for c, _, _ in work)
+    phones = [torch.randint(2, 150, ((n + 7) // 8,), generator=g) for n in lengths]      # dur == 8 units per char (const8 weights)
+    speakers = [i % 10 for i in range(len(lengths))]
+    return lengths, phones, speakers
 
-    def step():
-        for code, spk, lens in work:
-            voc(code=code, spkr=spk, lens=lens)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+def run_cfg4(args):
+    """BASELINE configs[3]: 256 utterances of 256..4096 units, text -> wav, sharded data-parallel by longest-processing-time-first on
+    their cost; per rank the TTE runs its utterances one at a time (the reference's inference mode), the vocoder in length buckets
+    (each item masked to its own length = its batch-of-1 result); no collective on the data path.  value = true (unpadded) samples
+    of ALL ranks / the slowest rank's time."""
+    b = Bench()
+    torch, dev, voc, tte = b.torch, b.dev, b.voc, b.tte
+    from parrot_tts_b200 import serving
+    steps, warmup = args.steps, max(args.warmup, 3)
+    lengths, phones_h, speakers = cfg4_pool(torch)
+    mine = serving.rank_share_tte(lengths, b.world, b.rank)
+    pipe = serving.SpeechPipeline(tte, voc, max_batch=8, long_form_units=None)
+    phones_pin = [p.pin_memory() for p in phones_h]
+    phones_dev = [p.to(dev) for p in phones_h]
+    my_units = sum(lengths[i] for i in mine)
     total_units = sum(lengths)
-    if rank == 0:
-        v = total_units * HOP / (ms * 1e-3)
-        if quiet is not None:
-            quiet.restore()
-        print(json.dumps({"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": "f32 (split-bf16 x3 products on tcgen05, fp32 accumulation in TMEM)", "data": "synthetic",
-                          "config": {"workload": "cfg4: 256 utterances, 256..4096 units each (numpy default_rng(0)), CodeGenerator, LPT-sharded over the ranks, length buckets of <= 8",
-                                     "rank0_units": my_units, "rank0_padded_units": padded, "rank0_batches": len(work)},
-                          "rtf_16k": v / 16000.0, "gpu_launches": int(voc.last_launches * len(work) * args.steps)}), flush=True)
-    if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+    res = {}
+
+    def step_dev():       # inputs resident in HBM, waveforms left on the device as f32
+        res["wav"] = pipe(phones_dev, speakers, indices=mine, pcm16=False, to_host=False)
+
+    def step_e2e():       # pinned host char tokens -> int16 PCM of every utterance on the host
+        res["pcm"] = pipe(phones_pin, speakers, indices=mine, pcm16=True, to_host=True)
+
+    step_dev()
+    torch.cuda.synchronize()
+    got = sum(int(w.numel()) for w in res["wav"] if w is not None)
+    assert got == my_units * HOP, (got, my_units)
+    launches_per_step = pipe.last_launches + pipe.synth.last_launches
+    plan = pipe.synth.last_plan
+    sampler = ClockSampler(b.local)
+    ms_step = b.timed(step_dev, warmup, steps, sampler)
+    value = total_units * HOP / (ms_step * 1e-3)
+    e2e_ms = b.timed(step_e2e, warmup, steps)
+    h2d = sum(phones_h[i].numel() * 8 + 8 + 8 for i in mine)
+    d2h = sum(int(a.size) * 2 for a in res["pcm"] if a is not None)
+    e2e = {"value": total_units * HOP / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_ms, "bytes_are": "rank 0's share",
+           "api": "parrot_tts_b200.serving.SpeechPipeline(parrot, generator)(phones, speakers, indices=rank share) -> int16 PCM on host"}
+
+    # ---- roofline of the ResBlock family: one more pass over this rank's vocoder batches with the section events on (reading them
+    # synchronises, so this pass is not the timed one; same batches, same kernels) ---------------------------------------------
+    units_dev = pipe.units(phones_dev, speakers, mine)
+    voc.set_timing(True, dev)
+    sec_acc, padded_units, rb_steps = {}, 0, 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    voc_ms = 0.0
+    for bt in plan["batches"]:
+        idx = [mine[k] for k in bt]
+        Lmax = lengths[idx[0]]
+        codes = torch.zeros(len(idx), Lmax, dtype=torch.long, device=dev)
+        for r, i in enumerate(idx):
+            codes[r, :lengths[i]] = units_dev[i]
+        lens = torch.tensor([lengths[i] for i in idx], dtype=torch.int32, device=dev)
+        spk = torch.tensor([[speakers[i]] for i in idx], dtype=torch.long, device=dev)
+        b.flush.fill_(1)
+        ev0.record()
+        voc(code=codes, spkr=spk, lens=lens)
+        ev1.record()
+        for k, v in voc.section_ms().items():
+            sec_acc[k] = sec_acc.get(k, 0.0) + v
+        voc_ms += ev0.elapsed_time(ev1)
+        padded_units += len(idx) * Lmax
+        rb_steps += 1
+    voc.set_timing(False, dev)
+    roofline = resblock_roofline(b, sec_acc, my_units, voc_ms, "cfg4")
+    roofline["bytes_per_launch_avg"] = sum(RESBLOCK_BYTES_PER_UNIT) * my_units / (N_RB_LAUNCH * rb_steps)
+    roofline["ms_per_launch_avg"] = sum(sec_acc[f"resblocks{i}"] for i in range(5)) / (N_RB_LAUNCH * rb_steps)
+    roofline["share_of_step"] = sum(sec_acc[f"resblocks{i}"] for i in range(5)) / ms_step
+    roofline["note"] = (f"rank 0's {rb_steps} vocoder batches ({my_units} true units, {padded_units} padded) in a separate pass with section "
+                        "events; bytes counted on TRUE units (padding is waste, not credit)")
+
+    extras = {}
+    if b.world > 1 and not args.no_extras:
+        # strong-scaling reference point measured in the same run: rank 0 alone synthesises the WHOLE pool while the others wait
+        if b.rank == 0:
+            everything = list(range(len(lengths)))
+            def step_all():
+                pipe(phones_dev, speakers, indices=everything, pcm16=False, to_host=False)
+            step_all()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_all(); step_all(); e1.record(); torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1) / 2
+            extras["strong_scaling"] = {"one_gpu_ms_per_step": ms1, "one_gpu_value": total_units * HOP / (ms1 * 1e-3),
+                                        "speedup": ms1 / ms_step, "efficiency": ms1 / ms_step / b.world,
+                                        "note": "same pool on rank 0 alone, measured inside this run (2 passes, CUDA events)"}
+        b.barrier()
+    cpu = None
+    if b.rank == 0 and b.world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample("cfg4")
+    costs = None
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": b.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
+        "data": "synthetic (seeded random weights, random char tokens)", "config": config_block("cfg4", b.world),
+        "rtf_16k": value / 16000.0, "rtf_22k05": value / 22050.0, "timed_region_s": ms_step * steps * 1e-3,
+        "rank0": {"utterances": len(mine), "units": my_units, "padded_units": padded_units, "vocoder_batches": rb_steps},
+        "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+    }
+    line.update(extras)
+    b.finish(line)
 
 
 def main():
     args = parse()
     if args.impl == "reference":
-        run_reference(args)
-    elif args.workload == "cfg4":
+        return run_reference(args)
+    name = resolve_workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")))
+    if name == "cfg4":
         run_cfg4(args)
     else:
-        run_ours(args)
+        run_rect(args, name)
 
 
 if __name__ == "__main__":

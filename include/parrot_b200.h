@@ -92,6 +92,17 @@ int pb_voc_finalize(pb_voc* h, void* stream);
 int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
                    int32_t B, int32_t T, float* wav, void* stream);
 
+/* nn.Embedding raises IndexError on an id outside its table (utils/vocoder/models.py:155-156).  The forward is asynchronous and its
+ * embedding kernel clamps such ids (and flags them, live positions only); this call SYNCHRONISES `stream`, returns PB_ERR_INDEX if
+ * any forward since the last check saw one, and clears the flag. */
+int pb_voc_check_ids(pb_voc* h, void* stream);
+
+/* pb_voc_forward with the generate() tail fused into conv_post's epilogue (utils/vocoder/inference.py:65-74): pcm i16 [B, hop*T] =
+ * (int16) trunc(wav * 32768), the same expression pb_wav_to_pcm16 applies to the same float; wav f32 [B,1,hop*T] or NULL (then
+ * the waveform never reaches HBM as f32).  conv_mode 0 needs wav (the cast is a separate launch there). */
+int pb_voc_forward_pcm16(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
+                         int32_t B, int32_t T, float* wav, int16_t* pcm, void* stream);
+
 /* generate() tail (utils/vocoder/inference.py:71-73): pcm = (int16) trunc(wav * 32768) (wraps like a C cast). */
 int pb_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, void* stream);
 
@@ -103,6 +114,9 @@ int pb_pcm16_peak_normalize(const int16_t* pcm, int32_t B, int64_t n, int32_t* p
 
 /* Number of this library's kernel launches issued by the last pb_voc_forward / pb_tte_* call on the handle. */
 int64_t pb_voc_last_launches(const pb_voc* h);
+/* Changes whenever the handle's weight arena or workspace has been (re)allocated: device pointers recorded earlier - a captured
+ * CUDA graph of pb_voc_forward - are stale once it differs (the workspace grows with the largest forward seen). */
+int64_t pb_voc_memory_epoch(const pb_voc* h);
 
 /* Section timing for the roofline report (bench.py): when enabled, pb_voc_forward records CUDA events on the
  * caller's stream at its section boundaries.  Sections: 0 = embedding + conv_pre; 1+2i = ups[i];
@@ -176,8 +190,12 @@ int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* src_mask, con
 
 /* length_regulator + pos_emb + decoder + head (+ argmax of Parrot.infer) (duration.py:6-24; parrot.py:106-108,115)
  * for the batch just encoded.  logits f32 [B,T,n_codes] or NULL; ids i64 [B,T] or NULL;
- * tgt_mask u8 [B,T] (t <= out_lens[b], data.py:18).  Asynchronous. */
-int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, float* logits, int64_t* ids, uint8_t* tgt_mask, void* stream);
+ * tgt_mask u8 [B,T] out (t <= out_lens[b], data.py:18).
+ * tgt_mask_in: NULL, or the caller's mask u8 [B,T] (batch['tgt_mask'] of the teacher-forced path, parrot.py:104 ->
+ * duration.py:22-24: the reference returns a supplied mask unchanged and the decoder attends with it); it then replaces the
+ * generated one for the decoder's key padding and is what tgt_mask returns.  Asynchronous. */
+int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, const uint8_t* tgt_mask_in, float* logits, int64_t* ids, uint8_t* tgt_mask,
+                  void* stream);
 
 int64_t pb_tte_last_launches(const pb_tte* h);
 

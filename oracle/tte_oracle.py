@@ -129,11 +129,12 @@ def _n_layers(sd, stack):
     return n
 
 
-def parrot_forward(sd, batch, n_head=2, dur_override=None):
+def parrot_forward(sd, batch, n_head=2, dur_override=None, tgt_mask=None):
     """Parrot.forward(batch, inference=True) (modules/parrot.py:90-110).
 
     Returns dict(logits, src_mask, tgt_mask, log_dur, dur, out_lens, enc_out).
-    ``dur_override`` plays the role of ``batch['duration']`` (teacher-forced path, :102).
+    ``dur_override`` plays the role of ``batch['duration']`` (teacher-forced path, :102) and ``tgt_mask`` of ``batch['tgt_mask']``:
+    length_regulator returns a supplied mask unchanged (modules/duration.py:9-10,22-24) and the decoder attends with it (:107).
     """
     with torch.no_grad():
         src_mask = batch["src_mask"]
@@ -146,7 +147,11 @@ def parrot_forward(sd, batch, n_head=2, dur_override=None):
         enc_out = out
         log_dur = duration_predictor(sd, out, ~src_mask)
         dur = round_durations(log_dur) if dur_override is None else dur_override
+        given = tgt_mask
         out, tgt_mask, out_lens = length_regulator(out, dur)
+        if given is not None:
+            assert given.shape[1] == out.shape[1]
+            tgt_mask = given
         out = pos_emb(sd, out)
         for i in range(_n_layers(sd, "decoder_layers")):
             out = fft_block(sd, f"decoder_layers.{i}", out, ~tgt_mask, n_head)

@@ -55,9 +55,12 @@ SIGNATURES = {
     "pb_voc_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(_I64), _I32, _I32]),
     "pb_voc_finalize": (C.c_int, [_P, _P]),
     "pb_voc_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
+    "pb_voc_forward_pcm16": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "pb_wav_to_pcm16": (C.c_int, [_P, _I64, _P, _P]),
     "pb_pcm16_peak_normalize": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "pb_voc_last_launches": (_I64, [_P]),
+    "pb_voc_memory_epoch": (_I64, [_P]),
+    "pb_voc_check_ids": (C.c_int, [_P, _P]),
     "pb_voc_set_timing": (C.c_int, [_P, _I32]),
     "pb_voc_section_count": (C.c_int, [_P]),
     "pb_voc_section_ms": (C.c_int, [_P, C.POINTER(_F), _I32]),
@@ -73,7 +76,7 @@ SIGNATURES = {
     "pb_tte_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(_I64), _I32, _I32]),
     "pb_tte_finalize": (C.c_int, [_P, _P]),
     "pb_tte_encode": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.POINTER(_I32), _P]),
-    "pb_tte_decode": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "pb_tte_decode": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "pb_tte_last_launches": (_I64, [_P]),
     "pb_tte_arena_bytes": (C.c_int, [_P, C.POINTER(_I64)]),
     "pb_tte_arena_ptr": (_P, [_P]),

@@ -2,9 +2,10 @@
 
 Every forward must know whether the device copy (folded + packed by ``*_finalize``) still matches the module's parameters.
 Walking ``state_dict()`` per call costs ~0.5 ms for the vocoder's 295 tensors - more than the launches of a small forward -
-so the tensor list is cached and only (data_ptr, version counter) of each tensor is compared per call (~60 us).  The cache is
-rebuilt whenever ANY module registers a parameter or buffer (a process-wide counter fed by torch's registration hooks:
-``remove_weight_norm``, ``load_state_dict(assign=True)``, manual re-registration); in-place updates bump the tensors' version
+so the tensor list is cached and only (data_ptr, version counter, shape) of each tensor is compared per call (~60 us).  The cached
+LIST is rebuilt whenever ANY module registers a parameter or buffer (a process-wide counter fed by torch's registration hooks:
+``remove_weight_norm``, ``load_state_dict(assign=True)``, manual re-registration) - the counter itself is not part of the
+comparison key, so unrelated registrations do not make an engine look stale; in-place updates bump the tensors' version
 counters and ``.to()`` / ``.cuda()`` change their data pointers, so both are seen by the per-call comparison."""
 from torch.nn.modules import module as _tm
 
@@ -39,5 +40,15 @@ class WeightStamp:
         return dict(zip(self._keys, self._tensors))
 
     def stamp(self):
+        """Comparison key of the module's weights AS THEY ARE NOW: names, storage, version counters and shapes.  The process-wide
+        registration counter only decides when the cached tensor list is rebuilt - it is not part of the key, so registering
+        parameters elsewhere in the process (a second model, an unrelated ``nn.Linear``) leaves this module's engine alone.
+        Edits through ``.data`` do not bump version counters: call ``invalidate()`` after them."""
         self._refresh()
-        return (self._seen,) + tuple((t.data_ptr(), t._version) for t in self._tensors)
+        return (self._epoch, self._keys) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in self._tensors)
+
+    _epoch = 0
+
+    def invalidate(self):
+        """Force the next forward to re-upload (after in-place edits torch cannot see, e.g. ``p.data.copy_()``)."""
+        self._epoch += 1

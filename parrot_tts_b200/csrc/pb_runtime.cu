@@ -61,6 +61,7 @@ int make_tmap_2d_f32(CUtensorMap* map, const float* base, int64_t cols, int64_t 
 int DevBuf::reserve(size_t nbytes) {
     if (nbytes <= bytes) return PB_OK;
     if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    ++epoch;
     // grow with slack so that slowly increasing shapes do not reallocate every call
     size_t want = nbytes + nbytes / 8;
     cudaError_t e = cudaMalloc(&ptr, want);

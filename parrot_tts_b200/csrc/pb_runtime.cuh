@@ -12,6 +12,7 @@ namespace pb {
 struct DevBuf {
     void* ptr = nullptr;
     size_t bytes = 0;
+    int64_t epoch = 0;          // bumped whenever the allocation moves: raw pointers captured earlier (CUDA graphs) are stale then
     int reserve(size_t nbytes);
     void release();
     template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }

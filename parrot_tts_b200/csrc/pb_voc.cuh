@@ -53,7 +53,7 @@ int launch_conv_post(const float* x, const float* w /*[Cin][K]*/, const float* b
 
 // unit/speaker embedding gather + concat + transpose: -> x0 [B, 2E (or E), pitch]
 int launch_voc_embed(const int64_t* code, const int64_t* spkr, const float* dict_w, const float* spkr_w,
-                     const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, int pitch, float* x0, cudaStream_t st);
+                     const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, int pitch, float* x0, int* err_flag /*or null*/, cudaStream_t st);
 
 // copy [B*C, L] (row stride src_pitch) -> (row stride dst_pitch), zero-filling columns >= valid
 int launch_repitch(const float* src, int64_t src_pitch, float* dst, int64_t dst_pitch, int64_t rows, int L,
@@ -68,10 +68,10 @@ int launch_pack_conv_weight(const float* src, int64_t s_co, int64_t s_ci, float*
 // ---- tensor-core path (activations split-bf16 channels-last [B][L][2C], see pb_tc.cuh) ----------------------------------
 // unit + speaker embedding -> x0 [B][T][2*(E or 2E)] split-bf16 (rows past the valid length are zero)
 int launch_voc_embed_split(const int64_t* code, const int64_t* spkr, const float* dict_w, const float* spkr_w,
-                           const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, __nv_bfloat16* x0, cudaStream_t st);
+                           const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, __nv_bfloat16* x0, int* err_flag /*or null*/, cudaStream_t st);
 // conv_post on a split-bf16 input that already carries the final leaky-relu: tanh(conv k7 + bias) -> wav f32 [B][L]
-int launch_conv_post_split(const __nv_bfloat16* x, const float* w /*[Cin][K]*/, const float* bias, float* wav,
-                           const int32_t* lens, int len_mul, int B, int Cin, int L, int K, cudaStream_t st);
+int launch_conv_post_split(const __nv_bfloat16* x, const float* w /*[Cin][K]*/, const float* bias, float* wav /*or null*/,
+                           int16_t* pcm /*or null*/, const int32_t* lens, int len_mul, int B, int Cin, int L, int K, cudaStream_t st);
 
 int launch_wav_to_pcm16(const float* wav, int64_t n, int16_t* pcm, cudaStream_t st);
 int launch_pcm16_peak_normalize(const int16_t* pcm, int B, int64_t n, int32_t* peak, float* out, cudaStream_t st);

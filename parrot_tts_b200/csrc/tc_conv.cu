@@ -21,55 +21,11 @@
 #include "pb_tc.cuh"
 #include "pb_umma.cuh"
 
-// EXPERIMENTAL build switch -DPB_TC_FAMILY (written in round 1 without GPU access, NOT yet run): a fourth template parameter VOC
-// instantiates the kernel for the vocoder's layer family - split-bf16 in and out, no tanh, no fp32 residual / output, no ablation -
-// so the per-item flag tests of the epilogue (a uniform branch per element pair in split2 / join2, the tanh / fp32 blocks) fold
-// away.  Without the switch the macros below expand to the plain parameter reads: the product's device code does not change.
-#ifdef PB_TC_FAMILY
-#define TC_KERNEL_TEMPLATE template <bool RES, bool ACC, bool CL, bool VOC>
-#define EP_FMT (VOC ? 0 : p.fmt)
-#define EP_ABL(x) (!VOC && (p.ablate & (x)))
-#define EP_TANH (!VOC && p.tanh_out)
-#define EP_RES_F32 (VOC ? static_cast<const float*>(nullptr) : p.res_f32)
-#define EP_OUT_F32 (VOC ? static_cast<float*>(nullptr) : p.out_f32)
-#define EP_HAS_OUT (VOC || p.out)
-#else
-#define TC_KERNEL_TEMPLATE template <bool RES, bool ACC, bool CL>
-#define EP_FMT p.fmt
-#define EP_ABL(x) (p.ablate & (x))
-#define EP_TANH p.tanh_out
-#define EP_RES_F32 p.res_f32
-#define EP_OUT_F32 p.out_f32
-#define EP_HAS_OUT p.out
-#endif
-
 namespace pb {
 
 namespace {
 
-#ifdef PB_TC_GROUPS4
-// EXPERIMENTAL build (-DPB_TC_GROUPS4; written in round 1 without GPU access, NOT yet run): a FOURTH epilogue warpgroup.  640 threads
-// leave 102 registers per thread at launch, which spilled when it was tried - here the service warpgroup hands
-// registers back (setmaxnreg.dec) and the epilogue warpgroups grow (setmaxnreg.inc).
-constexpr int TC_MAX_GROUPS = 4;
-#ifndef PB_TC_REGS_SERVICE
-#define PB_TC_REGS_SERVICE 56
-#endif
-#ifndef PB_TC_REGS_EPI
-#define PB_TC_REGS_EPI 112          // 128 x 56 + 512 x 112 = 64 512 of 65 536 registers; ptxas spills least at this split (40/112, 48/112,
-                                    // 56/104, 64/104, 72/96, 88/88 tried: 688 bytes of spill stores over the 16 instantiations here, 1 280+ elsewhere)
-#endif
-#define TC_STR2(x) #x
-#define TC_STR(x) TC_STR2(x)
-// The register hand-over must DOMINATE the code it governs (ptxas allocates per region) and all four warps of a warpgroup must
-// execute the same instruction: the service warpgroup shrinks at the top of its branch, the epilogue warpgroups grow at the top of theirs.
-#define TC_SERVICE_BEGIN if (warp < 4) { asm volatile("setmaxnreg.dec.sync.aligned.u32 " TC_STR(PB_TC_REGS_SERVICE) ";" ::: "memory");
-#define TC_EPILOGUE_BEGIN } else { asm volatile("setmaxnreg.inc.sync.aligned.u32 " TC_STR(PB_TC_REGS_EPI) ";" ::: "memory");
-#else
-#define TC_SERVICE_BEGIN
-#define TC_EPILOGUE_BEGIN else if (warp >= 4) {
 constexpr int TC_MAX_GROUPS = 3;
-#endif
 constexpr int TC_MAX_THREADS = 128 + 128 * TC_MAX_GROUPS;   // 4 service warps + up to 3 epilogue groups of 4 warps (128 registers per thread)
 constexpr int TC_M = 128;                 // time rows per tile (UMMA M, cta_group::1)
 constexpr int TC_MAX_STAGES = 8;
@@ -105,11 +61,9 @@ struct TcParams {
     int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
     int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads,
                   // 16 = skip the accumulator reads, 32 = skip the epilogue arithmetic
-#ifdef PB_TC_EPI_SPLIT
-    int epi_split;  // EXPERIMENTAL build (-DPB_TC_EPI_SPLIT; written in round 1 without GPU access, NOT yet run): every epilogue group works on
-                    // EVERY tile and takes the 16-column items grp, grp + n_groups, ... - a tile's epilogue latency drops from
-                    // (NT/16 items) to (NT/16 / n_groups) and n_groups is no longer capped by the number of accumulators
-#endif
+    int epi_split;  // column-split epilogue groups: every group works on EVERY tile and takes the 16-column items grp, grp + n_groups, ...
+                    // - a tile's epilogue latency drops from (NT/16 items) to (NT/16 / n_groups) and n_groups is no longer capped by the
+                    // number of accumulators (measured on B200, 8 x 1024 units: 8.08 -> 7.94 ms on the CTA-pair layers, slower on the others)
 };
 
 }  // namespace
@@ -268,7 +222,7 @@ __device__ __forceinline__ void mma_issuer(const TcParams& p, const MmaCtx& mc) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-TC_KERNEL_TEMPLATE
+template <bool RES, bool ACC, bool CL>
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap omap,
                const TcParams p) {
@@ -293,11 +247,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     const int cta0 = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int nctas = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int ROWS_PER_TILE = CL ? 2 * TC_M : TC_M;
-#ifdef PB_TC_EPI_SPLIT
     const bool EPI_SPLIT = p.epi_split != 0;        // column-split epilogue groups (see TcParams::epi_split)
-#else
-    constexpr bool EPI_SPLIT = false;
-#endif
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
@@ -333,7 +283,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     // phases live in uniform registers; only the asynchronous instructions themselves are issued by one elected lane.
     // (Measured: running the loops inside `if (lane == 0)` costs ~25 dependent R2UR/ELECT instructions per tcgen05.mma
     // and left the tensor pipe 57-80 % idle.)
-    TC_SERVICE_BEGIN
     if (warp == 0) {
         // =========================== producer ===========================
         if (p.res_blocks > 0) {
@@ -358,7 +307,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&empty_a[a_s], a_ph ^ 1);
                 if (elect_one()) {
-                    if (EP_ABL(8)) {
+                    if ((p.ablate & 8)) {
                         mbar_arrive(&full_a[a_s]);
                     } else if (CL) {
                         // both CTAs load their own 128 rows; both signal the LEADER's barrier, which expects both halves
@@ -422,7 +371,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             }
         }
     }
-    TC_EPILOGUE_BEGIN
+    else if (warp >= 4) {
         // =========================== epilogue ===========================
         // Work items are (tile, 16-column chunk) in order; the residual / running-sum rows of item k+1 are requested as soon
         // as item k has consumed its own, so their latency hides behind the rest of item k and the next accumulator read.
@@ -487,7 +436,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             }
         };
         auto request = [&](bool ok, size_t off, uint4 (&r)[4], uint4 (&a)[4]) {
-            if (!ok || EP_ABL(4)) return;
+            if (!ok || (p.ablate & 4)) return;
             if (RES) {
                 ld_global_nc_v8(p.res + off, r[0], r[1]);
                 ld_global_nc_v8(p.res + off + p.out_C, r[2], r[3]);
@@ -548,7 +497,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             float v[16];
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_cols + (uint32_t)n0;
-                if (EP_ABL(16)) {
+                if ((p.ablate & 16)) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 } else if (p.stack) tmem_ld16x2_sum(taddr, taddr + (uint32_t)p.NT, v);
@@ -561,7 +510,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     if (CL && rank != 0) mbar_arrive_remote(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
                 }
             }
-            if (cur.row_ok && !EP_ABL(32)) {
+            if (cur.row_ok && !(p.ablate & 32)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 bv = bv4[i];
@@ -573,7 +522,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     const uint32_t ll[8] = {R[2].x, R[2].y, R[2].z, R[2].w, R[3].x, R[3].y, R[3].z, R[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float2 r = join2(hh[i], ll[i], EP_FMT);
+                        const float2 r = join2(hh[i], ll[i], p.fmt);
                         float tx = r.x, ty = r.y;
                         mul2(tx, ty, p.res_unslope, p.res_unslope);
                         add2(v[2 * i], v[2 * i + 1], fminf(r.x, tx), fminf(r.y, ty));      // undo the stored leaky relu (1/slope >= 1)
@@ -584,7 +533,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     const uint32_t ll[8] = {A[2].x, A[2].y, A[2].z, A[2].w, A[3].x, A[3].y, A[3].z, A[3].w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float2 r = join2(hh[i], ll[i], EP_FMT);
+                        const float2 r = join2(hh[i], ll[i], p.fmt);
                         add2(v[2 * i], v[2 * i + 1], r.x, r.y);
                     }
                 }
@@ -594,9 +543,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             // have the rest of this item plus the next accumulator read to arrive
             request(nxt.ok && nxt.row_ok, offn, R, A);
             uint32_t hw[8], lw[8];
-            if (cur.row_ok && !EP_ABL(32)) {
-                if (EP_RES_F32) {      // fp32 residual stream [B][Lout][out_C] (TTE)
-                    const float4* rp = reinterpret_cast<const float4*>(EP_RES_F32 + (off - (size_t)co) / 2 + co);
+            if (cur.row_ok && !(p.ablate & 32)) {
+                if (p.res_f32) {      // fp32 residual stream [B][Lout][out_C] (TTE)
+                    const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + (off - (size_t)co) / 2 + co);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 rv = __ldg(rp + i);
@@ -612,13 +561,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     v[2 * i] = fmaxf(v[2 * i], tx);         // leaky relu for slope in [0,1]; slope 1 = identity
                     v[2 * i + 1] = fmaxf(v[2 * i + 1], ty);
                 }
-                if (EP_TANH) {
+                if (p.tanh_out) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
                 }
-                if (EP_HAS_OUT && !EP_ABL(2)) {
+                if (p.out && !(p.ablate & 2)) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], EP_FMT, hw[i], lw[i]);
+                    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], p.fmt, hw[i], lw[i]);
                     if (!p.tma_out) {
                         __nv_bfloat16* oh = p.out + off;
                         __nv_bfloat16* ol = oh + p.out_C;
@@ -626,14 +575,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                         st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
                     }
                 }
-                if (EP_OUT_F32) {
-                    float* of = EP_OUT_F32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch
+                if (p.out_f32) {
+                    float* of = p.out_f32 + (off - (size_t)co) / 2 + co;     // [B][Lout][out_C]: half the split row pitch
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<float4*>(of + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
-            if (p.tma_out && !EP_ABL(2)) {
+            if (p.tma_out && !(p.ablate & 2)) {
                 // Row-per-thread 32-byte global stores cost ~50 L1 wavefronts per instruction (every lane its own line); instead the
                 // warp parks its [32 rows x 16 ch] hi and lo tiles in shared memory (32B-swizzled: conflict-free 16-byte stores) and
                 // one lane hands them to the TMA unit.  Rows past the end of the sequence are clipped by the tensor map.
@@ -898,15 +847,12 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     // several warpgroups take alternate tiles so that those chains overlap.
     static const int env_groups = getenv("PB_TC_GROUPS") ? atoi(getenv("PB_TC_GROUPS")) : 0;
     p.n_groups = a.n_groups > 0 ? a.n_groups : (env_groups > 0 ? env_groups : (ctas_per_sm == 2 ? 1 : TC_MAX_GROUPS));
-#ifdef PB_TC_EPI_SPLIT
-    // EXPERIMENTAL (see TcParams::epi_split).  PB_TC_EPI_SPLIT: 0 = off, 1 = the CTA-pair layers (default of this build), 2 = every one-CTA-per-SM layer
+    // PB_TC_EPI_SPLIT (dev switch): 0 = off, 1 = the CTA-pair layers (default), 2 = every one-CTA-per-SM layer
     static const int epi_split_env = getenv("PB_TC_EPI_SPLIT") ? atoi(getenv("PB_TC_EPI_SPLIT")) : 1;
     p.epi_split = (ctas_per_sm == 1 && (epi_split_env >= 2 || (epi_split_env == 1 && p.cluster))) ? 1 : 0;
     if (p.epi_split) {
         if (p.n_groups > NT / 16) p.n_groups = NT / 16;       // every group needs an item in every tile
-    } else
-#endif
-    if (p.n_groups > p.n_acc) p.n_groups = p.n_acc;
+    } else if (p.n_groups > p.n_acc) p.n_groups = p.n_acc;
     if (p.n_groups > TC_MAX_GROUPS) p.n_groups = TC_MAX_GROUPS;
     const int threads = 128 + 128 * p.n_groups;
     int cols = 32;
@@ -943,14 +889,8 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         int dev = 0;
         PB_CUDA(cudaGetDevice(&dev));
         PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-#ifdef PB_TC_FAMILY
-#define TC_SET_ATTR(R, A, C) \
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<R, A, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT)); \
-        PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<R, A, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT))
-#else
 #define TC_SET_ATTR(R, A, C) \
         PB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<R, A, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT))
-#endif
         TC_SET_ATTR(false, false, false); TC_SET_ATTR(true, false, false); TC_SET_ATTR(true, true, false); TC_SET_ATTR(false, true, false);
         TC_SET_ATTR(false, false, true); TC_SET_ATTR(true, false, true); TC_SET_ATTR(true, true, true); TC_SET_ATTR(false, true, true);
 #undef TC_SET_ATTR
@@ -981,15 +921,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-#ifdef PB_TC_FAMILY
-    // the vocoder's layer family (see the top of the file): everything the VOC instantiation assumes is checked here
-    const bool voc = a.fmt == 0 && !a.tanh_out && a.res_f32 == nullptr && a.out_f32 == nullptr && a.out != nullptr && p.ablate == 0;
-#define TC_LAUNCH(R, A, C) \
-    do { if (voc) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<R, A, C, true>, xmap, wmap, omap, p)); \
-         else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<R, A, C, false>, xmap, wmap, omap, p)); } while (0)
-#else
 #define TC_LAUNCH(R, A, C) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<R, A, C>, xmap, wmap, omap, p))
-#endif
     if (p.cluster) {
         if (a.res && a.accin) TC_LAUNCH(true, true, true);
         else if (a.res) TC_LAUNCH(true, false, true);

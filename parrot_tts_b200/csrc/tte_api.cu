@@ -59,6 +59,9 @@ extern "C" int pb_tte_create(const pb_tte_cfg* cfg, pb_tte** out) {
     PB_REQUIRE(cfg->gemm_mode == 0 || cfg->gemm_mode == 1, PB_ERR_INVALID, "pb_tte_create: gemm_mode=%d (0 = fp32 SIMT, 1 = tcgen05 split-fp16)", cfg->gemm_mode);
     if (cfg->gemm_mode == 1) {
         PB_REQUIRE(cfg->fold_projections, PB_ERR_INVALID, "pb_tte_create: gemm_mode 1 needs fold_projections = 1 (the unfolded reference mode runs on the fp32 SIMT path)");
+        PB_REQUIRE(cfg->d_model / cfg->n_head == 128, PB_ERR_INVALID,
+                   "pb_tte_create: gemm_mode 1 needs a head width of 128 (d_model %d / n_head %d = %d): the fused attention kernel is built for it; use gemm_mode 0",
+                   cfg->d_model, cfg->n_head, cfg->d_model / cfg->n_head);
         PB_REQUIRE(cfg->conv_n_filter % 256 == 0 && cfg->conv_k2 == 1 && (cfg->conv_k1 - 1) <= 128, PB_ERR_INVALID,
                    "pb_tte_create: gemm_mode 1 needs conv_n_filter %% 256 == 0 and conv_kernel_sizes [k, 1]");
     }
@@ -449,7 +452,8 @@ extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* sr
     return PB_OK;
 }
 
-extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, float* logits, int64_t* ids, uint8_t* tgt_mask, void* stream) {
+extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, const uint8_t* tgt_mask_in, float* logits, int64_t* ids,
+                             uint8_t* tgt_mask, void* stream) {
     PB_REQUIRE(h, PB_ERR_INVALID, "pb_tte_decode: null handle");
     PB_REQUIRE(h->finalized, PB_ERR_STATE, "pb_tte_decode: weights not finalized");
     PB_REQUIRE(h->enc_T >= 0 && B == h->enc_B && S == h->enc_S && T == h->enc_T, PB_ERR_STATE,
@@ -481,6 +485,9 @@ extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, float* 
     }
     uint8_t* mk = tgt_mask ? tgt_mask : mask;
     PB_TRY(launch_length_regulate(h->enc_out, h->cum, h->P("pos_emb.pe") + (size_t)T * D, B, S, D, T, xa, mk, st));
+    // a caller-supplied target mask (teacher-forced path) is returned unchanged by the reference's length_regulator and is the
+    // decoder's key padding mask (parrot.py:104,107; duration.py:22-24): it replaces the generated t <= len mask
+    if (tgt_mask_in && tgt_mask_in != mk) PB_CUDA(cudaMemcpyAsync(mk, tgt_mask_in, (size_t)M, cudaMemcpyDeviceToDevice, st));
     float* cur = xa; float* nxt = xb;
     for (int i = 0; i < c.n_dec_layer; ++i) {
         PB_TRY(run_fft_block(h, layer_prefix(1, i), cur, mk, B, T, w, nxt, st));

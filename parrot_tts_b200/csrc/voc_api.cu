@@ -34,6 +34,7 @@ struct pb_voc {
     std::vector<ConvSlot> rb1, rb2;   // index ((i * num_kernels + j) * num_dilations + m)
     size_t dict_off = 0, spkr_off = 0;
     DevBuf work;
+    int* err_flag = nullptr;      // device: 1 = unit id, 2 = speaker id outside its embedding table (set by the embedding kernels)
     int64_t last_launches = 0;
     // optional section timing (bench.py roofline): events on the caller's stream at section boundaries
     bool timing = false;
@@ -78,10 +79,15 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
     }
     pb_voc* h = new pb_voc();
     h->cfg = *cfg;
-    PB_CUDA(cudaGetDevice(&h->device));
+    if (cudaGetDevice(&h->device) != cudaSuccess || cudaMalloc(&h->err_flag, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(h->err_flag, 0, 4 * sizeof(int)) != cudaSuccess) {
+        if (h->err_flag) cudaFree(h->err_flag);
+        delete h;
+        return cuda_fail(cudaGetLastError(), "pb_voc_create: device / error flag", __FILE__, __LINE__);
+    }
     const int c0 = cfg->upsample_initial_channel;
     int co = conv_co_tile(c0);
-    if (!co || cfg->model_in_dim % 8) { delete h; set_error("pb_voc_create: unsupported channel counts"); return PB_ERR_INVALID; }
+    if (!co || cfg->model_in_dim % 8) { cudaFree(h->err_flag); delete h; set_error("pb_voc_create: unsupported channel counts"); return PB_ERR_INVALID; }
     plan_slot(h, h->conv_pre, "conv_pre", cfg->model_in_dim, c0, 7, 1, false, co);
     h->hop = 1;
     for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -89,12 +95,12 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
         const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
         h->hop *= u;
         const int ct = convtr_co_tile(cout, u);
-        if (!ct || (k - u) % 2 || cin % 8) { delete h; set_error("pb_voc_create: unsupported upsample layer %d", i); return PB_ERR_INVALID; }
+        if (!ct || (k - u) % 2 || cin % 8) { cudaFree(h->err_flag); delete h; set_error("pb_voc_create: unsupported upsample layer %d", i); return PB_ERR_INVALID; }
         ConvSlot s;
         plan_slot(h, s, "ups." + std::to_string(i), cin, cout, k, u, true, ct);   // D field = stride of the transposed conv
         h->ups.push_back(s);
         const int cr = conv_co_tile(cout);
-        if (!cr || cout % 8) { delete h; set_error("pb_voc_create: unsupported resblock width %d", cout); return PB_ERR_INVALID; }
+        if (!cr || cout % 8) { cudaFree(h->err_flag); delete h; set_error("pb_voc_create: unsupported resblock width %d", cout); return PB_ERR_INVALID; }
         for (int j = 0; j < cfg->num_kernels; ++j)
             for (int m = 0; m < cfg->num_dilations; ++m) {
                 const std::string p = "resblocks." + std::to_string(i * cfg->num_kernels + j);
@@ -116,7 +122,7 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
         }
     }
     int st = h->arena.reserve(h->arena_bytes);
-    if (st != PB_OK) { delete h; return st; }
+    if (st != PB_OK) { cudaFree(h->err_flag); delete h; return st; }
     *out = h;
     return PB_OK;
 }
@@ -134,7 +140,22 @@ extern "C" void pb_voc_destroy(pb_voc* h) {
     }
     h->arena.release();
     h->work.release();
+    if (h->err_flag) cudaFree(h->err_flag);
     delete h;
+}
+
+// nn.Embedding raises IndexError for an id outside its table (reference utils/vocoder/models.py:155-156); the embedding kernels
+// clamp (the launch must stay in bounds) and flag.  Synchronises `stream`, reports and clears the flag.
+extern "C" int pb_voc_check_ids(pb_voc* h, void* stream) {
+    PB_REQUIRE(h, PB_ERR_INVALID, "pb_voc_check_ids: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    int flag = 0;
+    PB_CUDA(cudaMemcpyAsync(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (flag == 0) return PB_OK;
+    PB_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), st));
+    set_error(flag == 1 ? "index out of range in self (unit id outside the dictionary)" : "index out of range in self (speaker id)");
+    return PB_ERR_INDEX;
 }
 
 extern "C" int pb_voc_set_weight(pb_voc* h, const char* key, const void* data, const int64_t* shape, int32_t ndim, int32_t dtype) {
@@ -145,7 +166,10 @@ extern "C" int pb_voc_set_weight(pb_voc* h, const char* key, const void* data, c
     t.dtype = dtype;
     const size_t nbytes = (size_t)t.numel() * sizeof(float);
     PB_CUDA(cudaMalloc(&t.ptr, nbytes ? nbytes : 4));
-    PB_CUDA(cudaMemcpy(t.ptr, data, nbytes, cudaMemcpyDefault));
+    {
+        const cudaError_t e = cudaMemcpy(t.ptr, data, nbytes, cudaMemcpyDefault);
+        if (e != cudaSuccess) { cudaFree(t.ptr); return cuda_fail(e, "cudaMemcpy(staged weight)", __FILE__, __LINE__); }
+    }
     auto it = h->staged.find(key);
     if (it != h->staged.end()) { cudaFree(it->second.ptr); h->staged.erase(it); }
     h->staged[key] = t;
@@ -243,6 +267,7 @@ extern "C" int pb_voc_mark_finalized(pb_voc* h) {
 }
 
 extern "C" int64_t pb_voc_last_launches(const pb_voc* h) { return h ? h->last_launches : 0; }
+extern "C" int64_t pb_voc_memory_epoch(const pb_voc* h) { return h ? h->arena.epoch + h->work.epoch : -1; }
 
 extern "C" int pb_voc_section_count(const pb_voc* h) { return h ? 2 + 2 * h->cfg.num_upsamples : 0; }
 
@@ -270,7 +295,7 @@ extern "C" int pb_voc_section_ms(pb_voc* h, float* ms_host, int32_t n) {
 // Storage convention: a tensor that feeds a convolution is stored with the leaky-relu that precedes that convolution in
 // the reference already applied (slope 0.1, or 0.01 before conv_post); the residual read undoes it (x = a < 0 ? a/slope : a).
 static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
-                          int32_t B, int32_t T, float* wav, cudaStream_t st) {
+                          int32_t B, int32_t T, float* wav, int16_t* pcm, cudaStream_t st) {
     const pb_voc_cfg& c = h->cfg;
     const int64_t launches0 = g_launch_count;
     const int c0 = c.upsample_initial_channel;
@@ -287,7 +312,7 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
     }
     // PB_VOC_CHAINS=1: chain j (ResBlock kernel size j) of every stage runs on its own stream with its own XT / XA / XB buffers
     // (the last chain stays on the caller's stream); the running sum keeps its order k3 -> k7 -> k11, so results are bit-identical.
-    // Written in round 1 after the GPU budget was spent: NOT yet run on a GPU, hence off unless asked for.
+    // Measured on B200 (profiles/r01_ab_chains.txt): bit-identical, 8.24 vs 8.30 ms at 8 x 1024 units - no gain at batch size, off by default.
     static const bool chains_env = getenv("PB_VOC_CHAINS") != nullptr && atoi(getenv("PB_VOC_CHAINS")) != 0;
     const bool chains = chains_env && c.num_kernels > 1 && c.num_kernels <= PB_VOC_MAX_RESK;
     constexpr int MAX_SLOTS = 4 + 3 * PB_VOC_MAX_RESK;
@@ -317,7 +342,7 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
     PB_MARK();
     if (code) {
         PB_TRY(launch_voc_embed_split(code, spkr, h->A(h->dict_off), c.num_speakers > 0 ? h->A(h->spkr_off) : nullptr, lens, B, T,
-                                      c.embedding_dim, c.num_embeddings, c.num_speakers, x0, st));
+                                      c.embedding_dim, c.num_embeddings, c.num_speakers, x0, h->err_flag, st));
     } else {
         PB_TRY(launch_f32_to_split(x, T, x0, B, c.model_in_dim, T, 1.f, st));
     }
@@ -428,7 +453,7 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
         PB_MARK();
         cur_in = Y; in_slot = y_slot; L = Lo;
     }
-    PB_TRY(launch_conv_post_split(cur_in, h->A(h->conv_post.w_off), h->A(h->conv_post.b_off), wav, lens, mul, B,
+    PB_TRY(launch_conv_post_split(cur_in, h->A(h->conv_post.w_off), h->A(h->conv_post.b_off), wav, pcm, lens, mul, B,
                                   h->conv_post.Cin, (int)L, 7, st));
     PB_MARK();
 #undef PB_MARK
@@ -437,9 +462,26 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
     return PB_OK;
 }
 
+static int voc_forward_any(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
+                           int32_t B, int32_t T, float* wav, int16_t* pcm, void* stream);
+
 extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
                               int32_t B, int32_t T, float* wav, void* stream) {
     PB_REQUIRE(h && wav, PB_ERR_INVALID, "pb_voc_forward: null argument");
+    return voc_forward_any(h, x, code, spkr, lens, B, T, wav, nullptr, stream);
+}
+
+// forward + generate() tail: int16 PCM written by conv_post's epilogue (utils/vocoder/inference.py:65-74); wav optional
+extern "C" int pb_voc_forward_pcm16(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
+                                    int32_t B, int32_t T, float* wav, int16_t* pcm, void* stream) {
+    PB_REQUIRE(h && pcm, PB_ERR_INVALID, "pb_voc_forward_pcm16: null argument");
+    PB_REQUIRE(h->cfg.conv_mode != 0 || wav != nullptr, PB_ERR_INVALID,
+               "pb_voc_forward_pcm16: conv_mode 0 (fp32 SIMT) casts from the f32 waveform: pass wav as well");
+    return voc_forward_any(h, x, code, spkr, lens, B, T, wav, pcm, stream);
+}
+
+static int voc_forward_any(pb_voc* h, const float* x, const int64_t* code, const int64_t* spkr, const int32_t* lens,
+                           int32_t B, int32_t T, float* wav, int16_t* pcm, void* stream) {
     PB_REQUIRE(h->finalized, PB_ERR_STATE, "pb_voc_forward: weights not finalized");
     PB_REQUIRE((x != nullptr) != (code != nullptr), PB_ERR_INVALID, "pb_voc_forward: give exactly one of x / code");
     PB_REQUIRE(B > 0 && T > 0 && B <= 65535, PB_ERR_INVALID, "pb_voc_forward: bad shape B=%d T=%d", B, T);
@@ -451,7 +493,7 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
         PB_REQUIRE(in_dim == c.model_in_dim, PB_ERR_INVALID, "pb_voc_forward: embedding dims (%d) != model_in_dim (%d)", in_dim, c.model_in_dim);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (c.conv_mode != 0) return voc_forward_tc(h, x, code, spkr, lens, B, T, wav, st);
+    if (c.conv_mode != 0) return voc_forward_tc(h, x, code, spkr, lens, B, T, wav, pcm, st);
     const int64_t launches0 = g_launch_count;
     const int c0 = c.upsample_initial_channel;
     const int P0 = (int)round_up(T, 4);
@@ -484,7 +526,7 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
     // ---- input features [B, model_in_dim, P0]
     if (code) {
         PB_TRY(launch_voc_embed(code, spkr, h->A(h->dict_off), c.num_speakers > 0 ? h->A(h->spkr_off) : nullptr, lens, B, T,
-                                c.embedding_dim, c.num_embeddings, c.num_speakers, P0, x0, st));
+                                c.embedding_dim, c.num_embeddings, c.num_speakers, P0, x0, h->err_flag, st));
     } else {
         PB_TRY(launch_repitch(x, T, x0, P0, (int64_t)B * c.model_in_dim, T, lens, 1, c.model_in_dim, st));
     }
@@ -563,6 +605,7 @@ extern "C" int pb_voc_forward(pb_voc* h, const float* x, const int64_t* code, co
     }
     PB_TRY(launch_conv_post(cur_in, h->A(h->conv_post.w_off), h->A(h->conv_post.b_off), wav, lens, mul, B,
                             h->conv_post.Cin, (int)L, pitch_in, L, 7, st));
+    if (pcm) PB_TRY(launch_wav_to_pcm16(wav, (int64_t)B * L, pcm, st));      // fp32 SIMT mode: the cast is its own launch
     PB_MARK();
 #undef PB_MARK
     h->ev_valid = h->timing;

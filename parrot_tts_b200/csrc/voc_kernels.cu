@@ -527,7 +527,7 @@ int launch_conv_post(const float* x, const float* w, const float* bias, float* w
 __global__ void __launch_bounds__(256)
 voc_embed_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ spkr, const float* __restrict__ dict_w,
                  const float* __restrict__ spkr_w, const int32_t* __restrict__ lens, int T, int E, int n_codes, int n_spk,
-                 int pitch, int C, float* __restrict__ x0) {
+                 int pitch, int C, float* __restrict__ x0, int* __restrict__ err_flag) {
     // block: 32 time steps x all channels; tile transposed through shared memory
     extern __shared__ float tile[];  // [32][E + 1]
     const int b = blockIdx.y, t0 = blockIdx.x * 32;
@@ -536,6 +536,7 @@ voc_embed_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ s
     for (int tt = ty; tt < 32; tt += 8) {
         const int t = t0 + tt;
         long long id = (t < T) ? code[(size_t)b * T + t] : 0;
+        if (err_flag && tx == 0 && t < valid && (id < 0 || id >= n_codes)) *err_flag = 1;      // see voc_embed_split_kernel
         id = id < 0 ? 0 : (id >= n_codes ? n_codes - 1 : id);
         for (int c = tx; c < E; c += 32) tile[tt * (E + 1) + c] = (t < valid) ? dict_w[(size_t)id * E + c] : 0.f;
     }
@@ -546,6 +547,7 @@ voc_embed_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ s
         for (int c = ty; c < E; c += 8) xb[(size_t)c * pitch + t] = (t < T) ? tile[tx * (E + 1) + c] : 0.f;
         if (spkr_w) {
             long long s = spkr[b];
+            if (err_flag && threadIdx.x == 0 && blockIdx.x == 0 && valid > 0 && (s < 0 || s >= n_spk)) atomicMax(err_flag, 2);
             s = s < 0 ? 0 : (s >= n_spk ? n_spk - 1 : s);
             for (int c = ty; c < E; c += 8) xb[(size_t)(E + c) * pitch + t] = (t < valid) ? spkr_w[(size_t)s * E + c] : 0.f;
         }
@@ -553,10 +555,10 @@ voc_embed_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ s
 }
 
 int launch_voc_embed(const int64_t* code, const int64_t* spkr, const float* dict_w, const float* spkr_w, const int32_t* lens,
-                     int B, int T, int E, int n_codes, int n_spk, int pitch, float* x0, cudaStream_t st) {
+                     int B, int T, int E, int n_codes, int n_spk, int pitch, float* x0, int* err_flag, cudaStream_t st) {
     const int C = spkr_w ? 2 * E : E;
     dim3 grid((unsigned)ceil_div(pitch, 32), (unsigned)B);
-    voc_embed_kernel<<<grid, 256, 32 * (E + 1) * sizeof(float), st>>>(code, spkr, dict_w, spkr_w, lens, T, E, n_codes, n_spk, pitch, C, x0);
+    voc_embed_kernel<<<grid, 256, 32 * (E + 1) * sizeof(float), st>>>(code, spkr, dict_w, spkr_w, lens, T, E, n_codes, n_spk, pitch, C, x0, err_flag);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -660,7 +662,7 @@ int launch_pack_conv_weight(const float* src, int64_t s_co, int64_t s_ci, float*
 __global__ void __launch_bounds__(256)
 voc_embed_split_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ spkr, const float* __restrict__ dict_w,
                        const float* __restrict__ spkr_w, const int32_t* __restrict__ lens, int T, int E, int n_codes, int n_spk,
-                       int64_t rows, __nv_bfloat16* __restrict__ x0) {
+                       int64_t rows, __nv_bfloat16* __restrict__ x0, int* __restrict__ err_flag) {
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -668,8 +670,14 @@ voc_embed_split_kernel(const int64_t* __restrict__ code, const int64_t* __restri
     const int C = spkr_w ? 2 * E : E;
     const int valid = lens ? min(lens[b], T) : T;
     long long id = code[row];
-    id = id < 0 ? 0 : (id >= n_codes ? n_codes - 1 : id);
     long long sp = spkr_w ? spkr[b] : 0;
+    // nn.Embedding raises on an id outside the table (models.py:155-156): flag it for pb_voc_check_ids (live positions only - what
+    // lies past an item's length is padding and never read); the gather itself clamps so that the launch stays in bounds
+    if (err_flag && lane == 0 && t < valid) {
+        if (id < 0 || id >= n_codes) *err_flag = 1;
+        else if (sp < 0 || sp >= n_spk) *err_flag = 2;
+    }
+    id = id < 0 ? 0 : (id >= n_codes ? n_codes - 1 : id);
     sp = sp < 0 ? 0 : (sp >= n_spk ? n_spk - 1 : sp);
     __nv_bfloat16* out = x0 + row * 2 * C;
     for (int c = lane; c < C; c += 32) {
@@ -682,29 +690,34 @@ voc_embed_split_kernel(const int64_t* __restrict__ code, const int64_t* __restri
 }
 
 int launch_voc_embed_split(const int64_t* code, const int64_t* spkr, const float* dict_w, const float* spkr_w,
-                           const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, __nv_bfloat16* x0, cudaStream_t st) {
+                           const int32_t* lens, int B, int T, int E, int n_codes, int n_spk, __nv_bfloat16* x0, int* err_flag,
+                           cudaStream_t st) {
     const int64_t rows = (int64_t)B * T;
-    voc_embed_split_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(code, spkr, dict_w, spkr_w, lens, T, E, n_codes, n_spk, rows, x0);
+    voc_embed_split_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(code, spkr, dict_w, spkr_w, lens, T, E, n_codes, n_spk, rows, x0,
+                                                                         err_flag);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
 
-// conv_post + tanh on split-bf16 rows: a block stages POST_T + K - 1 input rows in shared memory as fp32 [channel][position]
-// (hi + lo joined once), then every thread produces POST_T / 256 samples from conflict-free shared-memory reads.
+// conv_post + tanh on split-bf16 rows (reference utils/vocoder/models.py:107-109): a block stages POST_T + K - 1 input rows in shared
+// memory as fp32 [channel][position] (hi + lo joined once); a thread owns 4 consecutive samples: 10 inputs (two 128-bit loads and a
+// 64-bit one) and the 7 weights of a channel serve 28 FMAs (the first version issued 2 shared-memory loads per FMA: 91 us per
+// 8 x 1024 units against a 27 us HBM floor).  The FMA order of one sample is channel outer, tap inner.
+// Outputs: the f32 waveform and / or - the generate() tail fused in (utils/vocoder/inference.py:71-73) - int16 PCM
+// (x 32768, truncation toward zero, two's-complement wrap: the same expression as wav_to_pcm16_kernel on the same float).
 constexpr int POST_T = 512;
+__device__ __forceinline__ int16_t pcm16_of(float v) {
+    const long long q = (long long)(v * 32768.0f);      // trunc toward zero
+    return (int16_t)(uint16_t)(q & 0xffff);
+}
 template <int CIN, int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(POST_T / 4)
 conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                       float* __restrict__ wav, const int32_t* __restrict__ lens, int len_mul, int L) {
+                       float* __restrict__ wav, int16_t* __restrict__ pcm, const int32_t* __restrict__ lens, int len_mul, int L) {
     constexpr int ROWS = POST_T + K - 1;
-#ifdef PB_POST_TILE4
     constexpr int PITCH = (ROWS + 3 + 3) / 4 * 4;     // rows o .. o + 9 of a 4-sample tile stay inside the pitch; multiple of 4 floats
     __shared__ __align__(16) float xs[CIN * PITCH];
-#else
-    constexpr int PITCH = ROWS + 1;
-    __shared__ float xs[CIN * PITCH];
-#endif
     __shared__ float ws[CIN * K];
     for (int i = threadIdx.x; i < CIN * K; i += blockDim.x) ws[i] = w[i];
     const int b = blockIdx.y;
@@ -732,11 +745,6 @@ conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
     }
     __syncthreads();
     const float bv = bias[0];
-#ifdef PB_POST_TILE4
-    // EXPERIMENTAL build (-DPB_POST_TILE4; written in round 1 without GPU access, NOT yet run): the loop below issues 2 shared-memory
-    // loads per FMA (91 us per 8 x 1024 units against a 27 us HBM floor, profiles/r01_model_vs_measured.txt).  Here a thread owns 4
-    // consecutive samples: 10 inputs (two 128-bit loads and a 64-bit one) and the 7 weights of a channel serve 28 FMAs.  The order of
-    // the FMAs of one sample is unchanged (channel outer, tap inner), so the waveform is bit-identical.
     static_assert(POST_T % 4 == 0 && PITCH % 4 == 0 && K <= 7, "4-sample tiles read xs[o .. o + 9] with aligned vector loads");
     for (int o = 4 * threadIdx.x; o < POST_T; o += 4 * blockDim.x) {
         if (t0 + o >= L) break;
@@ -754,39 +762,35 @@ conv_post_split_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
                 for (int q = 0; q < 4; ++q) acc[q] = fmaf(wj, in[q + j], acc[q]);
             }
         }
+        float y[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int t = t0 + o + q;
-            if (t < L) wav[(size_t)b * L + t] = t < valid ? tanhf(acc[q] + bv) : 0.f;
+        for (int q = 0; q < 4; ++q) y[q] = t0 + o + q < valid ? tanhf(acc[q] + bv) : 0.f;
+        const size_t at = (size_t)b * L + t0 + o;
+        if (t0 + o + 3 < L && (L & 3) == 0) {         // whole tile inside the row: one 128-bit (f32) / 64-bit (int16) store
+            if (wav) *reinterpret_cast<float4*>(wav + at) = make_float4(y[0], y[1], y[2], y[3]);
+            if (pcm) {
+                const uint32_t lo = (uint32_t)(uint16_t)pcm16_of(y[0]) | ((uint32_t)(uint16_t)pcm16_of(y[1]) << 16);
+                const uint32_t hi = (uint32_t)(uint16_t)pcm16_of(y[2]) | ((uint32_t)(uint16_t)pcm16_of(y[3]) << 16);
+                *reinterpret_cast<uint2*>(pcm + at) = make_uint2(lo, hi);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (t0 + o + q < L) {
+                    if (wav) wav[at + q] = y[q];
+                    if (pcm) pcm[at + q] = pcm16_of(y[q]);
+                }
+            }
         }
     }
-#else
-    for (int o = threadIdx.x; o < POST_T; o += blockDim.x) {
-        const int t = t0 + o;
-        if (t >= L) break;
-        float acc = 0.f;
-        if (t < valid) {
-#pragma unroll
-            for (int c = 0; c < CIN; ++c)
-#pragma unroll
-                for (int j = 0; j < K; ++j) acc = fmaf(ws[c * K + j], xs[c * PITCH + o + j], acc);
-            acc = tanhf(acc + bv);
-        }
-        wav[(size_t)b * L + t] = acc;
-    }
-#endif
 }
 
-int launch_conv_post_split(const __nv_bfloat16* x, const float* w, const float* bias, float* wav, const int32_t* lens, int len_mul,
-                           int B, int Cin, int L, int K, cudaStream_t st) {
+int launch_conv_post_split(const __nv_bfloat16* x, const float* w, const float* bias, float* wav, int16_t* pcm, const int32_t* lens,
+                           int len_mul, int B, int Cin, int L, int K, cudaStream_t st) {
     PB_REQUIRE(K == 7, PB_ERR_INVALID, "conv_post: kernel size %d unsupported (7 expected)", K);
+    PB_REQUIRE(wav || pcm, PB_ERR_INVALID, "conv_post: no output");
     dim3 grid((unsigned)ceil_div(L, POST_T), (unsigned)B);
-#ifdef PB_POST_TILE4
-    constexpr int POST_THREADS = POST_T / 4;      // one 4-sample tile per thread
-#else
-    constexpr int POST_THREADS = 256;
-#endif
-    if (Cin == 16) conv_post_split_kernel<16, 7><<<grid, POST_THREADS, 0, st>>>(x, w, bias, wav, lens, len_mul, L);
+    if (Cin == 16) conv_post_split_kernel<16, 7><<<grid, POST_T / 4, 0, st>>>(x, w, bias, wav, pcm, lens, len_mul, L);
     else { set_error("conv_post: Cin=%d unsupported on the tensor-core path (16 expected)", Cin); return PB_ERR_INVALID; }
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
@@ -796,9 +800,7 @@ int launch_conv_post_split(const __nv_bfloat16* x, const float* w, const float* 
 // generate() tail: (wav * 32768) -> int16 with C-cast semantics (truncate toward zero, wrap modulo 2^16)
 __global__ void wav_to_pcm16_kernel(const float* __restrict__ wav, int64_t n, int16_t* __restrict__ pcm) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float s = wav[i] * 32768.0f;
-        const long long q = (long long)s;  // trunc toward zero
-        pcm[i] = (int16_t)(uint16_t)(q & 0xffff);
+        pcm[i] = pcm16_of(wav[i]);
     }
 }
 

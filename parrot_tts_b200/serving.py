@@ -47,6 +47,7 @@ class BatchSynthesizer:
         self.chunk_units = int(chunk_units)
         self.halo_units = int(halo_units)
         self.last_plan = None
+        self.last_launches = 0        # kernels of the library launched by the last call (vocoder forwards + PCM casts)
 
     def _device(self):
         return next(self.generator.parameters()).device
@@ -62,18 +63,21 @@ class BatchSynthesizer:
         if dev.type != "cuda":
             raise RuntimeError("BatchSynthesizer needs a generator on a CUDA device (there is no CPU path)")
         hop = self.generator.hop
-        codes = [torch.as_tensor(c, dtype=torch.long).reshape(-1) for c in codes]
+        codes = [c.reshape(-1) if torch.is_tensor(c) and c.is_cuda else torch.as_tensor(c, dtype=torch.long).reshape(-1) for c in codes]
         lengths = [int(c.numel()) for c in codes]
+        on_device = bool(codes) and all(c.is_cuda for c in codes)      # unit ids handed over on the device (Parrot.infer_device)
         batches, long_form, empty = plan_batches(lengths, self.max_batch, self.max_pad_ratio, self.long_form_units, indices)
         self.last_plan = {"batches": batches, "long_form": long_form, "empty": empty,
                           "units": sum(lengths[i] for b in batches for i in b),
                           "padded_units": sum(len(b) * lengths[b[0]] for b in batches)}
         out = [None] * len(codes)
+        self.last_launches = 0
 
         def finish(wav):                               # f32 [n] on the device -> requested format
             if not pcm16:
                 return wav
             pcm = ops.wav_to_pcm16(wav.contiguous())
+            self.last_launches += 1 if wav.numel() else 0
             return ops.peak_normalize(pcm) if normalize else pcm
 
         def spk(i):
@@ -81,23 +85,92 @@ class BatchSynthesizer:
 
         for b in batches:
             Lmax = lengths[b[0]]
-            host = torch.zeros(len(b), Lmax, dtype=torch.long).pin_memory()
-            for r, i in enumerate(b):
-                host[r, :lengths[i]] = codes[i]
-            kw = {"code": host.to(dev, non_blocking=True),
+            if on_device:                              # no host round trip of the ids
+                batch_codes = torch.zeros(len(b), Lmax, dtype=torch.long, device=dev)
+                for r, i in enumerate(b):
+                    batch_codes[r, :lengths[i]] = codes[i]
+            else:
+                host = torch.zeros(len(b), Lmax, dtype=torch.long).pin_memory()
+                for r, i in enumerate(b):
+                    host[r, :lengths[i]] = codes[i]
+                batch_codes = host.to(dev, non_blocking=True)
+            kw = {"code": batch_codes,
                   "lens": torch.tensor([lengths[i] for i in b], dtype=torch.int32).to(dev, non_blocking=True)}
             if spkrs is not None:
                 kw["spkr"] = torch.tensor([[spk(i)] for i in b], dtype=torch.long).to(dev, non_blocking=True)
+            if pcm16:                                  # int16 straight from conv_post's epilogue (no f32 waveform round trip)
+                pcm = self.generator.forward_pcm16(**kw)
+                self.last_launches += self.generator.last_launches
+                for r, i in enumerate(b):
+                    p = pcm[r, 0, :lengths[i] * hop]
+                    out[i] = ops.peak_normalize(p.contiguous()) if normalize else p
+                continue
             wav = self.generator(**kw)                 # [len(b), 1, hop * Lmax], zero beyond each item's end
+            self.last_launches += self.generator.last_launches
             for r, i in enumerate(b):
                 out[i] = finish(wav[r, 0, :lengths[i] * hop])
         for i in long_form:                            # streamed: chunks of one utterance, each with its halo
             code = codes[i].to(dev).unsqueeze(0)
             sp = torch.tensor([[spk(i)]], dtype=torch.long, device=dev) if spkrs is not None else None
-            parts = [w[0] for _, w in stream_generate(self.generator, code, sp, self.chunk_units, self.halo_units)]
-            out[i] = finish(torch.cat(parts))
+            parts = [w[0] for _, w in stream_generate(self.generator, code, sp, self.chunk_units, self.halo_units, pcm16=pcm16)]
+            whole = torch.cat(parts)
+            out[i] = (ops.peak_normalize(whole) if normalize else whole) if pcm16 else whole
         for i in empty:
             out[i] = finish(torch.zeros(0, device=dev))
         if to_host:
             out = [None if o is None else (ops.to_host(o) if o.numel() else o.cpu().numpy()) for o in out]
         return out
+
+
+class SpeechPipeline:
+    """``pipe = SpeechPipeline(parrot, generator); audio = pipe(phones, speakers)`` - character-token sequences in, per-utterance
+    audio out: the whole hot path (demo.ipynb cells 11 + 13) for a pool of utterances, as one call.
+
+    The TTE runs one utterance per call - the reference's own inference mode (``DataLoader(batch_size=1)``, inference.py:31-37) and
+    the only batching whose result does not depend on the other items of the batch (the "positional" row is indexed by the PADDED
+    length, modules/fft.py:18) - and hands its unit ids to the vocoder ON THE DEVICE (``Parrot.infer_device``); the vocoder runs the
+    length-bucketed ragged batches of ``BatchSynthesizer``.  Under ``torch.distributed`` pass ``indices=rank_share_tte(...)``: each
+    rank synthesises its longest-processing-time-first share, nothing is exchanged on the data path.
+    """
+
+    def __init__(self, parrot, generator, **synth_kwargs):
+        self.parrot = parrot
+        self.synth = BatchSynthesizer(generator, **synth_kwargs)
+        self.last_units = None
+        self.last_launches = 0
+
+    def units(self, phones, speakers=None, indices=None):
+        """-> list of 1-D i64 device tensors of unit ids (``None`` outside ``indices``)."""
+        dev = self.synth._device()
+        idx = range(len(phones)) if indices is None else indices
+        out = [None] * len(phones)
+        pad = self.parrot.src_pad_idx
+        launches = 0
+        for i in idx:
+            ph = torch.as_tensor(phones[i], dtype=torch.long).reshape(1, -1)
+            if not ph.is_cuda:
+                ph = (ph.pin_memory() if ph.numel() else ph).to(dev, non_blocking=True)
+            spk = torch.tensor([0 if speakers is None else int(speakers[i])], dtype=torch.long).to(dev, non_blocking=True)
+            ids, n = self.parrot.infer_device({"phones": ph, "src_mask": ph != pad, "speaker": spk})
+            launches += self.parrot.last_launches
+            out[i] = ids[0]                           # batch of one: every position is live (n == T)
+        self.last_launches = launches
+        return out
+
+    def __call__(self, phones, speakers=None, vocoder_speakers=None, pcm16=True, normalize=False, indices=None, to_host=True):
+        units = self.units(phones, speakers, indices)
+        self.last_units = units
+        idx = list(range(len(phones))) if indices is None else list(indices)
+        vs = speakers if vocoder_speakers is None else vocoder_speakers
+        audio = self.synth([units[i] for i in idx], None if vs is None else [vs[i] for i in idx], pcm16=pcm16, normalize=normalize,
+                           to_host=to_host)
+        out = [None] * len(phones)
+        for i, a in zip(idx, audio):
+            out[i] = a
+        return out
+
+
+def rank_share_tte(unit_lengths, world_size, rank):
+    """Indices of the utterances rank ``rank`` runs end to end (LPT on the TTE + vocoder cost; same on every rank)."""
+    costs = [sharding.utterance_cost(n, with_tte=True) for n in unit_lengths]
+    return sorted(sharding.lpt_assign(costs, world_size)[rank])

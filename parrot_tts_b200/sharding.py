@@ -90,3 +90,32 @@ def broadcast_state_dict(sd, src=0, device=None, group=None):
         flat = flat.to(device)
     dist.broadcast(flat, src=src, group=group)
     return unpack_state_dict(flat, manifest)
+
+
+class _DeviceBytes:
+    """Raw device memory as a ``__cuda_array_interface__`` object (torch wraps it without copying)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def broadcast_engines(modules, src=0, device=None, group=None):
+    """ONE broadcast per model of the PACKED weight arena (SURVEY.md section 8e): ``src`` has loaded the checkpoint into its modules;
+    its engines upload, fold (weight norm, projection folding) and pack once, and every other rank receives the finished arena
+    straight into its own engine (``pb_*_arena_ptr``) - no state dict travels, nobody else folds or packs.  ``modules``: the
+    ``Parrot`` / ``CodeGenerator`` instances of this rank (constructed from the same configs on every rank; on the other ranks their
+    parameters stay placeholders).  Replaces every worker's own ``torch.load`` of the checkpoint (reference
+    utils/vocoder/inference.py:104-109)."""
+    rank = dist.get_rank(group)
+    device = torch.device(device if device is not None else "cuda")
+    if device.index is None:      # the engines key their device copy by the full device string
+        device = torch.device("cuda", torch.cuda.current_device())
+    total = 0
+    for m in modules:
+        ptr, nbytes = m.engine_arena(device, receive=(rank != src))
+        dist.broadcast(torch.as_tensor(_DeviceBytes(ptr, nbytes), device=device), src=src, group=group)
+        if rank != src:
+            m.engine_adopt()
+        total += nbytes
+    torch.cuda.synchronize(device)
+    return total

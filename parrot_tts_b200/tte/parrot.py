@@ -55,18 +55,33 @@ class Parrot(nn.Module):
         self.last_launches = 0
 
     # ------------------------------------------------------------------ engine
-    def _handle(self, device):
+    def _cfg_fields(self):
         tr, dp = self._tr, self._dp
         if tr["encoder"]["n_head"] != tr["decoder"]["n_head"]:
             raise NotImplementedError("encoder and decoder must use the same number of heads")
-        cfg = dict(src_vocab_size=self.src_vocab_size, src_pad_idx=self.src_pad_idx,
+        return dict(src_vocab_size=self.src_vocab_size, src_pad_idx=self.src_pad_idx,
                    n_speaker=self.speaker_emb.num_embeddings if self.speaker_emb is not None else 0,
                    d_model=self.d_model, n_head=tr["encoder"]["n_head"], n_enc_layer=len(self.encoder_layers),
                    n_dec_layer=len(self.decoder_layers), conv_n_filter=tr["conv_n_filter"], conv_k1=tr["conv_kernel_sizes"][0],
                    conv_k2=tr["conv_kernel_sizes"][1], dp_n_filter=dp["n_filter"], dp_kernel=dp["kernel_size"],
                    n_codes=self.n_codes, max_len=self.max_len, fold_projections=int(self.fold_projections),
                    gemm_mode=int(self.gemm_mode) if self.fold_projections else 0)   # the unfolded reference mode is fp32 SIMT
-        return self._eng.get(cfg, self._wstamp, device)
+
+    def _handle(self, device):
+        return self._eng.get(self._cfg_fields(), self._wstamp, device)
+
+    # ---- packed-arena hand-over (sharding.broadcast_engines), as on the vocoder
+    def engine_arena(self, device, receive=False):
+        lib = _lib.load()
+        device = torch.device(device)
+        hnd = self._eng.create_empty(self._cfg_fields(), device) if receive else self._handle(device)
+        self._arena_device = device
+        n = C.c_int64(0)
+        _lib.check(lib.pb_tte_arena_bytes(hnd, C.byref(n)))
+        return int(lib.pb_tte_arena_ptr(hnd)), int(n.value)
+
+    def engine_adopt(self):
+        self._eng.adopt(self._cfg_fields(), self._wstamp, self._arena_device)
 
     def _encode(self, batch, dur_in=None):
         phones = batch["phones"]
@@ -94,12 +109,13 @@ class Parrot(nn.Module):
         self.last_launches = int(_lib.load().pb_tte_last_launches(hnd))
         return hnd, dev, B, S, int(T.value), log_dur, dur, out_lens
 
-    def _decode(self, hnd, dev, B, S, T, want_logits, want_ids):
+    def _decode(self, hnd, dev, B, S, T, want_logits, want_ids, tgt_mask_in=None):
         logits = torch.empty(B, T, self.n_codes, device=dev, dtype=torch.float32) if want_logits else None
         ids = torch.empty(B, T, device=dev, dtype=torch.int64) if want_ids else None
         tgt_mask = torch.empty(B, T, device=dev, dtype=torch.uint8)
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().pb_tte_decode(hnd, B, S, T, _lib.ptr(logits), _lib.ptr(ids), _lib.ptr(tgt_mask), _lib.stream_ptr(dev)))
+            _lib.check(_lib.load().pb_tte_decode(hnd, B, S, T, _lib.ptr(tgt_mask_in), _lib.ptr(logits), _lib.ptr(ids), _lib.ptr(tgt_mask),
+                                                 _lib.stream_ptr(dev)))
         self.last_launches += int(_lib.load().pb_tte_last_launches(hnd))
         return logits, ids, tgt_mask
 
@@ -112,13 +128,14 @@ class Parrot(nn.Module):
             assert "duration" in batch.keys()
             dur_in = batch["duration"]
         hnd, dev, B, S, T, log_dur, _, _ = self._encode(batch, dur_in)
-        if dur_in is not None and batch.get("tgt_mask") is not None:
-            assert batch["tgt_mask"].shape[1] == T
-        logits, _, tgt_mask = self._decode(hnd, dev, B, S, T, True, False)
-        tgt_mask = tgt_mask.bool()
-        if dur_in is not None and batch.get("tgt_mask") is not None:
-            tgt_mask = batch["tgt_mask"]
-        return logits, batch["src_mask"], tgt_mask, log_dur
+        given = batch.get("tgt_mask") if dur_in is not None else None
+        mask_in = None
+        if given is not None:
+            # the reference's length_regulator returns a supplied mask unchanged and the decoder attends with it (duration.py:9-10,22-24)
+            assert given.shape[1] == T
+            mask_in = given.to(device=dev, dtype=torch.uint8).contiguous()
+        logits, _, tgt_mask = self._decode(hnd, dev, B, S, T, True, False, mask_in)
+        return logits, batch["src_mask"], (given if given is not None else tgt_mask.bool()), log_dur
 
     def infer_device(self, batch):
         """Device-resident variant of infer(): (ids i64 [B,T], n_valid i64 [B]) where item b's units are

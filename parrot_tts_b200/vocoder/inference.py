@@ -22,11 +22,17 @@ def generate(h, generator, code):
     (the reference's timing omits ``cuda.synchronize`` and under-reports GPU time).
     """
     start = time.time()
-    y_g_hat = generator(**code)
-    if type(y_g_hat) is tuple:
-        y_g_hat = y_g_hat[0]
-    audio = ops.to_host(ops.wav_to_pcm16(y_g_hat.squeeze()))
-    rtf = (time.time() - start) / (y_g_hat.shape[-1] / h.sampling_rate)
+    if hasattr(generator, "forward_pcm16"):          # the cast is conv_post's epilogue: no f32 waveform round trip through HBM
+        pcm = generator.forward_pcm16(**code)
+    else:
+        y_g_hat = generator(**code)
+        if type(y_g_hat) is tuple:
+            y_g_hat = y_g_hat[0]
+        pcm = ops.wav_to_pcm16(y_g_hat)
+    audio = ops.to_host(pcm.squeeze())
+    if hasattr(generator, "check_ids"):
+        generator.check_ids()                          # IndexError for ids outside the embedding tables, like nn.Embedding
+    rtf = (time.time() - start) / (pcm.shape[-1] / h.sampling_rate)
     return audio, rtf
 
 
@@ -48,38 +54,55 @@ class GraphedGenerator:
     captured once (stream capture keeps the programmatic-dependent-launch edges and the cluster launches) and replayed with
     one driver call, which is what bounds the small, latency-critical calls (a single utterance, the chunks of a stream).
     Inputs are copied into static buffers; the returned waveform (or int16 PCM with ``pcm16=True``) is a static buffer too,
-    valid until the next call.  Capture the LARGEST shape you will use first: a later, larger forward of the same generator
-    regrows its workspace and invalidates graphs captured before it."""
+    valid until the next call.  The graph records raw pointers into the engine's weight arena and workspace: every call compares
+    the engine handle and its memory epoch (``pb_voc_memory_epoch``) with the ones recorded at capture and captures again when the
+    weights were re-uploaded or a larger forward regrew the workspace (capturing the LARGEST shape first avoids the re-capture)."""
 
     def __init__(self, generator, B, T, pcm16=False):
         dev = next(generator.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedGenerator needs a generator on a CUDA device")
         self.generator, self.B, self.T, self.pcm16 = generator, int(B), int(T), bool(pcm16)
+        self.device = dev
         self.code = torch.zeros(B, T, dtype=torch.long, device=dev)
         self.spkr = torch.zeros(B, 1, dtype=torch.long, device=dev) if getattr(generator, "multispkr", None) else None
         self.lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+        self.captures = 0
+        self._capture()
 
-        def run():
-            kw = {"code": self.code, "lens": self.lens}
-            if self.spkr is not None:
-                kw["spkr"] = self.spkr
-            wav = generator(**kw)
-            return ops.wav_to_pcm16(wav) if self.pcm16 else wav
+    def _run(self):
+        kw = {"code": self.code, "lens": self.lens}
+        if self.spkr is not None:
+            kw["spkr"] = self.spkr
+        return self.generator.forward_pcm16(**kw) if self.pcm16 else self.generator(**kw)
 
+    def _memory_key(self):
+        """(engine handle, its memory epoch): the graph holds raw pointers into the handle's weight arena and workspace."""
+        from .. import _lib
+        hnd = self.generator._engine(self.device)          # rebuilds the engine if the module's weights changed
+        return (hnd.value, int(_lib.load().pb_voc_memory_epoch(hnd)))
+
+    def _capture(self):
+        dev = self.device
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                  # warm-up off the capture: engine, workspace, function attributes
-            run(); run()
+            self._run(); self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = run()
+            self.out = self._run()
+        self._key = self._memory_key()
+        self.captures += 1
 
     def __call__(self, code, spkr=None, lens=None):
         if tuple(code.shape) != (self.B, self.T):
             raise ValueError(f"GraphedGenerator captured for {(self.B, self.T)}, got {tuple(code.shape)}")
+        if self._memory_key() != self._key:
+            # the weights were re-uploaded (new engine) or a larger forward regrew the workspace since the capture: the recorded
+            # pointers are dead - capture again rather than replay into freed memory
+            self._capture()
         self.code.copy_(code, non_blocking=True)
         if self.spkr is not None:
             if spkr is None:
@@ -108,20 +131,21 @@ def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32,
     """Long-form synthesis in chunks (BASELINE configs[4]): yields (first_sample, audio) per chunk, audio f32 [B, n] on the
     device (or int16 with ``pcm16=True``), n = hop * (b - a).  ``code`` i64 [B, T] on the device.  Each chunk is one
     ``generator(code=window, spkr=spkr)`` call on the window of units it needs; nothing is recomputed beyond the two halos.
-    ``graphs={}`` replays one CUDA graph per distinct window length instead (the dict can be kept for the next stream)."""
+    ``graphs={}`` replays one CUDA graph per distinct window length instead (the dict can be kept for the next stream; a yielded
+    chunk is then a view of the graph's static output buffer, valid until the next chunk of the same window length)."""
     T = code.shape[1]
     hop = generator.hop
     chunks = stream_chunks(T, chunk_units, halo_units)
-    if graphs is not None:      # dict {window length: GraphedGenerator}, filled here (largest window first) and reusable across streams
+    if graphs is not None:      # dict {(window length, pcm16): GraphedGenerator}, filled here (largest window first), reusable across streams
         for n in sorted({hi - lo for lo, hi, _, _ in chunks}, reverse=True):
-            if n not in graphs:
-                graphs[n] = GraphedGenerator(generator, code.shape[0], n)
+            if (n, bool(pcm16)) not in graphs:
+                graphs[(n, bool(pcm16))] = GraphedGenerator(generator, code.shape[0], n, pcm16=pcm16)
     for lo, hi, a, b in chunks:
         if graphs is not None:
-            wav = graphs[hi - lo](code[:, lo:hi], spkr)[:, 0, (a - lo) * hop:(b - lo) * hop]
+            out = graphs[(hi - lo, bool(pcm16))](code[:, lo:hi], spkr)
         else:
             kw = {"code": code[:, lo:hi].contiguous()}
             if spkr is not None:
                 kw["spkr"] = spkr
-            wav = generator(**kw)[:, 0, (a - lo) * hop:(b - lo) * hop]
-        yield a * hop, (ops.wav_to_pcm16(wav.contiguous()) if pcm16 else wav)
+            out = generator.forward_pcm16(**kw) if pcm16 else generator(**kw)      # int16 straight from conv_post's epilogue
+        yield a * hop, out[:, 0, (a - lo) * hop:(b - lo) * hop]

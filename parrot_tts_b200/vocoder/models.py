@@ -164,7 +164,12 @@ class Generator(nn.Module):
             _lib.check(lib.pb_voc_create(C.byref(cfg), C.byref(hnd)))
             try:
                 for key, t in self.state_dict().items():
+                    src = t
                     t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+                    if t.data_ptr() != src.data_ptr():
+                        # a conversion / copy ran on torch's current stream; set_weight copies on the legacy default stream, which
+                        # does not order against non-blocking streams: wait for the temporary before handing its pointer over
+                        torch.cuda.current_stream(device).synchronize()
                     shape = (C.c_int64 * t.dim())(*t.shape)
                     _lib.check(lib.pb_voc_set_weight(hnd, key.encode(), _lib.ptr(t), shape, t.dim(), 0))
                 _lib.check(lib.pb_voc_finalize(hnd, _lib.stream_ptr(device)))
@@ -174,7 +179,33 @@ class Generator(nn.Module):
         eng.handle, eng.stamp, eng.device = hnd, stamp, device
         return hnd
 
-    def _run(self, x=None, code=None, spkr=None, lens=None):
+    # ---- packed-arena hand-over (sharding.broadcast_engines): the folded + packed weights live in ONE device arena whose layout is
+    # a pure function of the config, so a rank that did not load the checkpoint receives the arena instead of the state dict
+    def engine_arena(self, device, receive=False):
+        """(device pointer, bytes) of the engine's weight arena.  ``receive=True`` creates an EMPTY engine (no upload, no fold) whose
+        arena is about to be filled from another rank; call ``engine_adopt()`` once it has been."""
+        lib = _lib.load()
+        device = torch.device(device)
+        if receive:
+            self._eng.close()
+            with torch.cuda.device(device):
+                hnd = C.c_void_p()
+                cfg = self._cfg()
+                _lib.check(lib.pb_voc_create(C.byref(cfg), C.byref(hnd)))
+            self._eng.handle, self._eng.stamp, self._eng.device = hnd, None, device
+        else:
+            hnd = self._engine(device)
+        n = C.c_int64(0)
+        _lib.check(lib.pb_voc_arena_bytes(hnd, C.byref(n)))
+        return int(lib.pb_voc_arena_ptr(hnd)), int(n.value)
+
+    def engine_adopt(self):
+        """Declare the received arena complete: the engine now stands for this module's weights (its parameters are placeholders
+        until something is loaded into them, which rebuilds the engine like any other weight change)."""
+        _lib.check(_lib.load().pb_voc_mark_finalized(self._eng.handle))
+        self._eng.stamp = self._stamp(self._eng.device)
+
+    def _run(self, x=None, code=None, spkr=None, lens=None, pcm16=False):
         ref = x if x is not None else code
         if not ref.is_cuda:
             raise _lib.ParrotB200Error("Generator.forward needs CUDA tensors: the vocoder has no CPU path")
@@ -182,7 +213,11 @@ class Generator(nn.Module):
         lib = _lib.load()
         hnd = self._engine(device)
         B, T = (x.shape[0], x.shape[2]) if x is not None else code.shape
-        wav = torch.empty(B, 1, self.hop * T, device=device, dtype=torch.float32)
+        # pcm16: conv_post's epilogue writes the int16 PCM itself and the f32 waveform never reaches HBM (the fp32 SIMT mode casts
+        # from the waveform in a separate launch and needs it)
+        want_wav = not pcm16 or int(self.conv_mode) == 0
+        wav = torch.empty(B, 1, self.hop * T, device=device, dtype=torch.float32) if want_wav else None
+        pcm = torch.empty(B, 1, self.hop * T, device=device, dtype=torch.int16) if pcm16 else None
         if x is not None:
             x = x.to(torch.float32).contiguous()
         else:
@@ -194,10 +229,22 @@ class Generator(nn.Module):
         if lens is not None:
             lens = torch.as_tensor(lens).to(device=device, dtype=torch.int32).contiguous()
         with torch.cuda.device(device):
-            _lib.check(lib.pb_voc_forward(hnd, _lib.ptr(x), _lib.ptr(code), _lib.ptr(spkr), _lib.ptr(lens),
-                                          B, T, _lib.ptr(wav), _lib.stream_ptr(device)))
+            if pcm16:
+                _lib.check(lib.pb_voc_forward_pcm16(hnd, _lib.ptr(x), _lib.ptr(code), _lib.ptr(spkr), _lib.ptr(lens),
+                                                    B, T, _lib.ptr(wav), _lib.ptr(pcm), _lib.stream_ptr(device)))
+            else:
+                _lib.check(lib.pb_voc_forward(hnd, _lib.ptr(x), _lib.ptr(code), _lib.ptr(spkr), _lib.ptr(lens),
+                                              B, T, _lib.ptr(wav), _lib.stream_ptr(device)))
         self.last_launches = int(lib.pb_voc_last_launches(hnd))
-        return wav
+        return pcm if pcm16 else wav
+
+    def check_ids(self):
+        """Raise ``IndexError`` if a forward since the last check was given a unit / speaker id outside its embedding table at a
+        live position, as the reference's ``nn.Embedding`` does (utils/vocoder/models.py:155-156).  The forward itself is
+        asynchronous and clamps; this waits for the device."""
+        if self._eng.handle is not None:
+            with torch.cuda.device(self._eng.device):
+                _lib.check(_lib.load().pb_voc_check_ids(self._eng.handle, _lib.stream_ptr(self._eng.device)))
 
     # ------------------------------------------------------------------ measurement hooks
     def set_timing(self, enable, device="cuda:0"):
@@ -220,6 +267,11 @@ class Generator(nn.Module):
     def forward(self, x):
         """f32 [B, model_in_dim, T] -> f32 [B, 1, hop*T] (reference utils/vocoder/models.py:95-111)."""
         return self._run(x=x)
+
+    def forward_pcm16(self, x):
+        """forward + the generate() tail (x 32768, int16 cast; reference utils/vocoder/inference.py:71-73) as conv_post's
+        epilogue -> i16 [B, 1, hop*T]: bitwise ``ops.wav_to_pcm16(self.forward(x))`` without the f32 waveform round trip."""
+        return self._run(x=x, pcm16=True)
 
     def remove_weight_norm(self):
         for up in self.ups:
@@ -252,11 +304,15 @@ class CodeGenerator(Generator):
         ``lens`` (i32/i64 [B], optional, not in the reference) gives each item's true unit count: every
         item then equals its own batch-of-1 result instead of the padded-rectangle result.
         """
-        extra = [k for k in kwargs if k not in ("code", "spkr", "f0", "lens")]
+        extra = [k for k in kwargs if k not in ("code", "spkr", "f0", "lens", "pcm16")]
         if extra:
             raise NotImplementedError(f"extra conditioning features {extra} are not supported: model_in_dim is "
                                       "fully used by the unit and speaker embeddings")
         spkr = kwargs.get("spkr") if self.multispkr else None
         if self.multispkr and spkr is None:
             raise KeyError("spkr")
-        return self._run(code=kwargs["code"], spkr=spkr, lens=kwargs.get("lens"))
+        return self._run(code=kwargs["code"], spkr=spkr, lens=kwargs.get("lens"), pcm16=bool(kwargs.get("pcm16", False)))
+
+    def forward_pcm16(self, **kwargs):
+        """``forward(**kwargs)`` with the int16 cast of generate() fused into conv_post -> i16 [B, 1, hop*T]."""
+        return self.forward(**dict(kwargs, pcm16=True))

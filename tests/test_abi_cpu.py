@@ -53,7 +53,7 @@ def test_error_paths_without_gpu(lib_path):
     lib = _lib.load()
     assert lib.pb_voc_forward(None, None, None, None, None, 1, 1, None, None) == _lib.PB_ERR_INVALID
     assert b"null" in lib.pb_last_error()
-    assert lib.pb_tte_decode(None, 1, 1, 1, None, None, None, None) == _lib.PB_ERR_INVALID
+    assert lib.pb_tte_decode(None, 1, 1, 1, None, None, None, None, None) == _lib.PB_ERR_INVALID
     with pytest.raises(IndexError):
         _lib.check(_lib.PB_ERR_INDEX)
     with pytest.raises(_lib.ParrotB200Error):

@@ -26,7 +26,10 @@ def test_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_block("cfg3", 1) and d["scaling"] == "weak"      # same object as the GPU arm prints
 
 
 def test_reference_arm_is_silent_on_other_ranks():
@@ -77,7 +80,32 @@ def test_chain_schedule_is_hazard_free():
 def test_cpu_baseline_sample_is_bounded():
     sys.path.insert(0, ROOT)
     import bench
-    shape = dict(workload="tiny", B=2, T=24, S=0)
-    d = bench.cpu_baseline_sample(shape, budget_s=0.5, max_steps=3)
+    d = bench.cpu_baseline_sample("cfg2", budget_s=0.5, max_steps=3, plan=[(0, 24)] * 3)
     assert d["kind"] == "port" and d["unit"] == "samples/s" and d["cores"] >= 1 and d["value"] > 0 and d["best_step"] >= d["value"] * 0.999
     assert "1 utterance x 24 units" in d["sample"] and "step(s)" in d["sample"]
+
+
+def test_workload_selection_and_config_block():
+    """N = 1 measures the single-GPU text -> wav configuration (configs[2]), N > 1 the sharded pool (configs[3]); the `config` object
+    is the same function of (workload, world) in both arms, so the driver's same-config check compares like with like."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.resolve_workload("auto", 1) == "cfg3" and bench.resolve_workload("auto", 8) == "cfg4"
+    assert bench.resolve_workload("cfg2", 8) == "cfg2"
+    c3, c4 = bench.config_block("cfg3", 1), bench.config_block("cfg4", 8)
+    assert c3["workload"].startswith("cfg3") and c3["units_per_rank_per_step"] == 32 * 2048
+    assert c4["workload"].startswith("cfg4") and c4["pool_units"] == sum(bench.cfg4_lengths()) and "strong" in c4["sharding"]
+    L = bench.cfg4_lengths()
+    assert len(L) == 256 and min(L) >= 256 and max(L) <= 4096 and max(L) < bench.TTE_MAX_LEN
+    plan = bench.cpu_sample_plan("cfg4", 5)
+    assert len(plan) == 5 and all(S == (T + 7) // 8 for S, T in plan) and plan == sorted(plan)
+    assert bench.cpu_sample_plan("cfg3", 2) == [(256, 2048)] * 2
+
+
+def test_reference_arm_at_two_ranks_times_the_sharded_pool():
+    out = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert out.returncode == 0, out.stderr
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_block("cfg4", 2) and d["scaling"] == "strong"

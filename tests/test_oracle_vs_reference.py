@@ -102,6 +102,34 @@ def test_tte_oracle_vs_reference_teacher_forced_and_zero_durations():
     np.testing.assert_allclose(r["log_dur"].numpy(), log_dur.numpy(), atol=2e-5, rtol=0)
 
 
+def test_tte_oracle_vs_reference_supplied_tgt_mask():
+    # the training-side batch carries tgt_mask = codes != pad (exact lengths, modules/data.py:117-119); the reference's
+    # length_regulator returns it unchanged and the decoder attends with it (modules/duration.py:9-10,22-24; parrot.py:104,107) -
+    # one live key fewer per shorter item than the derived `<=` mask
+    cfg = configs.default_tte_config()
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=16)
+    ref = ref_shim.load_reference_parrot(cfg, 150, 0, 10)
+    ref.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(16)
+    phones = torch.randint(2, 150, (3, 9), generator=g)
+    phones[1, 5:] = 0
+    dur = torch.randint(1, 5, (3, 9), generator=g)
+    dur[1, 5:] = 0
+    dur[2, :] = 1
+    lens = dur.sum(1)
+    T = int(lens.max())
+    tgt_mask = torch.arange(T).unsqueeze(0) < lens.unsqueeze(1)           # exact lengths, unlike get_mask_from_lengths
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([3, 0, 7]), "duration": dur, "tgt_mask": tgt_mask}
+    with torch.no_grad():
+        logits, _, mask_out, log_dur = ref(batch)
+    assert mask_out is tgt_mask
+    r = tte_oracle.parrot_forward(sd, batch, dur_override=dur, tgt_mask=tgt_mask)
+    assert torch.equal(r["tgt_mask"], tgt_mask)
+    np.testing.assert_allclose(r["logits"].numpy(), logits.numpy(), atol=5e-4, rtol=0)
+    derived = tte_oracle.parrot_forward(sd, batch, dur_override=dur)        # the `<=` mask gives different logits for the shorter items
+    assert float((derived["logits"][1] - r["logits"][1]).abs().max()) > 1e-3
+
+
 def test_generator_oracle_vs_reference_feature_input():
     # Generator.forward on features (utils/vocoder/models.py:95-111) through the reference CodeGenerator's parent class
     h = configs.default_vocoder_config()

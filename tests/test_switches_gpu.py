@@ -1,0 +1,77 @@
+"""Bitwise parity of the library's dev switches against the default path - none of them changes the arithmetic:
+  PB_VOC_CHAINS=1     the three ResBlock chains of a stage on three streams (measured: no gain at batch size, off by default)
+  PB_TC_TMA_OUT=3     TMA-store epilogue also on the CTA-pair layers with k <= 3
+  PB_TC_EPI_SPLIT=0/2 column-split epilogue groups off / on every one-CTA-per-SM layer (default 1: the CTA-pair layers)
+  PB_TC_CLUSTER=0     single-CTA path instead of CTA pairs
+Each case runs in a fresh interpreter because the library reads its switches once.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_LIB_VARIANT")
+
+CODE = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from parrot_tts_b200 import configs, synth
+from parrot_tts_b200.vocoder import CodeGenerator, GraphedGenerator
+h = configs.default_vocoder_config()
+gen = CodeGenerator(h)
+gen.load_state_dict(synth.synth_vocoder_state_dict(h, seed=0))
+gen = gen.to("cuda:0")
+g = torch.Generator().manual_seed(11)
+out = {{}}
+for B, T in ((1, 7), (2, 50), (8, 300)):
+    code = torch.randint(0, 1000, (B, T), generator=g).cuda()
+    spkr = torch.randint(0, 10, (B, 1), generator=g).cuda()
+    out[f"rect_{{B}}_{{T}}"] = gen(code=code, spkr=spkr).cpu().numpy()
+code = torch.randint(0, 1000, (3, 120), generator=g).cuda()
+spkr = torch.randint(0, 10, (3, 1), generator=g).cuda()
+lens = torch.tensor([120, 33, 1], dtype=torch.int32).cuda()
+out["ragged"] = gen(code=code, spkr=spkr, lens=lens).cpu().numpy()
+gg = GraphedGenerator(gen, 3, 120)
+out["graph"] = gg(code, spkr).cpu().numpy().copy()
+out["graph_again"] = gg(code, spkr).cpu().numpy().copy()
+np.savez({path!r}, **out)
+"""
+
+
+def _run(tmp_path, name, env_extra):
+    path = str(tmp_path / f"{name}.npz")
+    env = {k: v for k, v in os.environ.items() if k not in env_extra}          # None = make sure the variable is unset
+    env.update({k: v for k, v in env_extra.items() if v is not None})
+    r = subprocess.run([sys.executable, "-c", CODE.format(root=ROOT, path=path)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return dict(np.load(path))
+
+
+def _same(a, b):
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+
+
+@pytest.fixture(scope="module")
+def baseline(tmp_path_factory):
+    return _run(tmp_path_factory.mktemp("exp"), "default", {k: None for k in SWITCHES})
+
+
+def test_chain_streams_are_bit_identical(tmp_path, baseline):
+    got = _run(tmp_path, "chains", {"PB_VOC_CHAINS": "1"})
+    _same(baseline, got)
+    assert np.array_equal(got["graph"], got["graph_again"])          # fork / join survives CUDA-graph capture and replay
+
+
+def test_tma_store_on_k3_pair_layers_is_bit_identical(tmp_path, baseline):
+    _same(baseline, _run(tmp_path, "tma3", {"PB_TC_TMA_OUT": "3"}))
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_column_split_epilogue_modes_are_bit_identical(tmp_path, baseline, mode):
+    _same(baseline, _run(tmp_path, "episplit" + mode, {"PB_TC_EPI_SPLIT": mode}))

@@ -199,6 +199,28 @@ def test_parrot_teacher_forced_durations():
     assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0)
 
 
+def test_parrot_teacher_forced_with_supplied_tgt_mask():
+    """batch['tgt_mask'] (exact lengths, as the reference's dataset builds it) is the decoder's key padding mask and is returned
+    unchanged (reference modules/duration.py:9-10,22-24; parrot.py:104,107)."""
+    cfg, sd, m = _parrot(seed=23)
+    g = _gen(10)
+    phones = torch.randint(2, VOCAB, (3, 12), generator=g)
+    phones[1, 7:] = 0
+    dur = torch.randint(1, 5, (3, 12), generator=g)
+    dur[1, 7:] = 0
+    dur[2, :] = 1
+    lens = dur.sum(1)
+    tgt_mask = torch.arange(int(lens.max())).unsqueeze(0) < lens.unsqueeze(1)
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([1, 2, 0]), "duration": dur, "tgt_mask": tgt_mask}
+    r = tte_oracle.parrot_forward(sd, batch, dur_override=dur, tgt_mask=tgt_mask)
+    dev_batch = _to_dev(batch)
+    logits, _, mask_out, _ = m(dev_batch, inference=False)
+    assert mask_out is dev_batch["tgt_mask"]
+    assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0), float((logits.cpu() - r["logits"]).abs().max())
+    r2 = tte_oracle.parrot_forward(sd, batch, dur_override=dur)
+    assert float((r2["logits"] - r["logits"]).abs().max()) > 1e-2          # the derived `<=` mask is a different computation
+
+
 def test_parrot_rejects_overlong_like_reference():
     _, _, m = _parrot(seed=0, max_len=40)
     phones = torch.randint(2, VOCAB, (1, 40), generator=_gen(1))
@@ -264,3 +286,30 @@ def test_full_size_tensor_core_vs_fp32_path():
     for b, t in bad.tolist():
         assert float(margin[b, t]) < 1e-4, f"id mismatch at a clear-cut position b={b} t={t} margin={float(margin[b, t])}"
     assert float((out[0][0] - out[1][0]).abs().max()) < 2e-3
+
+
+def test_single_speaker_parrot_matches_oracle():
+    """speakers.json with ONE entry: the reference builds no speaker_emb (modules/parrot.py:28-32); the handle is created with
+    n_speaker = 0 and the speaker pointer is NULL.  Integer outputs bit-exact, as everywhere."""
+    import json
+    import tempfile
+    d = tempfile.mkdtemp(prefix="parrot_one_spk_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({"only": 0}, f)
+    cfg = configs.default_tte_config(root_path=d)
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 1, seed=31)
+    m = Parrot(cfg, 150, 0)
+    assert m.speaker_emb is None
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to("cuda:0")
+    g = torch.Generator().manual_seed(31)
+    phones = torch.randint(2, 150, (3, 21), generator=g)
+    phones[1, 9:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.zeros(3, dtype=torch.long)}
+    ids_ref, r = tte_oracle.parrot_infer(sd, batch)
+    dev = {k: v.to("cuda:0") for k, v in batch.items()}
+    logits, _, tgt_mask, log_dur = m(dev, inference=True)
+    assert torch.equal(tgt_mask.cpu(), r["tgt_mask"])
+    assert torch.allclose(log_dur.cpu(), r["log_dur"], atol=5e-5, rtol=0)
+    assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0)
+    assert m.infer(dev) == ids_ref

@@ -351,4 +351,111 @@ def test_cuda_graph_replay_equals_direct_forward():
     plain = torch.cat([w for _, w in stream_generate(gen, code, spkr, chunk_units=128, halo_units=32)], dim=1)
     graphs = {}
     viag = torch.cat([w.clone() for _, w in stream_generate(gen, code, spkr, chunk_units=128, halo_units=32, graphs=graphs)], dim=1)
-    assert sorted(graphs) == [76, 160, 192] and torch.equal(plain, viag)
+    assert sorted(graphs) == [(76, False), (160, False), (192, False)] and torch.equal(plain, viag)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_pcm16_epilogue_equals_cast_of_the_waveform(mode):
+    """generate()'s tail (x 32768, int16 truncation; reference utils/vocoder/inference.py:71-73) as conv_post's epilogue: bitwise the
+    cast of the very waveform the plain forward returns - rectangular and ragged batches, and through generate() itself."""
+    from parrot_tts_b200.vocoder import generate
+    h, sd, gen = _code_generator(0, mode=mode)
+    g = _gen(31)
+    for B, T, lens in ((1, 9, None), (3, 41, None), (3, 57, [57, 20, 1])):
+        code = torch.randint(0, 1000, (B, T), generator=g).to(DEV)
+        spkr = torch.randint(0, 10, (B, 1), generator=g).to(DEV)
+        kw = dict(code=code, spkr=spkr)
+        if lens is not None:
+            kw["lens"] = torch.tensor(lens, dtype=torch.int32)
+        wav = gen(**kw)
+        pcm = gen.forward_pcm16(**kw)
+        assert pcm.dtype == torch.int16 and pcm.shape == wav.shape
+        assert np.array_equal(pcm.cpu().numpy(), voc_oracle.to_int16(wav.cpu()).reshape(pcm.shape)), (B, T)
+        assert torch.equal(pcm, ops.wav_to_pcm16(wav))
+    code = torch.randint(0, 1000, (1, 33), generator=g).to(DEV)
+    spkr = torch.randint(0, 10, (1, 1), generator=g).to(DEV)
+    audio, _ = generate(h, gen, dict(code=code, spkr=spkr))
+    assert np.array_equal(audio, voc_oracle.to_int16(gen(code=code, spkr=spkr).cpu()).squeeze())
+
+
+def test_out_of_range_ids_raise_like_nn_embedding():
+    """nn.Embedding raises IndexError for an id outside its table (reference utils/vocoder/models.py:155-156); padded positions
+    (past an item's length) are never looked up."""
+    h, sd, gen = _code_generator(1, mode=1)
+    code = torch.randint(0, 1000, (2, 12), generator=_gen(5)).to(DEV)
+    spkr = torch.tensor([[1], [2]], device=DEV)
+    gen(code=code, spkr=spkr)
+    gen.check_ids()
+    bad = code.clone()
+    bad[1, 7] = 1000                                   # the TTE dataset's pad value for codes (= num_embeddings)
+    gen(code=bad, spkr=spkr, lens=torch.tensor([12, 7], dtype=torch.int32))
+    gen.check_ids()                                    # position 7 of item 1 is padding under lens
+    gen(code=bad, spkr=spkr)
+    with pytest.raises(IndexError):
+        gen.check_ids()
+    gen.check_ids()                                    # the flag is cleared by the report
+    gen(code=code, spkr=torch.tensor([[1], [10]], device=DEV))
+    with pytest.raises(IndexError):
+        gen.check_ids()
+
+
+def test_cuda_graph_is_recaptured_when_its_pointers_die():
+    """A graph records raw pointers into the engine's arena and workspace: after a larger forward regrew the workspace, or after the
+    weights changed (new engine), the next call captures again instead of replaying into freed memory."""
+    from parrot_tts_b200.vocoder import GraphedGenerator
+    h, sd, gen = _code_generator(1, mode=1)
+    g = _gen(41)
+    gg = GraphedGenerator(gen, 1, 16)
+    code = torch.randint(0, 1000, (1, 16), generator=g).to(DEV)
+    spkr = torch.randint(0, 10, (1, 1), generator=g).to(DEV)
+    want = gen(code=code, spkr=spkr)
+    assert torch.equal(gg(code, spkr), want) and gg.captures == 1
+    big = torch.randint(0, 1000, (4, 400), generator=g).to(DEV)
+    gen(code=big, spkr=torch.zeros(4, 1, dtype=torch.long, device=DEV))      # regrows the workspace: old pointers are dead
+    assert torch.equal(gg(code, spkr), want) and gg.captures == 2
+    assert torch.equal(gg(code, spkr), want) and gg.captures == 2            # stable afterwards
+    torch.nn.Linear(3, 3)                                                      # unrelated registration: nothing of this model changed
+    assert torch.equal(gg(code, spkr), want) and gg.captures == 2
+    with torch.no_grad():
+        gen.conv_post.bias.add_(0.25)                                          # weights changed: new engine, new arena
+    want2 = gen(code=code, spkr=spkr)
+    assert not torch.equal(want2, want)
+    assert torch.equal(gg(code, spkr), want2) and gg.captures == 3
+
+
+def test_speech_pipeline_equals_one_utterance_at_a_time():
+    """serving.SpeechPipeline (char tokens -> TTE per utterance -> device hand-over of the ids -> ragged vocoder batches -> int16):
+    every utterance equals Parrot.infer + generate() run on it alone; a rank share (indices=) returns only its utterances."""
+    import json
+    import tempfile
+    from oracle import tte_oracle
+    from parrot_tts_b200.serving import SpeechPipeline, rank_share_tte
+    from parrot_tts_b200.tte import Parrot
+    from parrot_tts_b200.vocoder import generate
+    h, sd, gen = _code_generator(1, mode=1)
+    d = tempfile.mkdtemp(prefix="parrot_pipe_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({f"s{i}": i for i in range(10)}, f)
+    cfg = configs.default_tte_config(root_path=d)
+    sd_t = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=12)
+    tte = Parrot(cfg, 150, 0)
+    tte.load_state_dict(sd_t)
+    tte = tte.eval().to(DEV)
+    g = _gen(51)
+    phones = [torch.randint(2, 150, (n,), generator=g) for n in (5, 9, 3, 14, 7)]
+    spk = [1, 4, 0, 9, 2]
+    pipe = SpeechPipeline(tte, gen, max_batch=2)
+    audio = pipe(phones, spk)
+    for i, ph in enumerate(phones):
+        batch = {"phones": ph.view(1, -1), "src_mask": ph.view(1, -1) != 0, "speaker": torch.tensor([spk[i]])}
+        ids_ref, _ = tte_oracle.parrot_infer(sd_t, batch)
+        assert pipe.last_units[i].cpu().tolist() == ids_ref[0]                      # integer path: bit-exact vs the oracle
+        ref, _ = generate(h, gen, dict(code=torch.tensor([ids_ref[0]], device=DEV), spkr=torch.tensor([[spk[i]]], device=DEV)))
+        assert np.array_equal(audio[i], ref), i
+    lens = [int(u.numel()) for u in pipe.last_units]
+    shares = [rank_share_tte(lens, 2, r) for r in range(2)]
+    assert sorted(shares[0] + shares[1]) == list(range(5))
+    part = pipe(phones, spk, indices=shares[1])
+    assert [p is not None for p in part] == [i in shares[1] for i in range(5)]
+    for i in shares[1]:
+        assert np.array_equal(part[i], audio[i])
