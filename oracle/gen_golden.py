@@ -22,9 +22,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 VOCAB, PAD, NSPK = 150, 0, 10
 
 
-def tte_case(name, phones, speaker, seed=0):
+def tte_case(name, phones, speaker, seed=0, dur_mode="spread", stride=5):
     cfg = configs.default_tte_config()
-    sd = synth.synth_tte_state_dict(cfg, VOCAB, PAD, NSPK, seed=seed, dur_mode="spread")
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, PAD, NSPK, seed=seed, dur_mode=dur_mode)
     model = ref_shim.load_reference_parrot(cfg, VOCAB, PAD, NSPK)
     model.load_state_dict(sd, strict=True)
     phones = torch.as_tensor(phones, dtype=torch.long)
@@ -42,8 +42,8 @@ def tte_case(name, phones, speaker, seed=0):
         ids_flat=ids_flat, ids_lens=np.asarray([len(x) for x in ids_list], dtype=np.int64),
         argmax=torch.argmax(logits, -1).numpy(),
         margin=(top2[..., 0] - top2[..., 1]).numpy(),
-        logits_rows=logits[:, ::5, :].numpy().astype(np.float32),
-        logits_row_stride=np.int64(5),
+        logits_rows=logits[:, ::stride, :].numpy().astype(np.float32),
+        logits_row_stride=np.int64(stride), dur_mode=str(dur_mode),
         seed=np.int64(seed), torch_version=str(torch.__version__), vocab=np.int64(VOCAB), n_speaker=np.int64(NSPK),
     )
     print(name, "T =", logits.shape[1], "lens", [len(x) for x in ids_list], "min margin", float((top2[..., 0] - top2[..., 1]).min()))
@@ -85,6 +85,17 @@ def main():
     voc_case("voc_b1_t24", torch.randint(0, 1000, (1, 24), generator=g), [2])
     voc_case("voc_b2_t40", torch.randint(0, 1000, (2, 40), generator=g), [0, 9])
     voc_case("gen_b1_t12", None, None, x=torch.randn(1, 256, 12, generator=g))
+    # BASELINE configs[0] size, pinned to the REAL reference on CPU: 1 x 64 chars -> exactly 512 units
+    # (the const8 recipe of SURVEY 8d) -> and a 512-unit utterance through the vocoder (163 840 samples)
+    g2 = torch.Generator().manual_seed(4321)
+    tte_case("tte_cfg1_s64", torch.randint(2, VOCAB, (1, 64), generator=g2), [0], dur_mode="const8", stride=64)
+    voc_case("voc_cfg1_t512", torch.randint(0, 1000, (1, 512), generator=g2), [3])
+    # a ragged batch at config-3 source length: 4 items, up to 256 chars, predicted ("spread") durations
+    ph = torch.randint(2, VOCAB, (4, 256), generator=g2)
+    ph[1, 200:] = PAD
+    ph[2, 97:] = PAD
+    ph[3, 31:] = PAD
+    tte_case("tte_b4_s256_ragged", ph, [1, 8, 0, 5], seed=2, stride=128)
 
 
 if __name__ == "__main__":

@@ -14,11 +14,11 @@ def _load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name + ".npz"))
 
 
-@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged"])
+@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged", "tte_cfg1_s64", "tte_b4_s256_ragged"])
 def test_tte_oracle_matches_golden(golden_dir, name):
     g = _load(golden_dir, name)
     cfg = configs.default_tte_config()
-    sd = synth.synth_tte_state_dict(cfg, int(g["vocab"]), 0, int(g["n_speaker"]), seed=int(g["seed"]))
+    sd = synth.synth_tte_state_dict(cfg, int(g["vocab"]), 0, int(g["n_speaker"]), seed=int(g["seed"]), dur_mode=str(g["dur_mode"]))
     batch = {"phones": torch.from_numpy(g["phones"]), "src_mask": torch.from_numpy(g["src_mask"]),
              "speaker": torch.from_numpy(g["speaker"])}
     ids, r = tte_oracle.parrot_infer(sd, batch)
@@ -44,7 +44,7 @@ def test_round_half_even():
     assert tte_oracle.round_durations(ld).tolist() == [0, 2, 2, 0, 0]
 
 
-@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40"])
+@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40", "voc_cfg1_t512"])
 def test_voc_oracle_matches_golden(golden_dir, name):
     g = _load(golden_dir, name)
     h = configs.default_vocoder_config()

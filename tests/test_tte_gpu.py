@@ -137,10 +137,12 @@ def test_duration_predictor_matches_oracle():
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged"])
+@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged", "tte_cfg1_s64", "tte_b4_s256_ragged"])
 def test_parrot_matches_reference_golden(golden_dir, name, mode):
+    """Against vectors recorded from the reference's own modules on CPU (oracle/gen_golden.py), up to BASELINE configs[0] size
+    (64 chars -> 512 units) and a ragged batch at config-3 source length: ZERO id mismatches, durations and masks bit-exact."""
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    _, _, m = _parrot(seed=int(g["seed"]))
+    _, _, m = _parrot(seed=int(g["seed"]), dur_mode=str(g["dur_mode"]))
     m.gemm_mode = mode
     batch = _to_dev({"phones": torch.from_numpy(g["phones"]), "src_mask": torch.from_numpy(g["src_mask"]),
                      "speaker": torch.from_numpy(g["speaker"])})

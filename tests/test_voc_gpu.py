@@ -121,7 +121,7 @@ def _code_generator(seed, weight_norm=True, mode=1):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40"])
+@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40", "voc_cfg1_t512"])
 def test_code_generator_matches_reference_golden(golden_dir, name, mode):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     _, _, gen = _code_generator(int(g["seed"]), mode=mode)
