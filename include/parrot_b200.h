@@ -166,7 +166,8 @@ typedef struct pb_tte_cfg {
     int32_t n_codes;         /* 1000 */
     int32_t max_len;         /* 3500: rows of pos_emb.pe */
     int32_t fold_projections;/* 1: fold mha.in_proj*qkv and wo*out_proj at finalize (exact in real arithmetic) */
-    int32_t gemm_mode;       /* 0 = fp32 SIMT, 1 = tcgen05 split-bf16 (fp32-accurate), 2 = tcgen05 bf16 (throughput) */
+    int32_t gemm_mode;       /* 0 = fp32 SIMT, 1 = tcgen05 on split-fp16 operands, 3 products, fp32 accumulation (fp32-class; default).
+                              * There is no single-pass 16-bit mode for the TTE: unit ids are an integer output that must be bit-exact. */
 } pb_tte_cfg;
 
 typedef struct pb_tte pb_tte;
@@ -181,16 +182,21 @@ int pb_tte_finalize(pb_tte* h, void* stream);
 /* Parrot.forward up to and including the duration predictor and rounding (parrot.py:94-100,77-86;
  * duration.py:41-48).  phones i64 [B,S]; src_mask u8 [B,S] (1 = real char); speaker i64 [B] or NULL.
  * dur_in: NULL, or teacher-forced durations i64 [B,S] (batch['duration'], parrot.py:102).
+ * src_lens: NULL = the reference's padded-batch semantics (an item's result depends on the padded length: the "positional" row is
+ *   pe[S], fft.py:18, padded positions feed the k = 9 convolutions, and the target mask is t <= len, data.py:18), or i32 [B] =
+ *   RAGGED mode: item b is computed exactly as the reference computes it ALONE (batch of one, its inference mode, inference.py:34):
+ *   its own pe rows pe[src_lens[b]] / pe[out_lens[b]], zeros past its own end wherever a convolution looks, and exactly out_lens[b]
+ *   target positions.  src_mask must then be the prefix mask t < src_lens[b].  pb_tte_decode follows the mode of the last encode.
  * Outputs: log_dur f32 [B,S]; dur i64 [B,S]; out_lens i64 [B] (sum of durations per item).
  * *T_host = max_b out_lens (the length-regulated length).  SYNCHRONISES (T is data dependent).
  * Returns PB_ERR_INDEX if S >= max_len or T >= max_len (fft.py:18). */
 int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* src_mask, const int64_t* speaker,
-                  const int64_t* dur_in, int32_t B, int32_t S,
+                  const int64_t* dur_in, const int32_t* src_lens, int32_t B, int32_t S,
                   float* log_dur, int64_t* dur, int64_t* out_lens, int32_t* T_host, void* stream);
 
 /* length_regulator + pos_emb + decoder + head (+ argmax of Parrot.infer) (duration.py:6-24; parrot.py:106-108,115)
  * for the batch just encoded.  logits f32 [B,T,n_codes] or NULL; ids i64 [B,T] or NULL;
- * tgt_mask u8 [B,T] out (t <= out_lens[b], data.py:18).
+ * tgt_mask u8 [B,T] out (t <= out_lens[b], data.py:18; ragged mode: t < out_lens[b]).
  * tgt_mask_in: NULL, or the caller's mask u8 [B,T] (batch['tgt_mask'] of the teacher-forced path, parrot.py:104 ->
  * duration.py:22-24: the reference returns a supplied mask unchanged and the decoder attends with it); it then replaces the
  * generated one for the decoder's key padding and is what tgt_mask returns.  Asynchronous. */

@@ -75,7 +75,7 @@ SIGNATURES = {
     "pb_tte_destroy": (None, [_P]),
     "pb_tte_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(_I64), _I32, _I32]),
     "pb_tte_finalize": (C.c_int, [_P, _P]),
-    "pb_tte_encode": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.POINTER(_I32), _P]),
+    "pb_tte_encode": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.POINTER(_I32), _P]),
     "pb_tte_decode": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "pb_tte_last_launches": (_I64, [_P]),
     "pb_tte_arena_bytes": (C.c_int, [_P, C.POINTER(_I64)]),

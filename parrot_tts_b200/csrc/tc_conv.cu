@@ -60,7 +60,7 @@ struct TcParams {
     int fmt;                             // split storage / MMA operand type: 0 bf16, 1 fp16
     int tmem_cols, n_acc, n_groups;      // n_groups epilogue warpgroups take the tiles of a CTA round-robin (n_acc % n_groups == 0)
     int ablate;   // dev only (PB_TC_ABLATE): 1 = skip the MMAs, 2 = skip the output stores, 4 = skip residual / running-sum loads, 8 = skip the activation TMA loads,
-                  // 16 = skip the accumulator reads, 32 = skip the epilogue arithmetic
+                  // 16 = skip the accumulator reads, 32 = skip the epilogue arithmetic, 64 = skip the streamed weight loads
     int epi_split;  // column-split epilogue groups: every group works on EVERY tile and takes the 16-column items grp, grp + n_groups, ...
                     // - a tile's epilogue latency drops from (NT/16 items) to (NT/16 / n_groups) and n_groups is no longer capped by the
                     // number of accumulators (measured on B200, 8 x 1024 units: 8.08 -> 7.94 ms on the CTA-pair layers, slower on the others)
@@ -334,7 +334,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 for (int jb = 0; jb < (p.K - j0) * nsub; ++jb) {
                     mbar_wait(&empty_b[b_s], b_ph ^ 1);
                     if (elect_one()) {
-                        if (CL) {
+                        if (p.ablate & 64) {
+                            if (rank == 0) mbar_arrive(&full_b[b_s]);
+                        } else if (CL) {
                             // weights through a 2-D map over the packed bytes ([rows][256 B]) so that the load can signal the leader
                             if (rank == 0) mbar_expect_tx(&full_b[b_s], (uint32_t)(2 * p.b_sub_bytes));
                             const size_t off = (size_t)(wsrc - p.w) + (size_t)jb * sub_stride;
@@ -755,16 +757,15 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     uint32_t b_res_bytes = 0, ring_bytes = 0;
     const uint32_t w_all = (uint32_t)round_up(p.w_total_bytes, 1024);
     // TMA-store epilogue (U == 1, split output): 2 KB of staging per epilogue warp, up to 3 groups of 4 warps.
-    // PB_TC_TMA_OUT: 0 = never, 1 = layers that run one CTA per SM without CTA pairs (default), 2 = every eligible layer (dev switch),
-    // 3 = as 1 plus the CTA-pair layers with K <= 3 (not yet measured: those launches are epilogue-bound, profiles/r01_model_vs_measured.txt,
-    //     so the ring slot the staging tiles cost should matter less there than on the k = 7 / 11 layers mode 2 was measured on)
+    // PB_TC_TMA_OUT: 0 = never, 1 = layers that run one CTA per SM without CTA pairs (default), 2 = every eligible layer (dev switch;
+    // measured +1-2 % on the CTA-pair layers: the staging tiles cost a ring slot; restricted to their k <= 3 launches: no change)
     static const int tma_out_mode = getenv("PB_TC_TMA_OUT") ? atoi(getenv("PB_TC_TMA_OUT")) : 1;
     // two CTAs per SM (two producers, two MMA issuers, one epilogue group each) measured best for the 16-channel layers;
     // wider layers run one CTA per SM with up to 3 epilogue groups (PB_TC_2CTA=0/1 forces either, dev switch)
     static const int force_2cta = getenv("PB_TC_2CTA") ? atoi(getenv("PB_TC_2CTA")) : -1;
     const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
     p.tma_out = (a.out != nullptr && a.U == 1 && tma_out_mode > 0 && !want_2cta &&
-                 (tma_out_mode == 2 || !p.cluster || (tma_out_mode == 3 && a.K <= 3))) ? 1 : 0;
+                 (tma_out_mode == 2 || !p.cluster)) ? 1 : 0;
     uint32_t stage_bytes = p.tma_out ? (uint32_t)TC_MAX_GROUPS * 4u * 2048u : 0u;
     auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off - stage_bytes; };   // barriers + bias + alignment slack
     if (p.tma_out && !p.cluster && budget(TC_SMEM_LIMIT) < w_all + 2u * (uint32_t)p.a_stage_bytes) {

@@ -26,7 +26,9 @@ struct pb_tte {
     DevBuf work;                          // per-call activations
     DevBuf keep;                          // encoder output, cum durations, masks kept between encode and decode
     float* enc_out = nullptr; int32_t* cum = nullptr; int64_t* out_lens_dev = nullptr; int* err_flag = nullptr;
+    int32_t* tgt_lens32 = nullptr;        // unit count per item as i32 (decoder-side lens of the ragged mode)
     int enc_B = 0, enc_S = 0, enc_T = -1;
+    bool enc_ragged = false;              // the last encode ran in ragged mode: every item as if it were run alone
     int64_t last_launches = 0;
     float* P(const std::string& k) {
         auto it = slots.find(k);
@@ -267,19 +269,21 @@ static int tte_tc_gemm(const uint16_t* x, const uint8_t* w, const float* bias, c
 // FFTBlock.forward (fft.py:94-100) with the projections and the FFN convolutions on tcgen05 (split-fp16 operands, fp32
 // accumulation in TMEM, 3 passes per product); the residual stream, LayerNorm statistics and softmax stay fp32.
 static int run_fft_block_tc(pb_tte* h, const std::string& p, const float* x, const uint8_t* key_valid, int B, int L,
-                            const BlockWork& w, float* y, cudaStream_t st) {
+                            const BlockWork& w, float* y, cudaStream_t st, const int32_t* lens) {
     const pb_tte_cfg& c = h->cfg;
     const int D = c.d_model, F = c.conv_n_filter, H = c.n_head;
     const int M = B * L;
     auto TC = [&](const std::string& k) { return reinterpret_cast<const uint8_t*>(h->P(k)); };
-    PB_TRY(launch_layernorm_split(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn_s, M, D, st));
+    // lens (ragged mode): LayerNorm rows past an item's end are written as zeros - the zero padding its k = 9 convolution sees
+    // when the item is run alone; keys past the end are masked by key_valid, so nothing else of a short item sees the padding
+    PB_TRY(launch_layernorm_split(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn_s, M, D, st, lens, L));
     // q | k | v = LN(x) . Wqkv_eff^T   (rows flattened: a 1-tap GEMM has no sequence edges), kept as split-fp16 rows
     PB_TRY(tte_tc_gemm(w.xn_s, TC(p + ".attention.qkv_eff.tc"), nullptr, nullptr, w.qkv_s, nullptr, 1, M, D, 3 * D, 1, 0, st));
     // softmax(q.k^T / sqrt(dh) + mask) . v per (batch, head), fused on tcgen05 (attn_tc.cu): scores stay in tensor memory
     PB_TRY(launch_attention_tc(w.qkv_s, key_valid, w.o_s, B, L, H, D, st));
     // h = x + attn . Wo_eff^T
     PB_TRY(tte_tc_gemm(w.o_s, TC(p + ".attention.wo_eff.tc"), nullptr, x, nullptr, w.hbuf, 1, M, D, D, 1, 0, st));
-    PB_TRY(launch_layernorm_split(w.hbuf, h->P(p + ".conv_norm.weight"), h->P(p + ".conv_norm.bias"), w.xn_s, M, D, st));
+    PB_TRY(launch_layernorm_split(w.hbuf, h->P(p + ".conv_norm.weight"), h->P(p + ".conv_norm.bias"), w.xn_s, M, D, st, lens, L));
     // f = relu(conv1(LN(h)))  - per item ('same' zero padding at each sequence's own ends, fft.py:65-70)
     PB_TRY(tte_tc_gemm(w.xn_s, TC(p + ".convlayer.conv1.tc"), h->P(p + ".convlayer.conv1.bias"), nullptr, w.f_s, nullptr, B, L, D, F,
                        c.conv_k1, 1, st));
@@ -289,14 +293,14 @@ static int run_fft_block_tc(pb_tte* h, const std::string& p, const float* x, con
 }
 
 static int run_fft_block(pb_tte* h, const std::string& p, const float* x, const uint8_t* key_valid, int B, int L,
-                         const BlockWork& w, float* y, cudaStream_t st) {
+                         const BlockWork& w, float* y, cudaStream_t st, const int32_t* lens = nullptr) {
     const pb_tte_cfg& c = h->cfg;
     const int D = c.d_model, F = c.conv_n_filter, H = c.n_head, dh = D / H;
     const int M = B * L;
     const int Lp = (int)round_up(L, 4);
     const bool unfolded = !c.fold_projections;
-    if (c.gemm_mode == 1) return run_fft_block_tc(h, p, x, key_valid, B, L, w, y, st);
-    PB_TRY(launch_layernorm(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn, M, D, st));
+    if (c.gemm_mode == 1) return run_fft_block_tc(h, p, x, key_valid, B, L, w, y, st, lens);
+    PB_TRY(launch_layernorm(x, h->P(p + ".attn_norm.weight"), h->P(p + ".attn_norm.bias"), w.xn, M, D, st, lens, L));
     const float* qkv = w.qkv;
     {
         GemmArgs g;
@@ -342,7 +346,7 @@ static int run_fft_block(pb_tte* h, const std::string& p, const float* x, const 
         g.C = w.hbuf; g.ldc = D; g.res = x; g.ldres = D; g.M = M; g.N = D; g.K = D;
         PB_TRY(launch_sgemm(g, st));
     }
-    PB_TRY(launch_layernorm(w.hbuf, h->P(p + ".conv_norm.weight"), h->P(p + ".conv_norm.bias"), w.xn, M, D, st));
+    PB_TRY(launch_layernorm(w.hbuf, h->P(p + ".conv_norm.weight"), h->P(p + ".conv_norm.bias"), w.xn, M, D, st, lens, L));
     {   // f = relu(conv1(hn))
         GemmArgs g;
         g.A = w.xn; g.lda = D; g.B = h->P(p + ".convlayer.conv1.packed"); g.ldb = (int64_t)c.conv_k1 * D;
@@ -366,18 +370,20 @@ static int ensure_keep(pb_tte* h, int B, int S) {
     plan.take<int32_t>((size_t)B * S);
     plan.take<int64_t>(B);
     plan.take<int>(4);
+    plan.take<int32_t>(B);
     PB_TRY(h->keep.reserve(plan.off));
     Carver cv(h->keep.ptr);
     h->enc_out = cv.take<float>((size_t)B * S * h->cfg.d_model);
     h->cum = cv.take<int32_t>((size_t)B * S);
     h->out_lens_dev = cv.take<int64_t>(B);
     h->err_flag = cv.take<int>(4);
+    h->tgt_lens32 = cv.take<int32_t>(B);
     return PB_OK;
 }
 
 extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* src_mask, const int64_t* speaker,
-                             const int64_t* dur_in, int32_t B, int32_t S, float* log_dur, int64_t* dur, int64_t* out_lens,
-                             int32_t* T_host, void* stream) {
+                             const int64_t* dur_in, const int32_t* src_lens, int32_t B, int32_t S, float* log_dur, int64_t* dur,
+                             int64_t* out_lens, int32_t* T_host, void* stream) {
     PB_REQUIRE(h && phones && src_mask && log_dur && dur && out_lens && T_host, PB_ERR_INVALID, "pb_tte_encode: null argument");
     PB_REQUIRE(h->finalized, PB_ERR_STATE, "pb_tte_encode: weights not finalized");
     PB_REQUIRE(B > 0 && S > 0, PB_ERR_INVALID, "pb_tte_encode: bad shape B=%d S=%d", B, S);
@@ -405,18 +411,24 @@ extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* sr
         xa = cv.take<float>((size_t)M * D); xb = cv.take<float>((size_t)M * D);
         block_work_plan(cv, w, B, S, D, F, H, !c.fold_projections, c.gemm_mode == 1);
     }
-    PB_TRY(launch_embed_pos(phones, h->P("tok_emb.weight"), h->P("pos_emb.pe") + (size_t)S * D, c.src_vocab_size, M, D, xa, h->err_flag, st));
+    // ragged mode (src_lens given): every item is computed as if it were run alone - its own pe row, zero padding past its own end
+    // for the convolutions, exactly its own unit count of target positions.  src_mask must be the prefix mask t < src_lens[b].
+    const bool ragged = src_lens != nullptr;
+    PB_TRY(launch_embed_pos(phones, h->P("tok_emb.weight"), ragged ? h->P("pos_emb.pe") : h->P("pos_emb.pe") + (size_t)S * D, src_lens, S,
+                            c.src_vocab_size, M, D, xa, h->err_flag, st));
     float* cur = xa;
     for (int i = 0; i < c.n_enc_layer; ++i) {
         float* dst = (i + 1 == c.n_enc_layer) ? h->enc_out : (cur == xa ? xb : xa);
-        PB_TRY(run_fft_block(h, layer_prefix(0, i), cur, src_mask, B, S, w, dst, st));
+        PB_TRY(run_fft_block(h, layer_prefix(0, i), cur, src_mask, B, S, w, dst, st, src_lens));
         cur = dst;
     }
     if (c.n_enc_layer == 0) {
         PB_CUDA(cudaMemcpyAsync(h->enc_out, xa, (size_t)M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     if (c.n_speaker > 1)
-        PB_TRY(launch_add_indexed_row(h->enc_out, h->P("speaker_emb.weight"), speaker, c.n_speaker, B, S, D, h->err_flag, st));
+        PB_TRY(launch_add_indexed_row(h->enc_out, h->P("speaker_emb.weight"), speaker, c.n_speaker, B, S, D, h->err_flag, st, src_lens));
+    else if (ragged)      // zero the encoder output past every item's end (the duration predictor's conv padding)
+        PB_TRY(launch_add_indexed_row(h->enc_out, nullptr, nullptr, 0, B, S, D, h->err_flag, st, src_lens));
     // duration predictor (duration.py:41-48): conv3 -> relu -> LN -> conv3 (padding 1) -> relu -> LN -> proj
     {
         GemmArgs g;
@@ -424,7 +436,8 @@ extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* sr
         g.C = w.o; g.ldc = 256; g.bias = h->P("duration_predictor.layers.0.conv.bias"); g.relu = 1;
         g.M = M; g.N = 256; g.K = 3 * D; g.taps = 3; g.Cin = D; g.L = S; g.pad = 1;
         PB_TRY(launch_sgemm(g, st));
-        PB_TRY(launch_layernorm(w.o, h->P("duration_predictor.layers.2.weight"), h->P("duration_predictor.layers.2.bias"), w.xn, M, 256, st));
+        PB_TRY(launch_layernorm(w.o, h->P("duration_predictor.layers.2.weight"), h->P("duration_predictor.layers.2.bias"), w.xn, M, 256, st,
+                                src_lens, S));
         GemmArgs g2;
         g2.A = w.xn; g2.lda = 256; g2.B = h->P("duration_predictor.layers.4.conv.packed"); g2.ldb = 3 * 256;
         g2.C = w.o; g2.ldc = 256; g2.bias = h->P("duration_predictor.layers.4.conv.bias"); g2.relu = 1;
@@ -435,7 +448,7 @@ extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* sr
                                     log_dur, dur_in ? nullptr : dur, st));
     }
     if (dur_in && dur_in != dur) PB_CUDA(cudaMemcpyAsync(dur, dur_in, (size_t)M * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    PB_TRY(launch_duration_scan(dur, B, S, h->cum, h->out_lens_dev, st));
+    PB_TRY(launch_duration_scan(dur, B, S, h->cum, h->out_lens_dev, st, h->tgt_lens32));
     PB_CUDA(cudaMemcpyAsync(out_lens, h->out_lens_dev, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     std::vector<int64_t> lens_host(B);
     int flag = 0;
@@ -447,6 +460,7 @@ extern "C" int pb_tte_encode(pb_tte* h, const int64_t* phones, const uint8_t* sr
     int64_t T = 0;
     for (int b = 0; b < B; ++b) { PB_REQUIRE(lens_host[b] >= 0, PB_ERR_INVALID, "pb_tte_encode: negative duration"); T = std::max(T, lens_host[b]); }
     h->enc_B = B; h->enc_S = S; h->enc_T = (int)std::min<int64_t>(T, 0x7fffffff);
+    h->enc_ragged = ragged;
     *T_host = h->enc_T;
     PB_REQUIRE(T < c.max_len, PB_ERR_INDEX, "index %lld is out of bounds for dimension 0 with size %d (pos_emb.pe, unit length)", (long long)T, c.max_len);
     return PB_OK;
@@ -484,13 +498,15 @@ extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, const u
         block_work_plan(cv, w, B, T, D, F, H, !c.fold_projections, c.gemm_mode == 1);
     }
     uint8_t* mk = tgt_mask ? tgt_mask : mask;
-    PB_TRY(launch_length_regulate(h->enc_out, h->cum, h->P("pos_emb.pe") + (size_t)T * D, B, S, D, T, xa, mk, st));
+    const int32_t* tlens = h->enc_ragged ? h->tgt_lens32 : nullptr;
+    PB_TRY(launch_length_regulate(h->enc_out, h->cum, h->enc_ragged ? h->P("pos_emb.pe") : h->P("pos_emb.pe") + (size_t)T * D, B, S, D, T, xa,
+                                  mk, st, h->enc_ragged ? 1 : 0));
     // a caller-supplied target mask (teacher-forced path) is returned unchanged by the reference's length_regulator and is the
     // decoder's key padding mask (parrot.py:104,107; duration.py:22-24): it replaces the generated t <= len mask
     if (tgt_mask_in && tgt_mask_in != mk) PB_CUDA(cudaMemcpyAsync(mk, tgt_mask_in, (size_t)M, cudaMemcpyDeviceToDevice, st));
     float* cur = xa; float* nxt = xb;
     for (int i = 0; i < c.n_dec_layer; ++i) {
-        PB_TRY(run_fft_block(h, layer_prefix(1, i), cur, mk, B, T, w, nxt, st));
+        PB_TRY(run_fft_block(h, layer_prefix(1, i), cur, mk, B, T, w, nxt, st, tlens));
         std::swap(cur, nxt);
     }
     if (c.gemm_mode == 1) {

@@ -228,14 +228,16 @@ int launch_sgemm(const GemmArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embed_pos_kernel(const int64_t* __restrict__ phones, const float* __restrict__ tok_emb, const float* __restrict__ pe_row,
-                 int vocab, int M, float* __restrict__ out, int* err_flag) {
+                 const int32_t* __restrict__ lens, int L, int vocab, int M, float* __restrict__ out, int* err_flag) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
     long long id = phones[row];
     if (id < 0 || id >= vocab) { if (lane == 0 && err_flag) atomicExch(err_flag, 1); id = 0; }
     const float4* src = reinterpret_cast<const float4*>(tok_emb + (size_t)id * 256);
-    const float4* pe = reinterpret_cast<const float4*>(pe_row);
+    // ragged mode (lens != null): pe_row is the TABLE and every item takes the row of its OWN length - what the reference adds
+    // when the item is run alone (fft.py:18 indexes the table by the padded length, which is the item's length at batch 1)
+    const float4* pe = reinterpret_cast<const float4*>(lens ? pe_row + (size_t)lens[row / L] * 256 : pe_row);
     float4* dst = reinterpret_cast<float4*>(out + (size_t)row * 256);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -244,10 +246,10 @@ embed_pos_kernel(const int64_t* __restrict__ phones, const float* __restrict__ t
     }
 }
 
-int launch_embed_pos(const int64_t* phones, const float* tok_emb, const float* pe_row, int vocab, int M, int D, float* out,
-                     int* err_flag, cudaStream_t st) {
+int launch_embed_pos(const int64_t* phones, const float* tok_emb, const float* pe_row, const int32_t* lens, int L, int vocab, int M,
+                     int D, float* out, int* err_flag, cudaStream_t st) {
     PB_REQUIRE(D == 256, PB_ERR_INVALID, "embed: d_model=%d unsupported (256 expected)", D);
-    embed_pos_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(phones, tok_emb, pe_row, vocab, M, out, err_flag);
+    embed_pos_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(phones, tok_emb, pe_row, lens, L > 0 ? L : 1, vocab, M, out, err_flag);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -268,17 +270,21 @@ __device__ __forceinline__ void ln_row_256(const float4 v0, const float4 v1, flo
 
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float* __restrict__ y, int M) {
+                 float* __restrict__ y, int M, const int32_t* __restrict__ lens, int L) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
+    float4* dst = reinterpret_cast<float4*>(y + (size_t)row * 256);
+    if (lens && row % L >= lens[row / L]) {      // ragged mode: past the item's end the following convolution must see its zero padding
+        dst[lane] = make_float4(0.f, 0.f, 0.f, 0.f); dst[lane + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * 256);
     const float4 v0 = src[lane], v1 = src[lane + 32];
     float mean, rstd;
     ln_row_256(v0, v1, mean, rstd);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
-    float4* dst = reinterpret_cast<float4*>(y + (size_t)row * 256);
     const float4 g0 = g4[lane], g1 = g4[lane + 32], c0 = b4[lane], c1 = b4[lane + 32];
     dst[lane] = make_float4((v0.x - mean) * rstd * g0.x + c0.x, (v0.y - mean) * rstd * g0.y + c0.y,
                             (v0.z - mean) * rstd * g0.z + c0.z, (v0.w - mean) * rstd * g0.w + c0.w);
@@ -286,10 +292,11 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                                  (v1.z - mean) * rstd * g1.z + c1.z, (v1.w - mean) * rstd * g1.w + c1.w);
 }
 
-int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, cudaStream_t st) {
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, cudaStream_t st,
+                     const int32_t* lens, int L) {
     PB_REQUIRE(D == 256, PB_ERR_INVALID, "layernorm: width %d unsupported (256 expected)", D);
     PB_REQUIRE(M > 0, PB_ERR_INVALID, "layernorm: empty input");
-    layernorm_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, y, M);
+    layernorm_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, y, M, lens, L > 0 ? L : 1);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -309,10 +316,16 @@ __device__ __forceinline__ void split_h4(const float4 v, uint2& hi, uint2& lo) {
 // LayerNorm(256) with the result written in split-fp16 rows (the A operand of the following tensor-core GEMM)
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                       uint16_t* __restrict__ y, int M) {
+                       uint16_t* __restrict__ y, int M, const int32_t* __restrict__ lens, int L) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
+    uint2* dst = reinterpret_cast<uint2*>(y + (size_t)row * 512);     // 4 halves = 8 bytes per lane
+    if (lens && row % L >= lens[row / L]) {      // ragged mode: zero rows past the item's end (the k = 9 convolution's zero padding)
+        const uint2 z = make_uint2(0u, 0u);
+        dst[lane] = z; dst[lane + 32] = z; dst[64 + lane] = z; dst[96 + lane] = z;
+        return;
+    }
     const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * 256);
     const float4 v0 = src[lane], v1 = src[lane + 32];
     float mean, rstd;
@@ -327,15 +340,15 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ga
     uint2 h0, l0, h1, l1;
     split_h4(o0, h0, l0);
     split_h4(o1, h1, l1);
-    uint2* dst = reinterpret_cast<uint2*>(y + (size_t)row * 512);     // 4 halves = 8 bytes per lane
     dst[lane] = h0; dst[lane + 32] = h1;                              // hi: channels 4*lane.., 128 + 4*lane..
     dst[64 + lane] = l0; dst[96 + lane] = l1;                         // lo plane starts at element 256
 }
 
-int launch_layernorm_split(const float* x, const float* gamma, const float* beta, uint16_t* y, int M, int D, cudaStream_t st) {
+int launch_layernorm_split(const float* x, const float* gamma, const float* beta, uint16_t* y, int M, int D, cudaStream_t st,
+                           const int32_t* lens, int L) {
     PB_REQUIRE(D == 256, PB_ERR_INVALID, "layernorm: width %d unsupported (256 expected)", D);
     PB_REQUIRE(M > 0, PB_ERR_INVALID, "layernorm: empty input");
-    layernorm_split_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, y, M);
+    layernorm_split_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, y, M, lens, L > 0 ? L : 1);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -369,14 +382,19 @@ int launch_rows_to_split(const float* x, int64_t ldx, uint16_t* y, int64_t M, in
 
 __global__ void __launch_bounds__(256)
 add_indexed_row_kernel(float* __restrict__ x, const float* __restrict__ table, const int64_t* __restrict__ idx, int n_rows,
-                       int L, int M, int* err_flag) {
+                       int L, int M, int* err_flag, const int32_t* __restrict__ lens) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
+    float4* dst = reinterpret_cast<float4*>(x + (size_t)row * 256);
+    if (lens && row % L >= lens[row / L]) {      // ragged mode: the encoder output is zero past the item's end (duration-predictor conv padding)
+        dst[lane] = make_float4(0.f, 0.f, 0.f, 0.f); dst[lane + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    if (!table) return;
     long long id = idx[row / L];
     if (id < 0 || id >= n_rows) { if (lane == 0 && err_flag) atomicExch(err_flag, 2); id = 0; }
     const float4* src = reinterpret_cast<const float4*>(table + (size_t)id * 256);
-    float4* dst = reinterpret_cast<float4*>(x + (size_t)row * 256);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float4 a = dst[lane + 32 * h];
@@ -387,9 +405,9 @@ add_indexed_row_kernel(float* __restrict__ x, const float* __restrict__ table, c
 }
 
 int launch_add_indexed_row(float* x, const float* table, const int64_t* idx, int n_rows, int B, int L, int D, int* err_flag,
-                           cudaStream_t st) {
+                           cudaStream_t st, const int32_t* lens) {
     PB_REQUIRE(D == 256, PB_ERR_INVALID, "add_row: width %d unsupported", D);
-    add_indexed_row_kernel<<<(unsigned)ceil_div((int64_t)B * L, 8), 256, 0, st>>>(x, table, idx, n_rows, L, B * L, err_flag);
+    add_indexed_row_kernel<<<(unsigned)ceil_div((int64_t)B * L, 8), 256, 0, st>>>(x, table, idx, n_rows, L, B * L, err_flag, lens);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -475,7 +493,8 @@ int launch_duration_head(const float* x, const float* gamma, const float* beta, 
 
 // one block per item: inclusive scan of durations (S <= a few thousand)
 __global__ void __launch_bounds__(256)
-duration_scan_kernel(const int64_t* __restrict__ dur, int S, int32_t* __restrict__ cum, int64_t* __restrict__ out_lens) {
+duration_scan_kernel(const int64_t* __restrict__ dur, int S, int32_t* __restrict__ cum, int64_t* __restrict__ out_lens,
+                     int32_t* __restrict__ out_lens32) {
     __shared__ long long part[256];
     const int b = blockIdx.x;
     const int per = (S + 255) / 256;
@@ -492,11 +511,14 @@ duration_scan_kernel(const int64_t* __restrict__ dur, int S, int32_t* __restrict
         const int s = s0 + i;
         if (s < S) { run += dur[(size_t)b * S + s]; cum[(size_t)b * S + s] = (int32_t)(run > 0x7fffffffLL ? 0x7fffffffLL : run); }
     }
-    if (threadIdx.x == 255) out_lens[b] = base + local;
+    if (threadIdx.x == 255) {
+        out_lens[b] = base + local;
+        if (out_lens32) out_lens32[b] = (int32_t)(base + local > 0x7fffffffLL ? 0x7fffffffLL : base + local);
+    }
 }
 
-int launch_duration_scan(const int64_t* dur, int B, int S, int32_t* cum, int64_t* out_lens, cudaStream_t st) {
-    duration_scan_kernel<<<B, 256, 0, st>>>(dur, S, cum, out_lens);
+int launch_duration_scan(const int64_t* dur, int B, int S, int32_t* cum, int64_t* out_lens, cudaStream_t st, int32_t* out_lens32) {
+    duration_scan_kernel<<<B, 256, 0, st>>>(dur, S, cum, out_lens, out_lens32);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -504,7 +526,7 @@ int launch_duration_scan(const int64_t* dur, int B, int S, int32_t* cum, int64_t
 
 __global__ void __launch_bounds__(256)
 length_regulate_kernel(const float* __restrict__ seq, const int32_t* __restrict__ cum, const float* __restrict__ pe_row, int S,
-                       int T, int64_t rows, float* __restrict__ out, uint8_t* __restrict__ tgt_mask) {
+                       int T, int64_t rows, float* __restrict__ out, uint8_t* __restrict__ tgt_mask, int ragged) {
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -520,22 +542,25 @@ length_regulate_kernel(const float* __restrict__ seq, const int32_t* __restrict_
         a0 = src[lane]; a1 = src[lane + 32];
     }
     if (pe_row) {
-        const float4* pe = reinterpret_cast<const float4*>(pe_row);
+        // ragged mode: pe_row is the TABLE and the item takes the row of its own unit count (what it gets when run alone, fft.py:18)
+        const float4* pe = reinterpret_cast<const float4*>(ragged ? pe_row + (size_t)len * 256 : pe_row);
         const float4 p0 = pe[lane], p1 = pe[lane + 32];
         a0 = make_float4(p0.x + a0.x, p0.y + a0.y, p0.z + a0.z, p0.w + a0.w);
         a1 = make_float4(p1.x + a1.x, p1.y + a1.y, p1.z + a1.z, p1.w + a1.w);
     }
     float4* dst = reinterpret_cast<float4*>(out + (size_t)row * 256);
     dst[lane] = a0; dst[lane + 32] = a1;
-    if (lane == 0 && tgt_mask) tgt_mask[row] = (t <= len) ? 1 : 0;   // `<=`: reference data.py:18
+    // `<=`: reference data.py:18 (one extra live position for every item shorter than the batch maximum); run alone an item has
+    // exactly `len` positions (arange(len) <= len is all true), which is what the ragged mode reproduces
+    if (lane == 0 && tgt_mask) tgt_mask[row] = (ragged ? t < len : t <= len) ? 1 : 0;
 }
 
 int launch_length_regulate(const float* seq, const int32_t* cum, const float* pe_row, int B, int S, int D, int T, float* out,
-                           uint8_t* tgt_mask, cudaStream_t st) {
+                           uint8_t* tgt_mask, cudaStream_t st, int ragged) {
     PB_REQUIRE(D == 256, PB_ERR_INVALID, "length_regulate: width %d unsupported", D);
     const int64_t rows = (int64_t)B * T;
     if (rows == 0) return PB_OK;
-    length_regulate_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(seq, cum, pe_row, S, T, rows, out, tgt_mask);
+    length_regulate_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(seq, cum, pe_row, S, T, rows, out, tgt_mask, ragged);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;

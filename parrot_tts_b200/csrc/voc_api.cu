@@ -40,8 +40,8 @@ struct pb_voc {
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     bool ev_valid = false;
-    // PB_VOC_CHAINS=1 (experimental, off by default): the num_kernels ResBlock chains of a stage are independent until their
-    // outputs are summed, so each runs on its own stream and one chain's launch tails overlap the next chain's kernels
+    // chain streams (small forwards): the num_kernels ResBlock chains of a stage are independent until their outputs are summed,
+    // so each runs on its own stream and the chains' kernels fill the SMs side by side
     cudaStream_t chain_st[PB_VOC_MAX_RESK] = {};
     cudaEvent_t ev_fork = nullptr, ev_last[PB_VOC_MAX_RESK] = {};
     bool chains_ready = false;
@@ -310,11 +310,14 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
             slot_elems = std::max(slot_elems, (size_t)B * (size_t)L * 2 * (c0 >> (i + 1)));
         }
     }
-    // PB_VOC_CHAINS=1: chain j (ResBlock kernel size j) of every stage runs on its own stream with its own XT / XA / XB buffers
-    // (the last chain stays on the caller's stream); the running sum keeps its order k3 -> k7 -> k11, so results are bit-identical.
-    // Measured on B200 (profiles/r01_ab_chains.txt): bit-identical, 8.24 vs 8.30 ms at 8 x 1024 units - no gain at batch size, off by default.
-    static const bool chains_env = getenv("PB_VOC_CHAINS") != nullptr && atoi(getenv("PB_VOC_CHAINS")) != 0;
-    const bool chains = chains_env && c.num_kernels > 1 && c.num_kernels <= PB_VOC_MAX_RESK;
+    // Chain streams: chain j (ResBlock kernel size j) of every stage runs on its own stream with its own XT / XA / XB buffers (the
+    // last chain stays on the caller's stream); the running sum keeps its order k3 -> k7 -> k11, so results are bit-identical.
+    // Measured on B200: one utterance of 512 units 1.35 -> 1.13 ms (1.29 -> 1.01 ms replayed as a CUDA graph) - at that size the wide
+    // stages fill under a third of the SMs and three chains run side by side; 8 x 1024 units 8.30 -> 8.24 ms (nothing to fill).
+    // Default: on for small forwards (B x T <= 2048 units); PB_VOC_CHAINS=0 / 1 forces it off / on.
+    static const int chains_env = getenv("PB_VOC_CHAINS") ? atoi(getenv("PB_VOC_CHAINS")) : -1;
+    const bool chains_want = chains_env >= 0 ? chains_env != 0 : (int64_t)B * T <= 2048;
+    const bool chains = chains_want && c.num_kernels > 1 && c.num_kernels <= PB_VOC_MAX_RESK;
     constexpr int MAX_SLOTS = 4 + 3 * PB_VOC_MAX_RESK;
     const int n_slots = chains ? 4 + 3 * c.num_kernels : 7;        // X, XS, Y + the previous stage's Y, and (XT, XA, XB) per chain
     if (chains && !h->chains_ready) {

@@ -126,34 +126,52 @@ class SpeechPipeline:
     """``pipe = SpeechPipeline(parrot, generator); audio = pipe(phones, speakers)`` - character-token sequences in, per-utterance
     audio out: the whole hot path (demo.ipynb cells 11 + 13) for a pool of utterances, as one call.
 
-    The TTE runs one utterance per call - the reference's own inference mode (``DataLoader(batch_size=1)``, inference.py:31-37) and
-    the only batching whose result does not depend on the other items of the batch (the "positional" row is indexed by the PADDED
-    length, modules/fft.py:18) - and hands its unit ids to the vocoder ON THE DEVICE (``Parrot.infer_device``); the vocoder runs the
-    length-bucketed ragged batches of ``BatchSynthesizer``.  Under ``torch.distributed`` pass ``indices=rank_share_tte(...)``: each
+    The reference infers one utterance per call (``DataLoader(batch_size=1)``, inference.py:31-37) because a padded batch changes every
+    shorter item's result (the "positional" row is indexed by the PADDED length, modules/fft.py:18).  Here both stages run
+    length-bucketed RAGGED batches whose items each equal their batch-of-1 result (``Parrot.infer_ragged``, ``CodeGenerator(lens=)``),
+    and the unit ids go from the TTE to the vocoder ON THE DEVICE.  Under ``torch.distributed`` pass ``indices=rank_share_tte(...)``: each
     rank synthesises its longest-processing-time-first share, nothing is exchanged on the data path.
     """
 
-    def __init__(self, parrot, generator, **synth_kwargs):
+    def __init__(self, parrot, generator, tte_max_batch=16, tte_max_pad_ratio=1.25, **synth_kwargs):
         self.parrot = parrot
+        self.tte_max_batch, self.tte_max_pad_ratio = int(tte_max_batch), float(tte_max_pad_ratio)
         self.synth = BatchSynthesizer(generator, **synth_kwargs)
         self.last_units = None
         self.last_launches = 0
 
     def units(self, phones, speakers=None, indices=None):
-        """-> list of 1-D i64 device tensors of unit ids (``None`` outside ``indices``)."""
+        """-> list of 1-D i64 device tensors of unit ids (``None`` outside ``indices``).  Utterances are bucketed by character count
+        and run through ``Parrot.infer_ragged``: every item equals its own batch-of-1 result."""
         dev = self.synth._device()
-        idx = range(len(phones)) if indices is None else indices
+        idx = list(range(len(phones))) if indices is None else list(indices)
         out = [None] * len(phones)
         pad = self.parrot.src_pad_idx
+        seqs = {i: torch.as_tensor(phones[i], dtype=torch.long).reshape(-1) for i in idx}
+        n_chars = [int(seqs[i].numel()) if i in seqs else 0 for i in range(len(phones))]
         launches = 0
-        for i in idx:
-            ph = torch.as_tensor(phones[i], dtype=torch.long).reshape(1, -1)
-            if not ph.is_cuda:
-                ph = (ph.pin_memory() if ph.numel() else ph).to(dev, non_blocking=True)
-            spk = torch.tensor([0 if speakers is None else int(speakers[i])], dtype=torch.long).to(dev, non_blocking=True)
-            ids, n = self.parrot.infer_device({"phones": ph, "src_mask": ph != pad, "speaker": spk})
+        live = [i for i in idx if n_chars[i] > 0]
+        for b in sharding.length_buckets(live, n_chars, self.tte_max_batch, self.tte_max_pad_ratio):
+            Smax = n_chars[b[0]]
+            if all(seqs[i].is_cuda for i in b):
+                ph = torch.full((len(b), Smax), pad, dtype=torch.long, device=dev)
+                for r, i in enumerate(b):
+                    ph[r, :n_chars[i]] = seqs[i]
+            else:
+                host = torch.full((len(b), Smax), pad, dtype=torch.long).pin_memory()
+                for r, i in enumerate(b):
+                    host[r, :n_chars[i]] = seqs[i]
+                ph = host.to(dev, non_blocking=True)
+            lens = torch.tensor([n_chars[i] for i in b], dtype=torch.int32).to(dev, non_blocking=True)
+            spk = torch.tensor([0 if speakers is None else int(speakers[i]) for i in b], dtype=torch.long).to(dev, non_blocking=True)
+            ids, n_units = self.parrot.infer_ragged(ph, lens, spk)
             launches += self.parrot.last_launches
-            out[i] = ids[0]                           # batch of one: every position is live (n == T)
+            n_host = n_units.tolist()                  # one small D2H per bucket: the vocoder's batch plan needs the unit counts
+            for r, i in enumerate(b):
+                out[i] = ids[r, :n_host[r]]
+        for i in idx:
+            if out[i] is None:
+                out[i] = torch.zeros(0, dtype=torch.long, device=dev)
         self.last_launches = launches
         return out
 

@@ -83,7 +83,7 @@ class Parrot(nn.Module):
     def engine_adopt(self):
         self._eng.adopt(self._cfg_fields(), self._wstamp, self._arena_device)
 
-    def _encode(self, batch, dur_in=None):
+    def _encode(self, batch, dur_in=None, src_lens=None):
         phones = batch["phones"]
         need_cuda(phones, "Parrot.forward")
         if self.training:
@@ -101,11 +101,13 @@ class Parrot(nn.Module):
         out_lens = torch.empty(B, device=dev, dtype=torch.int64)
         if dur_in is not None:
             dur_in = dur_in.to(device=dev, dtype=torch.int64).contiguous()
+        if src_lens is not None:
+            src_lens = src_lens.to(device=dev, dtype=torch.int32).contiguous()
         T = C.c_int32(0)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().pb_tte_encode(hnd, _lib.ptr(phones), _lib.ptr(src_mask), _lib.ptr(speaker), _lib.ptr(dur_in),
-                                                 B, S, _lib.ptr(log_dur), _lib.ptr(dur), _lib.ptr(out_lens), C.byref(T),
-                                                 _lib.stream_ptr(dev)))
+                                                 _lib.ptr(src_lens), B, S, _lib.ptr(log_dur), _lib.ptr(dur), _lib.ptr(out_lens),
+                                                 C.byref(T), _lib.stream_ptr(dev)))
         self.last_launches = int(_lib.load().pb_tte_last_launches(hnd))
         return hnd, dev, B, S, int(T.value), log_dur, dur, out_lens
 
@@ -143,6 +145,32 @@ class Parrot(nn.Module):
         hnd, dev, B, S, T, _, _, out_lens = self._encode(batch)
         _, ids, _ = self._decode(hnd, dev, B, S, T, False, True)
         return ids, torch.clamp(out_lens + 1, max=T)
+
+    def infer_ragged(self, phones, lens, speaker=None, return_logits=False):
+        """Batched inference in which every item equals the reference's result for that item ALONE (its batch-of-1 inference mode,
+        inference.py:31-37): phones i64 [B, S] padded with ``src_pad_idx``, lens [B] = characters per item, speaker i64 [B].
+        -> (ids i64 [B, T], n_units i64 [B]), item b's units are ``ids[b, :n_units[b]]`` (exactly its own unit count - the extra
+        `<=` position of a padded batch does not exist for an item run alone).
+
+        In the reference a padded batch changes every shorter item's result (the "positional" row is indexed by the PADDED length,
+        modules/fft.py:18; padded positions feed the k = 9 convolutions; the target mask is ``t <= len``, modules/data.py:18), which
+        is why it infers one utterance at a time.  Here the kernels take each item's own length: its own ``pe`` rows, zeros past its
+        own end wherever a convolution looks, keys past its end masked - so a length-bucketed batch reproduces the one-at-a-time
+        results at batch throughput.  ``return_logits=True`` appends the logits f32 [B, T, n_codes] (rows past an item's end are
+        meaningless)."""
+        need_cuda(phones, "Parrot.infer_ragged")
+        dev = phones.device
+        lens = torch.as_tensor(lens).to(device=dev, dtype=torch.int32).reshape(-1)
+        B, S = phones.shape
+        if lens.numel() != B:
+            raise ValueError(f"lens must hold one length per item, got {lens.numel()} for batch {B}")
+        src_mask = torch.arange(S, device=dev).unsqueeze(0) < lens.unsqueeze(1)
+        batch = {"phones": phones, "src_mask": src_mask, "speaker": speaker if speaker is not None else torch.zeros(B, dtype=torch.long, device=dev)}
+        hnd, dev, B, S, T, _, _, out_lens = self._encode(batch, src_lens=lens)
+        if T == 0:
+            return torch.zeros(B, 0, dtype=torch.int64, device=dev), out_lens
+        logits, ids, _ = self._decode(hnd, dev, B, S, T, bool(return_logits), True)
+        return (ids, out_lens, logits) if return_logits else (ids, out_lens)
 
     def infer(self, batch):
         """-> list[list[int]]: per item the argmax unit ids at the positions its tgt_mask marks (reference parrot.py:112-120)."""

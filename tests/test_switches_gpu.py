@@ -1,6 +1,6 @@
 """Bitwise parity of the library's dev switches against the default path - none of them changes the arithmetic:
-  PB_VOC_CHAINS=1     the three ResBlock chains of a stage on three streams (measured: no gain at batch size, off by default)
-  PB_TC_TMA_OUT=3     TMA-store epilogue also on the CTA-pair layers with k <= 3
+  PB_VOC_CHAINS=0/1   the three ResBlock chains of a stage on three streams (default: on for forwards of <= 2048 units)
+  PB_TC_TMA_OUT=2     TMA-store epilogue on every eligible layer (default 1: the one-CTA-per-SM layers)
   PB_TC_EPI_SPLIT=0/2 column-split epilogue groups off / on every one-CTA-per-SM layer (default 1: the CTA-pair layers)
   PB_TC_CLUSTER=0     single-CTA path instead of CTA pairs
 Each case runs in a fresh interpreter because the library reads its switches once.
@@ -63,13 +63,15 @@ def baseline(tmp_path_factory):
 
 
 def test_chain_streams_are_bit_identical(tmp_path, baseline):
+    # the default runs the small cases with chain streams and the 8 x 300-unit one without: forced off / on must both agree with it
+    _same(baseline, _run(tmp_path, "nochains", {"PB_VOC_CHAINS": "0"}))
     got = _run(tmp_path, "chains", {"PB_VOC_CHAINS": "1"})
     _same(baseline, got)
     assert np.array_equal(got["graph"], got["graph_again"])          # fork / join survives CUDA-graph capture and replay
 
 
-def test_tma_store_on_k3_pair_layers_is_bit_identical(tmp_path, baseline):
-    _same(baseline, _run(tmp_path, "tma3", {"PB_TC_TMA_OUT": "3"}))
+def test_tma_store_epilogue_everywhere_is_bit_identical(tmp_path, baseline):
+    _same(baseline, _run(tmp_path, "tma2", {"PB_TC_TMA_OUT": "2"}))
 
 
 @pytest.mark.parametrize("mode", ["0", "2"])

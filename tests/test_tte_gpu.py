@@ -315,3 +315,34 @@ def test_single_speaker_parrot_matches_oracle():
     assert torch.allclose(log_dur.cpu(), r["log_dur"], atol=5e-5, rtol=0)
     assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0)
     assert m.infer(dev) == ids_ref
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_infer_ragged_equals_every_item_run_alone(mode):
+    """Parrot.infer_ragged: a padded batch in which every item is computed as the reference computes it ALONE (its inference mode,
+    inference.py:31-37) - own pe rows (fft.py:18), zeros past its own end under the k = 9 / k = 3 convolutions, exactly its own unit
+    count (no `<=` extra position).  Integer outputs bit-exact against the oracle run per item; logits BITWISE equal to this
+    library's own batch-of-1 forward (same kernels, same accumulation order per row)."""
+    cfg, sd, m = _parrot(seed=33)
+    m.gemm_mode = mode
+    g = _gen(12)
+    lens = [37, 20, 5, 37, 1, 29]
+    S = max(lens)
+    phones = torch.zeros(len(lens), S, dtype=torch.long)
+    for b, n in enumerate(lens):
+        phones[b, :n] = torch.randint(2, VOCAB, (n,), generator=g)
+    spk = torch.tensor([0, 9, 4, 2, 7, 1])
+    ids, n_units, logits = m.infer_ragged(phones.to(DEV), torch.tensor(lens), spk.to(DEV), return_logits=True)
+    n_units = n_units.tolist()
+    for b, n in enumerate(lens):
+        one = {"phones": phones[b:b + 1, :n], "src_mask": torch.ones(1, n, dtype=torch.bool), "speaker": spk[b:b + 1]}
+        ids_ref, r = tte_oracle.parrot_infer(sd, one)
+        assert n_units[b] == len(ids_ref[0]) == int(r["out_lens"][0])                  # durations bit-exact (integer path)
+        assert ids[b, :n_units[b]].cpu().tolist() == ids_ref[0], b
+        lg1, _, _, _ = m(_to_dev(one), inference=True)                                 # this library, batch of one
+        assert torch.equal(logits[b, :n_units[b]], lg1[0]), (b, float((logits[b, :n_units[b]] - lg1[0]).abs().max()))
+        assert torch.allclose(lg1[0].cpu(), r["logits"][0], atol=3e-3, rtol=0)
+    # the reference's own padded-batch semantics (src_lens = NULL) still run on the same handle afterwards
+    padded = m.infer({"phones": phones.to(DEV), "src_mask": (phones != 0).to(DEV), "speaker": spk.to(DEV)})
+    ids_pad, _ = tte_oracle.parrot_infer(sd, {"phones": phones, "src_mask": phones != 0, "speaker": spk})
+    assert [len(x) for x in padded] == [len(x) for x in ids_pad]
