@@ -100,8 +100,10 @@ def workload_shape(name):
 
 
 def cfg4_lengths():
+    """Unit count per utterance of the pool: L_i ~ U{256..4096} (numpy default_rng(0)), realised as ceil(L_i / 8) characters at 8 units
+    per character (the const8 duration recipe of SURVEY.md 8d) - i.e. rounded up to a multiple of 8."""
     import numpy as np
-    return [int(v) for v in np.random.default_rng(0).integers(256, 4097, CFG4_POOL)]
+    return [8 * ((int(v) + 7) // 8) for v in np.random.default_rng(0).integers(256, 4097, CFG4_POOL)]
 
 
 def config_block(name, world):
@@ -663,7 +665,7 @@ def cfg4_pool(torch):
     """The pool: (unit lengths, char-token sequences on the host, TTE speaker ids, vocoder voices) - identical on every rank."""
     lengths = cfg4_lengths()
     g = torch.Generator().manual_seed(7)
-    phones = [torch.randint(2, 150, ((n + 7) // 8,), generator=g) for n in lengths]      # dur == 8 units per char (const8 weights)
+    phones = [torch.randint(2, 150, (n // 8,), generator=g) for n in lengths]      # dur == 8 units per char (const8 weights)
     speakers = [i % 10 for i in range(len(lengths))]
     return lengths, phones, speakers
 
