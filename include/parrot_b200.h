@@ -221,6 +221,13 @@ int pb_length_regulate(const float* seq, const int64_t* dur, const float* pe_row
 /* Y[M,N] = X[M,K] . W[N,K]^T + bias, fp32 (nn.Linear). mode as pb_tte_cfg.gemm_mode. */
 int pb_linear(const float* x, const float* w, const float* bias, float* y, int32_t M, int32_t N, int32_t K, int32_t mode, void* stream);
 
+/* mel_spectrogram (utils/vocoder/dataset.py:43-69; spectral_normalize_torch :85-95) of audio on the device - the validation metric
+ * beside the sample tolerance: reflect padding by (n_fft - hop) / 2, STFT with the periodic Hann window
+ * (center = False; win must equal n_fft, a power of two in 256..2048), sqrt(re^2 + im^2 + 1e-9), mel_basis f32 [n_mels][1 + n_fft/2]
+ * (librosa.filters.mel layout), log(clamp(., 1e-5)).  y f32 [B, N] -> out f32 [B, n_mels, *frames].  out == NULL: size query only. */
+int pb_mel_spectrogram(const float* y, int32_t B, int64_t N, const float* mel_basis, int32_t n_fft, int32_t hop, int32_t win,
+                       int32_t n_mels, float* out, int32_t* frames, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU, weights broadcast once at init.
  * `comm` is an ncclComm_t passed as void*.  Must be called after *_finalize on root and after

@@ -70,6 +70,25 @@ def voc_case(name, code, spkr, seed=0, x=None):
     print(name, tuple(wav.shape), "abs max", float(wav.abs().max()), "rms", float(wav.pow(2).mean().sqrt()))
 
 
+def mel_case(name, seed=0):
+    """The reference's own mel_spectrogram (utils/vocoder/dataset.py:43-69) at the shipped config (n_fft 1024, hop 256, 80 mels,
+    16 kHz, 0..8000 Hz) on noise + a chirp; the librosa mel basis (absent here) is the oracle's restatement - see ref_shim."""
+    from oracle import mel_oracle
+    ref = ref_shim.load_reference_mel_spectrogram(
+        lambda sr, n_fft, n_mels, fmin, fmax: mel_oracle.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax))
+    g = torch.Generator().manual_seed(seed)
+    n = 16384
+    t = torch.arange(n, dtype=torch.float64) / 16000.0
+    chirp = torch.sin(2 * torch.pi * (200.0 * t + 1500.0 * t * t)).float()
+    y = torch.stack([0.5 * chirp + 0.05 * torch.randn(n, generator=g), 0.8 * (torch.rand(n, generator=g) * 2 - 1)])
+    y[1, 9000:] = 0.0                                     # a silent tail: exercises the clamp at 1e-5
+    with torch.no_grad():
+        mel = ref(y, 1024, 80, 16000, 256, 1024, 0, 8000)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), y=y.numpy(), mel=mel.numpy().astype(np.float32), seed=np.int64(seed),
+                        torch_version=str(torch.__version__))
+    print(name, tuple(mel.shape), "range", float(mel.min()), float(mel.max()))
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -96,6 +115,7 @@ def main():
     ph[2, 97:] = PAD
     ph[3, 31:] = PAD
     tte_case("tte_b4_s256_ragged", ph, [1, 8, 0, 5], seed=2, stride=128)
+    mel_case("mel_b2_n16384")
 
 
 if __name__ == "__main__":

@@ -72,3 +72,29 @@ def load_reference_vocoder(h):
         _purge({"modules", "utils", "models"})
         for k, v in saved_mods.items():
             sys.modules.setdefault(k, v)
+
+
+def load_reference_mel_spectrogram(mel_fn):
+    """The reference's own ``mel_spectrogram`` (utils/vocoder/dataset.py:43-69), imported from where it lies.  Its module imports
+    amfm_decompy, soundfile and librosa at the top (none installed, none used by this function except ``librosa.filters.mel``):
+    they are stubbed, and ``librosa.filters.mel`` is ``mel_fn`` - so everything but the mel BASIS (padding, STFT, magnitude, log)
+    is the reference's code; the basis is the oracle's restatement of the published librosa algorithm (parity-unpinned)."""
+    saved_path, saved_mods = list(sys.path), dict(sys.modules)
+    try:
+        _purge({"dataset", "librosa", "amfm_decompy", "soundfile"})
+        for name in ("amfm_decompy", "amfm_decompy.basic_tools", "amfm_decompy.pYAAPT", "soundfile", "librosa", "librosa.filters", "librosa.util"):
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["amfm_decompy"].basic_tools = sys.modules["amfm_decompy.basic_tools"]
+        sys.modules["amfm_decompy"].pYAAPT = sys.modules["amfm_decompy.pYAAPT"]
+        sys.modules["librosa"].filters = sys.modules["librosa.filters"]
+        sys.modules["librosa"].util = sys.modules["librosa.util"]
+        sys.modules["librosa.filters"].mel = mel_fn
+        sys.modules["librosa.util"].normalize = lambda x, **k: x
+        sys.path.insert(0, os.path.join(REF_ROOT, "utils", "vocoder"))
+        ds = importlib.import_module("dataset")
+        return ds.mel_spectrogram
+    finally:
+        sys.path[:] = saved_path
+        _purge({"dataset", "librosa", "amfm_decompy", "soundfile"})
+        for k, v in saved_mods.items():
+            sys.modules.setdefault(k, v)

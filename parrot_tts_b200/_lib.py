@@ -57,6 +57,7 @@ SIGNATURES = {
     "pb_voc_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     "pb_voc_forward_pcm16": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "pb_wav_to_pcm16": (C.c_int, [_P, _I64, _P, _P]),
+    "pb_mel_spectrogram": (C.c_int, [_P, _I32, _I64, _P, _I32, _I32, _I32, _I32, _P, C.POINTER(_I32), _P]),
     "pb_pcm16_peak_normalize": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "pb_voc_last_launches": (_I64, [_P]),
     "pb_voc_memory_epoch": (_I64, [_P]),

@@ -69,3 +69,26 @@ def test_generator_oracle_matches_golden(golden_dir):
 def test_int16_truncates_toward_zero():
     y = torch.tensor([[0.5 / 32768 * 3, -0.5 / 32768 * 3, 0.99997]])
     assert voc_oracle.to_int16(y).tolist() == [1, -1, 32767]
+
+
+def test_mel_oracle_matches_golden(golden_dir):
+    """The golden file holds the output of the reference's own mel_spectrogram (utils/vocoder/dataset.py:43-69) with the oracle's
+    mel basis standing in for the absent librosa call."""
+    from oracle import mel_oracle
+    g = _load(golden_dir, "mel_b2_n16384")
+    mel = mel_oracle.mel_spectrogram(torch.from_numpy(g["y"]), 1024, 80, 16000, 256, 1024, 0, 8000)
+    assert mel.shape == g["mel"].shape == (2, 80, 64)
+    np.testing.assert_allclose(mel.numpy(), g["mel"], rtol=0, atol=1e-5)
+    assert float(g["mel"].min()) == pytest.approx(np.log(1e-5), abs=1e-6)       # the clamp is exercised
+
+
+def test_mel_filterbank_product_and_oracle_restatements_agree():
+    """Two independent restatements of librosa.filters.mel's published algorithm (vectorised in the product, loop form in the
+    oracle): identical float32 matrices, unit-area Slaney triangles."""
+    from oracle import mel_oracle
+    from parrot_tts_b200.vocoder.mel import mel_filterbank
+    for sr, n_fft, n_mels, fmin, fmax in ((16000, 1024, 80, 0, 8000), (22050, 1024, 80, 0, None), (16000, 512, 40, 50, 7600)):
+        a, b = mel_filterbank(sr, n_fft, n_mels, fmin, fmax), mel_oracle.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+        assert a.dtype == np.float32 and a.shape == (n_mels, 1 + n_fft // 2)
+        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9)
+        assert (a >= 0).all() and (a.sum(1) > 0).all()

@@ -178,3 +178,15 @@ def test_checkpoint_layouts_are_interchangeable_with_the_reference():
     ours_v.load_state_dict(b, strict=True)
     for k in b:                                      # and the folded weights really are the reference's g * v / ||v||
         assert torch.equal(ours_v.state_dict()[k], b[k])
+
+
+def test_mel_oracle_vs_reference_function():
+    # the reference's own mel_spectrogram (utils/vocoder/dataset.py:43-69), imported with its absent top-level imports stubbed
+    from oracle import mel_oracle
+    ref = ref_shim.load_reference_mel_spectrogram(
+        lambda sr, n_fft, n_mels, fmin, fmax: mel_oracle.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax))
+    y = (torch.rand(3, 5000, generator=torch.Generator().manual_seed(3)) * 2 - 1) * 0.9
+    a = ref(y, 1024, 80, 16000, 256, 1024, 0, 8000)
+    b = mel_oracle.mel_spectrogram(y, 1024, 80, 16000, 256, 1024, 0, 8000)
+    assert a.shape == b.shape == (3, 80, 19)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=0, atol=1e-6)

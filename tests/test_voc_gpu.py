@@ -459,3 +459,33 @@ def test_speech_pipeline_equals_one_utterance_at_a_time():
     assert [p is not None for p in part] == [i in shares[1] for i in range(5)]
     for i in shares[1]:
         assert np.array_equal(part[i], audio[i])
+
+
+def test_mel_spectrogram_matches_reference_golden(golden_dir):
+    """Device log-mel (pb_mel_spectrogram) against the output of the reference's own function (utils/vocoder/dataset.py:43-69)
+    recorded in tests/golden; tolerance 2e-3 in the log domain (fp32 radix-2 FFT vs torch.stft; the basis itself is parity-unpinned)."""
+    from parrot_tts_b200.vocoder.mel import mel_spectrogram
+    g = np.load(os.path.join(golden_dir, "mel_b2_n16384.npz"))
+    got = mel_spectrogram(torch.from_numpy(g["y"]).to(DEV), 1024, 80, 16000, 256, 1024, 0, 8000).cpu().numpy()
+    assert got.shape == g["mel"].shape
+    err = np.abs(got - g["mel"])
+    assert err.max() < 2e-3, float(err.max())
+    with pytest.raises(NotImplementedError):
+        mel_spectrogram(torch.zeros(1, 4096, device=DEV), 1024, 80, 16000, 256, 1024, 0, 8000, center=True)
+
+
+def test_mel_distance_of_generated_audio_vs_oracle():
+    """The metric in use: log-mel of the waveform this library generates vs log-mel of the oracle's waveform for the same units -
+    the mel-L1 the reference's training loop reports (train.py:135-137), here as a parity figure beside the sample tolerance."""
+    from oracle import mel_oracle
+    from parrot_tts_b200.vocoder.mel import mel_spectrogram
+    h, sd, gen = _code_generator(0, mode=1)
+    g = _gen(61)
+    code = torch.randint(0, 1000, (2, 40), generator=g)
+    spkr = torch.randint(0, 10, (2, 1), generator=g)
+    wav = gen(code=code.to(DEV), spkr=spkr.to(DEV))
+    ref = voc_oracle.code_generator_forward(sd, h, code, spkr)
+    m_dev = mel_spectrogram(wav.squeeze(1), h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax).cpu()
+    m_ref = mel_oracle.mel_spectrogram(ref.squeeze(1), h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax)
+    assert m_dev.shape == m_ref.shape
+    assert float((m_dev - m_ref).abs().mean()) < 1e-3, float((m_dev - m_ref).abs().mean())
