@@ -39,7 +39,13 @@ struct TcConvArgs {
     int n_groups = 0;                      // epilogue warpgroups per CTA (0 = choose)
     int fmt = 0;                           // split storage + MMA operand type of x / w / res / accin / out: 0 = bf16, 1 = fp16
     const float* res_f32 = nullptr;        // [B][U*L][out_C] fp32 residual (added like res, no activation to undo) or null
+    // fused row argmax (U == 1): key[b*L + t] = max over columns n < argmax_n of (order-preserving bits of v[t, n]) << 32 | ~n, merged
+    // with atomicMax (zero the keys first; tc_argmax_unpack turns them into indices - first maximum, like torch.argmax).  out and
+    // out_f32 may then both be null: the GEMM result never reaches HBM.
+    unsigned long long* argmax_key = nullptr;
+    int argmax_n = 0;
 };
+int tc_argmax_unpack(const unsigned long long* key, int64_t M, int64_t* ids, cudaStream_t st);
 
 int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)
 size_t tc_packed_weight_bytes(int Cin, int N, int K);

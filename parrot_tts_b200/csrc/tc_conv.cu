@@ -42,6 +42,8 @@ struct TcParams {
     __nv_bfloat16* out;
     float* out_f32;
     const int32_t* lens;
+    unsigned long long* argmax_key;   // fused row argmax (see TcConvArgs::argmax_key) or null
+    int argmax_n;
     int len_mul;
     int B, L, Cin, N, NT, n_tiles_n, out_C, U;
     int K, D, pad;
@@ -391,7 +393,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 
         // Tile coordinates advance incrementally by gridDim.x tiles (no division per tile); the valid length of a batch
         // item is read from global memory only when the item changes.
-        struct TileCtx { int b, rem, nt, orow0, valid_rows; size_t row_el; bool ok, row_ok; };
+        struct TileCtx { int b, rem, nt, orow0, valid_rows; size_t row_el, row_idx; bool ok, row_ok; };
         const int n_tiles_n = p.n_tiles_n;
         auto valid_of = [&](int b) {
             int valid = Lout;
@@ -405,7 +407,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const int t = tt * ROWS_PER_TILE + (int)rank * TC_M + row;
             c.row_ok = t < p.L;
             c.orow0 = t * p.U;
-            c.row_el = ((size_t)c.b * Lout + c.orow0) * out_pitch;
+            c.row_idx = (size_t)c.b * Lout + c.orow0;
+            c.row_el = c.row_idx * out_pitch;
         };
         auto locate_first = [&](int tile, TileCtx& c) {
             c.ok = tile < p.total_tiles;
@@ -458,6 +461,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         if (cur.ok) item(cur, n0_first, off, co, live);
         uint4 R[4], A[4];
         request(cur.ok && cur.row_ok, off, R, A);
+        float best_v = -INFINITY;      // fused argmax: this thread's running maximum over its items of the current tile
+        int best_c = 0;
         while (cur.ok) {
             // next item
             TileCtx nxt = cur;
@@ -566,6 +571,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 if (p.tanh_out) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+                }
+                if (!RES && !ACC && p.argmax_key) {      // (plain GEMM instantiations only: keeps the residual variants' registers)
+                    // argmax over the row as an epilogue (Parrot.infer's torch.argmax, parrot.py:115): the logits never reach HBM.  A
+                    // thread keeps the first maximum of its own columns (visited in increasing order) and publishes it once per tile
+                    // with a 64-bit atomicMax on (order-preserving bits of the value, ~column): ties resolve to the lowest column.
+                    if (n0 == n0_first) { best_v = -INFINITY; best_c = 0; }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x = v[i] + 0.f;                    // -0 -> +0: equal under float comparison, equal keys
+                        if (co + i < p.argmax_n && x > best_v) { best_v = x; best_c = co + i; }
+                    }
+                    if (n0n == n0_first) {
+                        const uint32_t bits = __float_as_uint(best_v);
+                        const uint32_t ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+                        atomicMax(p.argmax_key + cur.row_idx, ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (uint32_t)best_c));
+                    }
                 }
                 if (p.out && !(p.ablate & 2)) {
 #pragma unroll
@@ -708,7 +729,9 @@ int tc_make_tmap_out(CUtensorMap* map, __nv_bfloat16* base, int C, int L, int B,
 }
 
 int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
-    PB_REQUIRE(a.x && a.w && (a.out || a.out_f32), PB_ERR_INVALID, "tc_conv: null tensor");
+    PB_REQUIRE(a.x && a.w && (a.out || a.out_f32 || a.argmax_key), PB_ERR_INVALID, "tc_conv: null tensor");
+    PB_REQUIRE(!a.argmax_key || (a.U == 1 && a.argmax_n > 0 && a.argmax_n <= a.N && !a.res && !a.accin), PB_ERR_INVALID,
+               "tc_conv: fused argmax needs U = 1, 0 < argmax_n <= N and no residual / running sum");
     PB_REQUIRE(a.B > 0 && a.L > 0 && a.K >= 1 && a.D >= 1 && a.U >= 1, PB_ERR_INVALID, "tc_conv: bad shape");
     const int cin_t = tc_cin_tile(a.Cin);
     const int NT = tc_n_tile(a.N);
@@ -718,6 +741,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     PB_REQUIRE((a.K - 1) * a.D % 2 == 0, PB_ERR_INVALID, "tc_conv: (K-1)*D must be even ('same' padding)");
     TcParams p{};
     p.w = a.w; p.bias = a.bias; p.res = a.res; p.res_f32 = a.res_f32; p.accin = a.accin; p.out = a.out; p.out_f32 = a.out_f32; p.lens = a.lens;
+    p.argmax_key = a.argmax_key; p.argmax_n = a.argmax_n;
     p.len_mul = a.len_mul;
     p.B = a.B; p.L = a.L; p.Cin = a.Cin; p.N = a.N; p.NT = NT; p.n_tiles_n = a.N / NT; p.out_C = a.out_C; p.U = a.U;
     p.K = a.K; p.D = a.D; p.pad = (a.K - 1) * a.D / 2;
@@ -1104,6 +1128,21 @@ __global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* 
 int launch_split_to_f32(const __nv_bfloat16* x, float* y, int64_t pitch, int B, int C, int L, cudaStream_t st) {
     dim3 grid((unsigned)ceil_div(L, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
     split_to_f32_kernel<<<grid, 256, 0, st>>>(x, y, pitch, C, L);
+    PB_COUNT_LAUNCH();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// keys written by the fused argmax epilogue -> ids (the column is stored complemented so that atomicMax prefers the lowest index)
+__global__ void argmax_unpack_kernel(const unsigned long long* __restrict__ key, int64_t M, int64_t* __restrict__ ids) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
+        ids[i] = (int64_t)(0xffffffffu - (uint32_t)(key[i] & 0xffffffffull));
+}
+
+int tc_argmax_unpack(const unsigned long long* key, int64_t M, int64_t* ids, cudaStream_t st) {
+    if (M <= 0) return PB_OK;
+    const int blocks = (int)(ceil_div(M, 256) < 1184 ? ceil_div(M, 256) : 1184);
+    argmax_unpack_kernel<<<blocks, 256, 0, st>>>(key, M, ids);
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -484,16 +484,22 @@ extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, const u
     const int M = (int)M64;
     BlockWork w;
     float *xa, *xb, *lg = nullptr, *lgp = nullptr; uint8_t* mask;
+    unsigned long long* keys = nullptr;
+    // ids only (Parrot.infer): the head GEMM takes the argmax in its epilogue and the [M, 1024] logits (268 MB at 32 x 2048 units)
+    // never reach HBM; they are materialised only when the caller asks for them (Parrot.forward)
+    const bool fused_argmax = c.gemm_mode == 1 && ids != nullptr && logits == nullptr;
     {
         Carver plan(nullptr);
         plan.take<float>((size_t)M * D); plan.take<float>((size_t)M * D); plan.take<uint8_t>(M);
-        if (c.gemm_mode == 1) plan.take<float>((size_t)M * round_up(c.n_codes, 256));
+        if (fused_argmax) plan.take<unsigned long long>(M);
+        else if (c.gemm_mode == 1) plan.take<float>((size_t)M * round_up(c.n_codes, 256));
         else if (!logits) plan.take<float>((size_t)M * c.n_codes);
         block_work_plan(plan, w, B, T, D, F, H, !c.fold_projections, c.gemm_mode == 1);
         PB_TRY(h->work.reserve(plan.off));
         Carver cv(h->work.ptr);
         xa = cv.take<float>((size_t)M * D); xb = cv.take<float>((size_t)M * D); mask = cv.take<uint8_t>(M);
-        if (c.gemm_mode == 1) { lgp = cv.take<float>((size_t)M * round_up(c.n_codes, 256)); lg = nullptr; }
+        if (fused_argmax) keys = cv.take<unsigned long long>(M);
+        else if (c.gemm_mode == 1) { lgp = cv.take<float>((size_t)M * round_up(c.n_codes, 256)); lg = nullptr; }
         else lg = logits ? logits : cv.take<float>((size_t)M * c.n_codes);
         block_work_plan(cv, w, B, T, D, F, H, !c.fold_projections, c.gemm_mode == 1);
     }
@@ -513,6 +519,17 @@ extern "C" int pb_tte_decode(pb_tte* h, int32_t B, int32_t S, int32_t T, const u
         // head on tcgen05: N padded to a multiple of 256 (zero rows), logits land in a padded scratch
         const int np = (int)round_up(c.n_codes, 256);
         PB_TRY(launch_rows_to_split(cur, D, w.xn_s, M, D, st));
+        if (fused_argmax) {
+            PB_CUDA(cudaMemsetAsync(keys, 0, (size_t)M * sizeof(unsigned long long), st));
+            TcConvArgs a;
+            a.x = reinterpret_cast<const __nv_bfloat16*>(w.xn_s); a.w = reinterpret_cast<const uint8_t*>(h->P("head.weight.tc"));
+            a.bias = h->P("head.bias.pad"); a.argmax_key = keys; a.argmax_n = c.n_codes;
+            a.B = 1; a.L = M; a.Cin = D; a.N = np; a.out_C = np; a.U = 1; a.K = 1; a.D = 1; a.fmt = 1;
+            PB_TRY(launch_tc_conv(a, st));
+            PB_TRY(tc_argmax_unpack(keys, M, ids, st));
+            h->last_launches = g_launch_count - launches0;
+            return PB_OK;
+        }
         PB_TRY(tte_tc_gemm(w.xn_s, reinterpret_cast<const uint8_t*>(h->P("head.weight.tc")), h->P("head.bias.pad"), nullptr, nullptr, lgp,
                            1, M, D, np, 1, 0, st));
         if (ids) PB_TRY(launch_argmax(lgp, M, c.n_codes, np, ids, st));

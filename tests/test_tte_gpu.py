@@ -346,3 +346,28 @@ def test_infer_ragged_equals_every_item_run_alone(mode):
     padded = m.infer({"phones": phones.to(DEV), "src_mask": (phones != 0).to(DEV), "speaker": spk.to(DEV)})
     ids_pad, _ = tte_oracle.parrot_infer(sd, {"phones": phones, "src_mask": phones != 0, "speaker": spk})
     assert [len(x) for x in padded] == [len(x) for x in ids_pad]
+
+
+def test_fused_head_argmax_equals_argmax_of_the_logits():
+    """Parrot.infer asks for ids only: the head GEMM takes the row argmax in its epilogue (64-bit atomicMax keys, first maximum on
+    ties) and the logits never reach HBM.  Same accumulators, same bias add -> exactly torch.argmax of the logits Parrot.forward
+    returns (reference modules/parrot.py:108,115), on a batch large enough for several N tiles, epilogue groups and CTA pairs."""
+    cfg, sd, m = _parrot(seed=44, dur_mode="const8")
+    g = _gen(13)
+    phones = torch.randint(2, VOCAB, (5, 70), generator=g)
+    phones[3, 41:] = 0
+    batch = _to_dev({"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([0, 1, 2, 3, 4])})
+    logits, _, tgt_mask, _ = m(batch, inference=True)
+    ids, n_valid = m.infer_device(batch)
+    assert ids.shape == logits.shape[:2] == (5, 560)
+    assert torch.equal(ids, torch.argmax(logits, dim=-1))
+    assert int(ids.max()) < 1000 and int(ids.min()) >= 0               # the 24 zero-padded head columns can never win
+    # ties: with the head zeroed every logit is 0 -> the first index wins, as in torch.argmax
+    with torch.no_grad():
+        m.head.weight.zero_(); m.head.bias.zero_()
+    ids0, _ = m.infer_device(batch)
+    assert int(ids0.abs().max()) == 0
+    with torch.no_grad():
+        m.head.bias[7] = -0.0; m.head.bias[3] = 1.0; m.head.bias[900] = 1.0
+    ids1, _ = m.infer_device(batch)
+    assert torch.equal(ids1, torch.full_like(ids1, 3))
