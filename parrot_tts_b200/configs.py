@@ -52,6 +52,8 @@ _VOC_DEFAULT = {
     "code_hop_size": 320,
     "multispkr": "_",
     "sampling_rate": 16000,
+    # mel_spectrogram parameters (reference utils/vocoder/config.json:26-36; validation metric, vocoder/mel.py)
+    "num_mels": 80, "n_fft": 1024, "hop_size": 256, "win_size": 1024, "fmin": 0, "fmax": 8000,
 }
 
 
