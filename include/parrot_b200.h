@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 2
+#define PB_ABI_VERSION 3
 
 typedef enum pb_status {
     PB_OK = 0,

@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(lib_path):
 def test_ctypes_table_matches_header(lib_path):
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.pb_version() == 2
+    assert lib.pb_version() == 3
     assert lib.pb_last_error() is not None
 
 
