@@ -110,7 +110,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.pb_version() != 2:
+    if lib.pb_version() != 3:
         raise ParrotB200Error(f"ABI version mismatch: library reports {lib.pb_version()}")
     _lib = lib
     return lib

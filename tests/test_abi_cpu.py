@@ -188,4 +188,4 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert r.stdout.startswith("2 ")
+    assert r.stdout.startswith("3 ")

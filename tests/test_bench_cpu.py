@@ -56,9 +56,9 @@ def test_peaks_reader_tolerates_the_driver_file(tmp_path, monkeypatch):
 
 
 def test_roofline_model_reproduces_the_committed_table():
-    """profiles/r01_model_vs_measured.txt is `tools/roofline_model.py` over the two committed launch lists: the tool still runs and
+    """profiles/r02_model_vs_measured.txt is `tools/roofline_model.py` over the two committed launch lists: the tool still runs and
     pairs every expected launch with a measured one (80 vocoder launches, 67 TTE launches), floors below the measured times."""
-    for args, n_launches in ((["profiles/r01_launches_voc_cfg2.csv"], 80), (["profiles/r01_launches_tte_cfg3.csv", "--tte"], 67)):
+    for args, n_launches in ((["profiles/r02_launches_voc_cfg2.csv"], 80), (["profiles/r02_launches_tte_cfg3.csv", "--tte"], 67)):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "roofline_model.py")] + args, capture_output=True, text=True,
                              timeout=120, cwd=ROOT)
         assert out.returncode == 0, out.stderr
@@ -69,7 +69,7 @@ def test_roofline_model_reproduces_the_committed_table():
         assert total[0] == "total"
         meas, floor, frac = float(total[1]), float(total[4]), float(total[5])
         assert 0.3 < frac < 1.0 and floor < meas
-        assert " ".join(lines[-1].split()) in " ".join(open(os.path.join(ROOT, "profiles", "r01_model_vs_measured.txt")).read().split())
+        assert " ".join(lines[-1].split()) in " ".join(open(os.path.join(ROOT, "profiles", "r02_model_vs_measured.txt")).read().split())
 
 
 def test_chain_schedule_is_hazard_free():

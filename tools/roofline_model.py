@@ -108,8 +108,10 @@ def expected_tte(B, S, T, d=256, ff=1024, k1=9, heads=2, n_layers=4, n_codes=100
     for i in range(n_layers):
         out += block(f"dec{i}", Md, T)
     out.append(dict(name="rows -> split", bytes=Md * d * (F32 + EL), cycles=0))
-    out.append(gemm(f"head {d}->{n_codes}", Md, d, 1, n_codes, False))
-    out.append(dict(name="argmax", bytes=Md * n_codes * F32 + Md * 8, cycles=0))
+    head = gemm(f"head {d}->{n_codes} + argmax epilogue", Md, d, 1, n_codes, False)
+    head["bytes"] = Md * d * EL + Md * 8          # reads the split rows, writes one 64-bit (value, index) key per row: no logits in HBM
+    out.append(head)
+    out.append(dict(name="argmax keys -> ids", bytes=Md * 16, cycles=0))
     return out
 
 
