@@ -27,7 +27,7 @@ def gpu(fn, n=30):
     torch.cuda.synchronize(); e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
-print("tte.infer_device      wall %.3f ms" % wall(lambda: tte.infer_device(batch)))
+print("tte.infer_device      wall %.3f ms   back-to-back %.3f ms" % (wall(lambda: tte.infer_device(batch)), gpu(lambda: tte.infer_device(batch))))
 print("tte._encode only      wall %.3f ms" % wall(lambda: tte._encode(batch)))
 print("voc forward           wall %.3f ms   back-to-back %.3f ms" % (wall(lambda: voc(code=ids, spkr=sp1)), gpu(lambda: voc(code=ids, spkr=sp1))))
 print("voc graph (+pcm)      wall %.3f ms   back-to-back %.3f ms" % (wall(lambda: gg(ids, sp1)), gpu(lambda: gg(ids, sp1))))
