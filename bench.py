@@ -112,7 +112,7 @@ def config_block(name, world):
     cfg = {"workload": shape["workload"], "n_ranks": world,
            "l2": "GPU arm: 256 MB flush write before every timed step; the per-step activation working set (> 5 GB) exceeds the 126 MB L2",
            "sharding": ("one batch of the workload per rank (weak scaling)" if name != "cfg4" else
-                        "the pool is split over the ranks by longest-processing-time-first on the utterance cost (strong scaling)") +
+                        "the pool is bucketed by length, the buckets go to the ranks longest-processing-time-first (strong scaling)") +
                        ", weights broadcast once at init, no per-step collective",
            "reference_arm_sample": "one utterance of the workload per step (the reference's own batch-of-1 inference mode), all host threads"}
     if name == "cfg4":
@@ -688,84 +688,82 @@ def cfg4_pool(torch):
 
 
 def run_cfg4(args):
-    """BASELINE configs[3]: 256 utterances of 256..4096 units, text -> wav, sharded data-parallel by longest-processing-time-first on
-    their cost; per rank the TTE runs its utterances one at a time (the reference's inference mode), the vocoder in length buckets
-    (each item masked to its own length = its batch-of-1 result); no collective on the data path.  value = true (unpadded) samples
-    of ALL ranks / the slowest rank's time."""
+    """BASELINE configs[3]: 256 utterances of 256..4096 units, text -> wav, sharded data-parallel: the pool is bucketed globally by
+    length, the buckets go to the ranks longest-processing-time-first (serving.plan_shares), and every bucket runs through both stages
+    as one ragged batch in which each item equals its batch-of-1 result (serving.SpeechPipeline); no collective on the data path.
+    value = true (unpadded) samples of ALL ranks / the slowest rank's time."""
     b = Bench()
     torch, dev, voc, tte = b.torch, b.dev, b.voc, b.tte
     from parrot_tts_b200 import serving
     steps, warmup = args.steps, max(args.warmup, 3)
     lengths, phones_h, speakers = cfg4_pool(torch)
-    mine = serving.rank_share_tte(lengths, b.world, b.rank)
-    pipe = serving.SpeechPipeline(tte, voc, max_batch=8, long_form_units=None)
+    est = [8 * int(p.numel()) for p in phones_h]          # what a scheduler knows before the TTE ran: 8 units per character
+    shares = serving.plan_shares(est, b.world, max_batch=8, max_pad_ratio=1.1)
+    mine = shares[b.rank]
+    my_idx = [i for bk in mine for i in bk]
+    pipe = serving.SpeechPipeline(tte, voc, max_batch=8, max_pad_ratio=1.1)
     phones_pin = [p.pin_memory() for p in phones_h]
     phones_dev = [p.to(dev) for p in phones_h]
-    my_units = sum(lengths[i] for i in mine)
+    my_units = sum(lengths[i] for i in my_idx)
     total_units = sum(lengths)
     res = {}
 
     def step_dev():       # inputs resident in HBM, waveforms left on the device as f32
-        res["wav"] = pipe(phones_dev, speakers, indices=mine, pcm16=False, to_host=False)
+        res["wav"] = pipe(phones_dev, speakers, batches=mine, pcm16=False, to_host=False)
 
     def step_e2e():       # pinned host char tokens -> int16 PCM of every utterance on the host
-        res["pcm"] = pipe(phones_pin, speakers, indices=mine, pcm16=True, to_host=True)
+        res["pcm"] = pipe(phones_pin, speakers, batches=mine, pcm16=True, to_host=True)
 
     step_dev()
     torch.cuda.synchronize()
     got = sum(int(w.numel()) for w in res["wav"] if w is not None)
     assert got == my_units * HOP, (got, my_units)
-    launches_per_step = pipe.last_launches + pipe.synth.last_launches
-    plan = pipe.synth.last_plan
+    launches_per_step = pipe.last_launches
     sampler = ClockSampler(b.local)
     ms_step = b.timed(step_dev, warmup, steps, sampler)
     value = total_units * HOP / (ms_step * 1e-3)
     e2e_ms = b.timed(step_e2e, warmup, steps)
-    h2d = sum(phones_h[i].numel() * 8 + 8 + 8 for i in mine)
-    d2h = sum(int(a.size) * 2 for a in res["pcm"] if a is not None)
+    h2d = sum(phones_h[i].numel() * 8 + 4 + 8 + 8 for i in my_idx)
+    d2h = sum(len(bk) * max(lengths[i] for i in bk) * HOP * 2 + len(bk) * 8 for bk in mine)      # padded int16 blocks + unit counts
     e2e = {"value": total_units * HOP / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_ms, "bytes_are": "rank 0's share",
-           "api": "parrot_tts_b200.serving.SpeechPipeline(parrot, generator)(phones, speakers, indices=rank share) -> int16 PCM on host"}
+           "api": "parrot_tts_b200.serving.SpeechPipeline(parrot, generator)(phones, speakers, batches=plan_shares(...)[rank]) -> int16 PCM on host"}
 
-    # ---- roofline of the ResBlock family: one more pass over this rank's vocoder batches with the section events on (reading them
-    # synchronises, so this pass is not the timed one; same batches, same kernels) ---------------------------------------------
-    units_dev = pipe.units(phones_dev, speakers, mine)
+    # ---- roofline of the ResBlock family: one more pass over this rank's buckets with the section events on (reading them synchronises,
+    # so this pass is not the timed one; same buckets, same kernels) --------------------------------------------------------------
     voc.set_timing(True, dev)
-    sec_acc, padded_units, rb_steps = {}, 0, 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    voc_ms = 0.0
-    for bt in plan["batches"]:
-        idx = [mine[k] for k in bt]
-        Lmax = lengths[idx[0]]
-        codes = torch.zeros(len(idx), Lmax, dtype=torch.long, device=dev)
-        for r, i in enumerate(idx):
-            codes[r, :lengths[i]] = units_dev[i]
-        lens = torch.tensor([lengths[i] for i in idx], dtype=torch.int32, device=dev)
-        spk = torch.tensor([[speakers[i]] for i in idx], dtype=torch.long, device=dev)
-        b.flush.fill_(1)
-        ev0.record()
-        voc(code=codes, spkr=spk, lens=lens)
-        ev1.record()
+    sec_acc, stat = {}, {"padded": 0, "n": 0}
+
+    def read_sections(bucket, padded_units):
         for k, v in voc.section_ms().items():
             sec_acc[k] = sec_acc.get(k, 0.0) + v
-        voc_ms += ev0.elapsed_time(ev1)
-        padded_units += len(idx) * Lmax
-        rb_steps += 1
+        stat["padded"] += padded_units
+        stat["n"] += 1
+
+    pipe.on_vocoder_forward = read_sections
+    b.flush.fill_(1)
+    step_dev()
+    torch.cuda.synchronize()
+    pipe.on_vocoder_forward = None
     voc.set_timing(False, dev)
+    voc_ms = sum(sec_acc.values())
     roofline = resblock_roofline(b, sec_acc, my_units, voc_ms, "cfg4")
-    roofline["bytes_per_launch_avg"] = sum(RESBLOCK_BYTES_PER_UNIT) * my_units / (N_RB_LAUNCH * rb_steps)
-    roofline["ms_per_launch_avg"] = sum(sec_acc[f"resblocks{i}"] for i in range(5)) / (N_RB_LAUNCH * rb_steps)
-    roofline["share_of_step"] = sum(sec_acc[f"resblocks{i}"] for i in range(5)) / ms_step
-    roofline["note"] = (f"rank 0's {rb_steps} vocoder batches ({my_units} true units, {padded_units} padded) in a separate pass with section "
-                        "events; bytes counted on TRUE units (padding is waste, not credit)")
+    rb_ms = sum(sec_acc[f"resblocks{i}"] for i in range(5))
+    roofline["bytes_per_launch_avg"] = sum(RESBLOCK_BYTES_PER_UNIT) * my_units / (N_RB_LAUNCH * stat["n"])
+    roofline["ms_per_launch_avg"] = rb_ms / (N_RB_LAUNCH * stat["n"])
+    roofline["share_of_step"] = rb_ms / ms_step
+    roofline["note"] = (f"rank 0's {stat['n']} buckets ({my_units} true units, {stat['padded']} padded) in a separate pass with section events; "
+                        "bytes counted on TRUE units (padding is waste, not credit)")
 
     extras = {}
     if b.world > 1 and not args.no_extras:
         # strong-scaling reference point measured in the same run: rank 0 alone synthesises the WHOLE pool while the others wait
         if b.rank == 0:
-            everything = list(range(len(lengths)))
+            everything = serving.plan_shares(est, 1, max_batch=8, max_pad_ratio=1.1)[0]
+
             def step_all():
-                pipe(phones_dev, speakers, indices=everything, pcm16=False, to_host=False)
+                pipe(phones_dev, speakers, batches=everything, pcm16=False, to_host=False)
+
             step_all()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -778,13 +776,12 @@ def run_cfg4(args):
     cpu = None
     if b.rank == 0 and b.world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample("cfg4")
-    costs = None
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": b.world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic (seeded random weights, random char tokens)", "config": config_block("cfg4", b.world),
         "rtf_16k": value / 16000.0, "rtf_22k05": value / 22050.0, "timed_region_s": ms_step * steps * 1e-3,
-        "rank0": {"utterances": len(mine), "units": my_units, "padded_units": padded_units, "vocoder_batches": rb_steps},
+        "rank0": {"utterances": len(my_idx), "units": my_units, "padded_units": stat["padded"], "buckets": stat["n"]},
         "e2e": e2e, "gpu_launches": int(launches_per_step * steps), "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
     }

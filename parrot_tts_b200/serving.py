@@ -127,64 +127,127 @@ class SpeechPipeline:
     audio out: the whole hot path (demo.ipynb cells 11 + 13) for a pool of utterances, as one call.
 
     The reference infers one utterance per call (``DataLoader(batch_size=1)``, inference.py:31-37) because a padded batch changes every
-    shorter item's result (the "positional" row is indexed by the PADDED length, modules/fft.py:18).  Here both stages run
-    length-bucketed RAGGED batches whose items each equal their batch-of-1 result (``Parrot.infer_ragged``, ``CodeGenerator(lens=)``),
-    and the unit ids go from the TTE to the vocoder ON THE DEVICE.  Under ``torch.distributed`` pass ``indices=rank_share_tte(...)``: each
-    rank synthesises its longest-processing-time-first share, nothing is exchanged on the data path.
+    shorter item's result (the "positional" row is indexed by the PADDED length, modules/fft.py:18).  Here a BUCKET of utterances of
+    similar length goes through both stages as one ragged batch whose items each equal their batch-of-1 result
+    (``Parrot.infer_ragged`` -> ``CodeGenerator(lens=)``): the padded unit ids and the per-item unit counts go from the TTE to the
+    vocoder ON THE DEVICE as they are (no re-bucketing, no host round trip), int16 PCM comes out of ``conv_post``'s epilogue, and the
+    host reads the unit counts only after every bucket has been launched.  Under ``torch.distributed`` pass
+    ``batches=plan_shares(...)[rank]``: each rank synthesises its share of the buckets, nothing is exchanged on the data path.
     """
 
-    def __init__(self, parrot, generator, tte_max_batch=16, tte_max_pad_ratio=1.25, **synth_kwargs):
+    def __init__(self, parrot, generator, max_batch=8, max_pad_ratio=1.1, **synth_kwargs):
         self.parrot = parrot
-        self.tte_max_batch, self.tte_max_pad_ratio = int(tte_max_batch), float(tte_max_pad_ratio)
-        self.synth = BatchSynthesizer(generator, **synth_kwargs)
+        self.generator = generator
+        self.max_batch, self.max_pad_ratio = int(max_batch), float(max_pad_ratio)
+        self.synth = BatchSynthesizer(generator, max_batch=max_batch, **synth_kwargs)      # the vocoder-only front door (kept for callers)
         self.last_units = None
         self.last_launches = 0
+        self.last_batches = None
+        self.on_vocoder_forward = None      # optional callback(bucket indices, padded units) after each vocoder launch (profiling hooks)
 
-    def units(self, phones, speakers=None, indices=None):
-        """-> list of 1-D i64 device tensors of unit ids (``None`` outside ``indices``).  Utterances are bucketed by character count
-        and run through ``Parrot.infer_ragged``: every item equals its own batch-of-1 result."""
-        dev = self.synth._device()
+    def _device(self):
+        return next(self.generator.parameters()).device
+
+    def plan(self, phones, indices=None):
+        """Buckets (lists of utterance indices, longest first, shortest item within ``max_pad_ratio`` of the longest, at most
+        ``max_batch`` items) over the utterances in ``indices`` - by character count, the only length known before the TTE ran."""
         idx = list(range(len(phones))) if indices is None else list(indices)
-        out = [None] * len(phones)
-        pad = self.parrot.src_pad_idx
-        seqs = {i: torch.as_tensor(phones[i], dtype=torch.long).reshape(-1) for i in idx}
-        n_chars = [int(seqs[i].numel()) if i in seqs else 0 for i in range(len(phones))]
-        launches = 0
-        live = [i for i in idx if n_chars[i] > 0]
-        for b in sharding.length_buckets(live, n_chars, self.tte_max_batch, self.tte_max_pad_ratio):
-            Smax = n_chars[b[0]]
-            if all(seqs[i].is_cuda for i in b):
+        n_chars = [int(torch.as_tensor(p).numel()) for p in phones]
+        return sharding.length_buckets([i for i in idx if n_chars[i] > 0], n_chars, self.max_batch, self.max_pad_ratio)
+
+    def __call__(self, phones, speakers=None, vocoder_speakers=None, pcm16=True, normalize=False, indices=None, to_host=True, batches=None):
+        """phones: list of 1-D char-token sequences (host or device); speakers / vocoder_speakers: TTE speaker and vocoder voice per
+        utterance.  ``batches`` (explicit buckets, e.g. a rank's share from ``plan_shares``) or ``indices`` select the utterances; the
+        result list is aligned with ``phones`` (``None`` for the others).  Audio per utterance: int16 PCM (``pcm16``), float32
+        peak-normalised (``normalize``) or the raw float32 waveform; numpy arrays when ``to_host`` else device tensors."""
+        if normalize and not pcm16:
+            raise ValueError("normalize=True normalises the int16 audio (as the reference does): it needs pcm16=True")
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("SpeechPipeline needs its models on a CUDA device (there is no CPU path)")
+        explicit = batches is not None
+        if not explicit:
+            batches = self.plan(phones, indices)
+        vs = speakers if vocoder_speakers is None else vocoder_speakers
+        pad, hop = self.parrot.src_pad_idx, self.generator.hop
+        multispkr = bool(getattr(self.generator, "multispkr", None))
+        launches, pending = 0, []
+        for b in batches:
+            seqs = [torch.as_tensor(phones[i], dtype=torch.long).reshape(-1) for i in b]
+            n_chars = [int(q.numel()) for q in seqs]
+            Smax = max(n_chars)
+            if all(q.is_cuda for q in seqs):
                 ph = torch.full((len(b), Smax), pad, dtype=torch.long, device=dev)
-                for r, i in enumerate(b):
-                    ph[r, :n_chars[i]] = seqs[i]
+                for r, q in enumerate(seqs):
+                    ph[r, :n_chars[r]] = q
             else:
                 host = torch.full((len(b), Smax), pad, dtype=torch.long).pin_memory()
-                for r, i in enumerate(b):
-                    host[r, :n_chars[i]] = seqs[i]
+                for r, q in enumerate(seqs):
+                    host[r, :n_chars[r]] = q
                 ph = host.to(dev, non_blocking=True)
-            lens = torch.tensor([n_chars[i] for i in b], dtype=torch.int32).to(dev, non_blocking=True)
+            lens = torch.tensor(n_chars, dtype=torch.int32).to(dev, non_blocking=True)
             spk = torch.tensor([0 if speakers is None else int(speakers[i]) for i in b], dtype=torch.long).to(dev, non_blocking=True)
-            ids, n_units = self.parrot.infer_ragged(ph, lens, spk)
+            ids, n_units = self.parrot.infer_ragged(ph, lens, spk)            # ids i64 [B, Tmax] padded, n_units i64 [B]: stay on the device
             launches += self.parrot.last_launches
-            n_host = n_units.tolist()                  # one small D2H per bucket: the vocoder's batch plan needs the unit counts
+            out = None
+            if ids.shape[1] > 0:
+                kw = {"code": ids, "lens": n_units.to(torch.int32)}
+                if multispkr:
+                    kw["spkr"] = torch.tensor([[0 if vs is None else int(vs[i])] for i in b], dtype=torch.long).to(dev, non_blocking=True)
+                out = self.generator.forward_pcm16(**kw) if pcm16 else self.generator(**kw)      # [B, 1, hop * Tmax], zero past each item's end
+                launches += self.generator.last_launches
+                if self.on_vocoder_forward is not None:
+                    self.on_vocoder_forward(b, int(ids.shape[0] * ids.shape[1]))
+            pending.append((b, ids, n_units, out))
+        # everything is launched: only now read the unit counts (one small D2H per bucket) and cut the utterances out
+        result = [None] * len(phones)
+        units = [None] * len(phones)
+        for b, ids, n_units, out in pending:
+            n_host = n_units.tolist()
+            host_block = ops.to_host(out) if (to_host and out is not None and not normalize) else None
             for r, i in enumerate(b):
-                out[i] = ids[r, :n_host[r]]
-        for i in idx:
-            if out[i] is None:
-                out[i] = torch.zeros(0, dtype=torch.long, device=dev)
-        self.last_launches = launches
-        return out
+                n = int(n_host[r])
+                units[i] = ids[r, :n]
+                if out is None or n == 0:
+                    a = torch.zeros(0, dtype=torch.int16 if pcm16 and not normalize else torch.float32)
+                    result[i] = a.numpy() if to_host else a.to(dev)
+                elif host_block is not None:
+                    result[i] = host_block[r, 0, :n * hop]
+                else:
+                    a = out[r, 0, :n * hop]
+                    if normalize:
+                        a = ops.peak_normalize(a.contiguous())
+                        launches += 2
+                    result[i] = ops.to_host(a) if to_host else a
+        if not explicit:       # utterances of the selection that have no characters: empty audio, no launch
+            wanted = range(len(phones)) if indices is None else indices
+            covered = {i for b in batches for i in b}
+            for i in wanted:
+                if i not in covered and torch.as_tensor(phones[i]).numel() == 0:
+                    units[i] = torch.zeros(0, dtype=torch.long, device=dev)
+                    a = torch.zeros(0, dtype=torch.int16 if pcm16 and not normalize else torch.float32)
+                    result[i] = a.numpy() if to_host else a.to(dev)
+        self.last_units, self.last_launches, self.last_batches = units, launches, [list(b) for b in batches]
+        return result
 
-    def __call__(self, phones, speakers=None, vocoder_speakers=None, pcm16=True, normalize=False, indices=None, to_host=True):
-        units = self.units(phones, speakers, indices)
-        self.last_units = units
-        idx = list(range(len(phones))) if indices is None else list(indices)
-        vs = speakers if vocoder_speakers is None else vocoder_speakers
-        audio = self.synth([units[i] for i in idx], None if vs is None else [vs[i] for i in idx], pcm16=pcm16, normalize=normalize,
-                           to_host=to_host)
+    def units(self, phones, speakers=None, indices=None):
+        """TTE only: -> list of 1-D i64 device tensors of unit ids (``None`` outside ``indices``)."""
+        dev = self._device()
+        pad = self.parrot.src_pad_idx
         out = [None] * len(phones)
-        for i, a in zip(idx, audio):
-            out[i] = a
+        launches = 0
+        for b in self.plan(phones, indices):
+            seqs = [torch.as_tensor(phones[i], dtype=torch.long).reshape(-1) for i in b]
+            n_chars = [int(q.numel()) for q in seqs]
+            ph = torch.full((len(b), max(n_chars)), pad, dtype=torch.long, device=dev)
+            for r, q in enumerate(seqs):
+                ph[r, :n_chars[r]] = q.to(dev)
+            spk = torch.tensor([0 if speakers is None else int(speakers[i]) for i in b], dtype=torch.long, device=dev)
+            ids, n_units = self.parrot.infer_ragged(ph, torch.tensor(n_chars, dtype=torch.int32, device=dev), spk)
+            launches += self.parrot.last_launches
+            for r, (i, n) in enumerate(zip(b, n_units.tolist())):
+                out[i] = ids[r, :int(n)]
+        self.last_launches = launches
         return out
 
 
@@ -192,3 +255,16 @@ def rank_share_tte(unit_lengths, world_size, rank):
     """Indices of the utterances rank ``rank`` runs end to end (LPT on the TTE + vocoder cost; same on every rank)."""
     costs = [sharding.utterance_cost(n, with_tte=True) for n in unit_lengths]
     return sorted(sharding.lpt_assign(costs, world_size)[rank])
+
+
+def plan_shares(unit_estimates, world_size, max_batch=8, max_pad_ratio=1.1):
+    """-> per rank, a list of buckets (lists of utterance indices): the pool is bucketed GLOBALLY by length first (so that every
+    bucket is full and tightly padded whatever the number of ranks), then the buckets go to the ranks longest-processing-time-first
+    on their padded cost.  Splitting utterance by utterance instead leaves every rank a thin mix of all lengths: at 8 ranks the
+    256-utterance pool of BASELINE configs[3] then pays 9.6 % of padded work on the slowest rank against 2.6 % this way.
+    ``unit_estimates``: expected unit count per utterance (e.g. 8 x its characters); a pure function, identical on every rank."""
+    idx = [i for i in range(len(unit_estimates)) if unit_estimates[i] > 0]
+    buckets = sharding.length_buckets(idx, unit_estimates, max_batch, max_pad_ratio)
+    costs = [len(b) * sharding.utterance_cost(max(unit_estimates[i] for i in b), with_tte=True) for b in buckets]
+    assign = sharding.lpt_assign(costs, world_size)
+    return [[buckets[k] for k in sorted(assign[r])] for r in range(world_size)]

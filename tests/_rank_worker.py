@@ -54,9 +54,10 @@ def main():
     nbytes = sharding.broadcast_engines([voc, tte], src=0, device=dev)
     phones, spk = pool()
     unit_lens = [8 * int(p.numel()) for p in phones]                 # cost estimate only (the share must not depend on results)
-    mine = serving.rank_share_tte(unit_lens, world, rank)
+    buckets = serving.plan_shares(unit_lens, world, max_batch=3, max_pad_ratio=1.25)[rank]
+    mine = sorted(i for b in buckets for i in b)
     pipe = serving.SpeechPipeline(tte, voc, max_batch=3)
-    audio = pipe(phones, spk, indices=mine)
+    audio = pipe(phones, spk, batches=buckets)
     assert [a is not None for a in audio] == [i in mine for i in range(len(phones))]
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), **{f"u{i}": audio[i] for i in mine}, broadcast_bytes=np.int64(nbytes))
     dist.barrier()

@@ -211,3 +211,29 @@ def test_receptive_field_radius_on_the_oracle():
     lo_u, hi_u = int(touched.min()) // hop, int(touched.max()) // hop
     assert mid - 24 <= lo_u <= mid and mid <= hi_u <= mid + 24, (lo_u, hi_u)
     assert hi_u - lo_u >= 20                               # and it really is that wide: a halo of a few units would not do
+
+
+def test_plan_shares_buckets_globally_then_balances():
+    """serving.plan_shares: the pool is bucketed by length FIRST (full, tightly padded buckets whatever the number of ranks), then the
+    buckets are spread longest-processing-time-first.  A partition of the pool, identical on every rank, padding and imbalance bounded
+    on the BASELINE configs[3] pool - and better than splitting utterance by utterance and bucketing per rank."""
+    from parrot_tts_b200 import serving
+    lengths = [8 * ((int(v) + 7) // 8) for v in np.random.default_rng(0).integers(256, 4097, 256)]
+    cost = lambda n: sharding.utterance_cost(n, with_tte=True)
+    ideal = sum(cost(n) for n in lengths)
+    for world in (1, 2, 4, 8):
+        shares = serving.plan_shares(lengths, world, max_batch=8, max_pad_ratio=1.1)
+        assert shares == serving.plan_shares(lengths, world, max_batch=8, max_pad_ratio=1.1)        # deterministic: no communication needed
+        flat = sorted(i for rank in shares for b in rank for i in b)
+        assert flat == list(range(256))
+        loads = []
+        for rank in shares:
+            for b in rank:
+                assert 1 <= len(b) <= 8 and lengths[b[0]] == max(lengths[i] for i in b) and lengths[b[0]] <= 1.1 * min(lengths[i] for i in b)
+            loads.append(sum(len(b) * cost(lengths[b[0]]) for b in rank))
+        assert max(loads) <= 1.05 * ideal / world, (world, max(loads) / (ideal / world))
+        # the utterance-by-utterance split pays more padded work on its slowest rank
+        bins = sharding.lpt_assign([cost(n) for n in lengths], world)
+        per_rank = [sum(len(b) * cost(lengths[b[0]]) for b in sharding.length_buckets(bins[r], lengths, 8, 1.25)) for r in range(world)]
+        assert max(loads) <= max(per_rank)
+    assert serving.plan_shares([0, 5, 0], 2) == [[[1]], []]                      # empty utterances are nobody's work

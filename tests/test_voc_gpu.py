@@ -452,6 +452,14 @@ def test_speech_pipeline_equals_one_utterance_at_a_time():
         assert pipe.last_units[i].cpu().tolist() == ids_ref[0]                      # integer path: bit-exact vs the oracle
         ref, _ = generate(h, gen, dict(code=torch.tensor([ids_ref[0]], device=DEV), spkr=torch.tensor([[spk[i]]], device=DEV)))
         assert np.array_equal(audio[i], ref), i
+    assert sorted(i for b in pipe.last_batches for i in b) == list(range(5)) and all(len(b) <= 2 for b in pipe.last_batches)
+    f32 = pipe(phones, spk, pcm16=False, to_host=False)                              # raw waveform, left on the device
+    for i in range(5):
+        assert f32[i].is_cuda and f32[i].dtype == torch.float32
+        assert np.array_equal(voc_oracle.to_int16(f32[i].cpu()), audio[i])
+    nrm = pipe(phones, spk, normalize=True)
+    from parrot_tts_b200.vocoder import normalize as _normalize
+    assert np.array_equal(nrm[3], _normalize(audio[3]))
     lens = [int(u.numel()) for u in pipe.last_units]
     shares = [rank_share_tte(lens, 2, r) for r in range(2)]
     assert sorted(shares[0] + shares[1]) == list(range(5))
