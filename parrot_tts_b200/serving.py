@@ -144,6 +144,7 @@ class SpeechPipeline:
         self.last_launches = 0
         self.last_batches = None
         self.on_vocoder_forward = None      # optional callback(bucket indices, padded units) after each vocoder launch (profiling hooks)
+        self._copy_stream = None
 
     def _device(self):
         return next(self.generator.parameters()).device
@@ -171,7 +172,9 @@ class SpeechPipeline:
         vs = speakers if vocoder_speakers is None else vocoder_speakers
         pad, hop = self.parrot.src_pad_idx, self.generator.hop
         multispkr = bool(getattr(self.generator, "multispkr", None))
-        launches, pending = 0, []
+        launches, staged, pending = 0, [], []
+        # phase 1: the TTE of every bucket (its encode reads the unit count back - the only synchronisation on the path - while the
+        # queue holds nothing but short TTE work); phase 2: the vocoder of every bucket, back to back with no synchronisation at all
         for b in batches:
             seqs = [torch.as_tensor(phones[i], dtype=torch.long).reshape(-1) for i in b]
             n_chars = [int(q.numel()) for q in seqs]
@@ -189,6 +192,8 @@ class SpeechPipeline:
             spk = torch.tensor([0 if speakers is None else int(speakers[i]) for i in b], dtype=torch.long).to(dev, non_blocking=True)
             ids, n_units = self.parrot.infer_ragged(ph, lens, spk)            # ids i64 [B, Tmax] padded, n_units i64 [B]: stay on the device
             launches += self.parrot.last_launches
+            staged.append((b, ids, n_units))
+        for b, ids, n_units in staged:
             out = None
             if ids.shape[1] > 0:
                 kw = {"code": ids, "lens": n_units.to(torch.int32)}
@@ -198,13 +203,30 @@ class SpeechPipeline:
                 launches += self.generator.last_launches
                 if self.on_vocoder_forward is not None:
                     self.on_vocoder_forward(b, int(ids.shape[0] * ids.shape[1]))
-            pending.append((b, ids, n_units, out))
-        # everything is launched: only now read the unit counts (one small D2H per bucket) and cut the utterances out
+            # the bucket's audio block and unit counts leave for pinned host memory on a copy stream, behind the next buckets' kernels
+            host_block = host_n = None
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(done)
+                host_n = torch.empty(n_units.shape, dtype=n_units.dtype, pin_memory=True)
+                host_n.copy_(n_units, non_blocking=True)
+                n_units.record_stream(self._copy_stream)
+                if to_host and out is not None and not normalize:
+                    host_block = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                    host_block.copy_(out, non_blocking=True)
+                    out.record_stream(self._copy_stream)
+            pending.append((b, ids, host_n, out, host_block))
+        # everything is launched: only now wait for the unit counts and cut the utterances out
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()
         result = [None] * len(phones)
         units = [None] * len(phones)
-        for b, ids, n_units, out in pending:
-            n_host = n_units.tolist()
-            host_block = ops.to_host(out) if (to_host and out is not None and not normalize) else None
+        for b, ids, host_n, out, host_block in pending:
+            n_host = host_n.tolist()
+            host_block = host_block.numpy() if host_block is not None else None
             for r, i in enumerate(b):
                 n = int(n_host[r])
                 units[i] = ids[r, :n]
