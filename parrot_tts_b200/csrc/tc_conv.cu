@@ -289,11 +289,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         // =========================== producer ===========================
         if (p.res_blocks > 0) {
             if (elect_one()) {
-                const int rbytes = p.res_blocks * p.b_block_bytes;
-                mbar_expect_tx(b_res_full, (uint32_t)rbytes);
-                for (int off = 0; off < rbytes; off += 32768) {
-                    const int n = rbytes - off < 32768 ? rbytes - off : 32768;
-                    bulk_load_1d(sm + p.smem_b_off + off, p.w + off, (uint32_t)n, b_res_full);
+                if (CL) {
+                    // CTA pair with RESIDENT weights: each CTA keeps its half of every block ([rank 0 half][rank 1 half] per block in
+                    // the packed operand) for the whole launch; both CTAs' loads complete on the LEADER's barrier (the MMA issuer
+                    // lives there and reads B from both CTAs' shared memory at the same offsets)
+                    if (rank == 0) mbar_expect_tx(b_res_full, (uint32_t)(2 * p.res_blocks * p.b_sub_bytes));
+                    const uint32_t lb = cluster_bar_addr(b_res_full, 0);
+                    for (int blk = 0; blk < p.res_blocks; ++blk) {
+                        const size_t off = (size_t)blk * p.b_block_bytes + (size_t)rank * p.b_sub_bytes;
+                        tma_load_2d_2cta(sm + p.smem_b_off + (size_t)blk * p.b_sub_bytes, &wmap, 0, (int)(off >> 8), lb);
+                    }
+                } else {
+                    const int rbytes = p.res_blocks * p.b_block_bytes;
+                    mbar_expect_tx(b_res_full, (uint32_t)rbytes);
+                    for (int off = 0; off < rbytes; off += 32768) {
+                        const int n = rbytes - off < 32768 ? rbytes - off : 32768;
+                        bulk_load_1d(sm + p.smem_b_off + off, p.w + off, (uint32_t)n, b_res_full);
+                    }
                 }
             }
             __syncwarp();
@@ -676,7 +688,13 @@ size_t tc_packed_weight_bytes(int Cin, int N, int K) { return (size_t)Cin * N * 
 bool tc_use_cluster(int Cin, int N, int K) {
     static const bool on = !(getenv("PB_TC_CLUSTER") != nullptr && atoi(getenv("PB_TC_CLUSTER")) == 0);
     if (!on) return false;
-    return Cin % 64 == 0 && tc_n_tile(N) == 128 && (size_t)Cin * N * K * 4 > 160 * 1024;
+    if (Cin % 64 != 0) return false;
+    if (tc_n_tile(N) == 128 && (size_t)Cin * N * K * 4 > 160 * 1024) return true;
+    // 64 -> 64 channels with 7 or more taps (vocoder stage 3, k = 7 / 11): as one CTA per SM these layers are bound by the single
+    // MMA-issuing thread (two ~56-cycle MMAs per k-step against a ~70-cycle issue loop) and, at k = 11, stream 6 of 11 taps per tile;
+    // as a pair one issuer drives both SMs' tensor cores and each CTA keeps its half of the weights resident (66 / 103 KB)
+    static const bool pair64 = !(getenv("PB_TC_PAIR64") != nullptr && atoi(getenv("PB_TC_PAIR64")) == 0);
+    return pair64 && Cin == 64 && N == 64 && K >= 7;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -799,7 +817,15 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
         const bool full_without = TC_SMEM_LIMIT - 1024u - p.smem_a_off >= w_all + 2u * (uint32_t)p.a_stage_bytes;
         if (full_without || !(a.res && a.accin)) { p.tma_out = 0; stage_bytes = 0; }
     }
-    if (p.cluster) {
+    const uint32_t w_half_all = (uint32_t)round_up((int64_t)p.total_blocks * p.b_sub_bytes, 1024);      // (pairs: this CTA's half of every block)
+    static const bool cl_resident = !(getenv("PB_TC_CL_RESIDENT") != nullptr && atoi(getenv("PB_TC_CL_RESIDENT")) == 0);
+    if (p.cluster && cl_resident && budget(TC_SMEM_LIMIT) >= w_half_all + 2u * (uint32_t)p.a_stage_bytes) {
+        // CTA pair, weights split across the pair and RESIDENT: nothing is streamed per tile (the 64-channel k = 7 / 11 layers,
+        // the 128-channel k = 3 layers); the rest of the shared memory deepens the activation ring
+        p.res_blocks = p.total_blocks; b_res_bytes = w_half_all;
+        p.n_a_stages = (int)((budget(TC_SMEM_LIMIT) - w_half_all) / (uint32_t)p.a_stage_bytes);
+        p.n_b_stages = 0;
+    } else if (p.cluster) {
         const uint32_t bud = budget(TC_SMEM_LIMIT);
         p.res_blocks = 0;
         p.n_a_stages = 2;

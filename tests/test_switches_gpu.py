@@ -3,6 +3,8 @@
   PB_TC_TMA_OUT=2     TMA-store epilogue on every eligible layer (default 1: the one-CTA-per-SM layers)
   PB_TC_EPI_SPLIT=0/2 column-split epilogue groups off / on every one-CTA-per-SM layer (default 1: the CTA-pair layers)
   PB_TC_CLUSTER=0     single-CTA path instead of CTA pairs
+  PB_TC_PAIR64=0      the 64-channel k = 7 / 11 layers as one CTA per SM instead of CTA pairs
+  PB_TC_CL_RESIDENT=0 CTA pairs always stream their weights (no resident halves)
 Each case runs in a fresh interpreter because the library reads its switches once.
 """
 import os
@@ -14,7 +16,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
-SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_LIB_VARIANT")
+SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_TC_PAIR64", "PB_TC_CL_RESIDENT", "PB_LIB_VARIANT")
 
 CODE = r"""
 import sys, numpy as np, torch
@@ -77,3 +79,10 @@ def test_tma_store_epilogue_everywhere_is_bit_identical(tmp_path, baseline):
 @pytest.mark.parametrize("mode", ["0", "2"])
 def test_column_split_epilogue_modes_are_bit_identical(tmp_path, baseline, mode):
     _same(baseline, _run(tmp_path, "episplit" + mode, {"PB_TC_EPI_SPLIT": mode}))
+
+
+@pytest.mark.parametrize("switch", ["PB_TC_PAIR64", "PB_TC_CL_RESIDENT", "PB_TC_CLUSTER"])
+def test_cta_pair_placement_switches_are_bit_identical(tmp_path, baseline, switch):
+    # where a layer runs (one CTA per SM, a CTA pair streaming its weights, a pair with resident halves) changes neither the order of
+    # the K loop nor the products: same bits
+    _same(baseline, _run(tmp_path, switch.lower(), {switch: "0"}))

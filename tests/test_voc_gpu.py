@@ -70,7 +70,9 @@ MODES = [0, 1]
 
 
 @pytest.mark.parametrize("C,K,D,L", [(16, 3, 1, 300), (16, 11, 5, 5000), (32, 7, 3, 777), (64, 11, 1, 500), (64, 1, 1, 129),
-                                     (128, 3, 5, 260), (256, 7, 3, 200), (256, 11, 5, 130)])
+                                     (128, 3, 5, 260), (256, 7, 3, 200), (256, 11, 5, 130),
+                                     # CTA pairs with the weights split and resident: 64 channels at k = 7 / 11, 128 channels at k = 3
+                                     (64, 7, 5, 1000), (64, 11, 5, 700), (64, 11, 3, 257), (128, 3, 1, 600), (64, 3, 3, 900)])
 def test_conv1d_tensor_core_kernel(C, K, D, L):
     g = _gen(K * 100 + D * 10 + C + 1)
     B = 2
