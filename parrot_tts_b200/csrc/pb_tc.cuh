@@ -38,6 +38,7 @@ struct TcConvArgs {
     int single_pass = 0;                   // 1: hi.hi only (plain bf16 product, throughput mode)
     int n_groups = 0;                      // epilogue warpgroups per CTA (0 = choose)
     int fmt = 0;                           // split storage + MMA operand type of x / w / res / accin / out: 0 = bf16, 1 = fp16
+    int pair64 = 0;                        // as given to tc_pack_conv_weight for this layer
     const float* res_f32 = nullptr;        // [B][U*L][out_C] fp32 residual (added like res, no activation to undo) or null
     // fused row argmax (U == 1): key[b*L + t] = max over columns n < argmax_n of (order-preserving bits of v[t, n]) << 32 | ~n, merged
     // with atomicMax (zero the keys first; tc_argmax_unpack turns them into indices - first maximum, like torch.argmax).  out and
@@ -48,10 +49,12 @@ struct TcConvArgs {
 int tc_argmax_unpack(const unsigned long long* key, int64_t M, int64_t* ids, cudaStream_t st);
 
 int tc_n_tile(int N);                       // N-tile the kernel uses for a GEMM N (0 = unsupported)
-size_t tc_packed_weight_bytes(int Cin, int N, int K);
-bool tc_use_cluster(int Cin, int N, int K);     // layer runs on CTA pairs (cta_group::2); decides the packed weight layout
+// pair64: the caller's per-layer choice for the 64 -> 64-channel layers with >= 7 taps (see tc_use_cluster); must be the same at pack
+// and at launch time.  Every other shape is decided by the shape alone.
+size_t tc_packed_weight_bytes(int Cin, int N, int K, int pair64 = 0);
+bool tc_use_cluster(int Cin, int N, int K, int pair64 = 0);     // layer runs on CTA pairs (cta_group::2); decides the packed weight layout
 // torch Conv1d weight f32 [Cout][Cin][K]  -> packed split-bf16 B operand (N = Cout)
-int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt = 0);
+int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt = 0, int pair64 = 0);
 // torch ConvTranspose1d weight f32 [Cin][Cout][Kt], stride U, padding (Kt-U)/2 -> 3-tap polyphase operand (N = U*Cout)
 int tc_pack_convtr_weight(const float* w, uint8_t* packed, int Cin, int Cout, int Kt, int U, cudaStream_t st, int fmt = 0);
 int launch_tc_conv(const TcConvArgs& a, cudaStream_t st);

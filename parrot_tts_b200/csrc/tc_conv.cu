@@ -674,9 +674,9 @@ static int tc_cin_tile(int Cin) {
     return 0;
 }
 
-bool tc_use_cluster(int Cin, int N, int K);
+bool tc_use_cluster(int Cin, int N, int K, int pair64);
 // split 16-bit hi + lo = 4 bytes per weight; the CTA-pair layout stores the hi rows a second time (operand R2): 6 bytes
-size_t tc_packed_weight_bytes(int Cin, int N, int K) { return (size_t)Cin * N * K * (tc_use_cluster(Cin, N, K) ? 6 : 4); }
+size_t tc_packed_weight_bytes(int Cin, int N, int K, int pair64) { return (size_t)Cin * N * K * (tc_use_cluster(Cin, N, K, pair64) ? 6 : 4); }
 
 // CTA pairs (cta_group::2) for the wide layers whose weights cannot stay resident: M = 256 per pair, each CTA streams (and
 // reads) half of the weight rows - halves the L2 -> SM weight traffic and the B-operand shared-memory traffic that bound
@@ -685,16 +685,18 @@ size_t tc_packed_weight_bytes(int Cin, int N, int K) { return (size_t)Cin * N * 
 // relayed "my half has landed" through the peer's idle warp left the leader waiting on that hop 40 % of the time and was
 // 25 % slower than the single-CTA path; with direct signalling the pair path is ~8 % faster on the 256 / 128-channel stages.
 // PB_TC_CLUSTER=0 selects the single-CTA path (same results).
-bool tc_use_cluster(int Cin, int N, int K) {
+bool tc_use_cluster(int Cin, int N, int K, int pair64) {
     static const bool on = !(getenv("PB_TC_CLUSTER") != nullptr && atoi(getenv("PB_TC_CLUSTER")) == 0);
     if (!on) return false;
     if (Cin % 64 != 0) return false;
     if (tc_n_tile(N) == 128 && (size_t)Cin * N * K * 4 > 160 * 1024) return true;
-    // 64 -> 64 channels with 7 or more taps (vocoder stage 3, k = 7 / 11): as one CTA per SM these layers are bound by the single
-    // MMA-issuing thread (two ~56-cycle MMAs per k-step against a ~70-cycle issue loop) and, at k = 11, stream 6 of 11 taps per tile;
-    // as a pair one issuer drives both SMs' tensor cores and each CTA keeps its half of the weights resident (66 / 103 KB)
-    static const bool pair64 = !(getenv("PB_TC_PAIR64") != nullptr && atoi(getenv("PB_TC_PAIR64")) == 0);
-    return pair64 && Cin == 64 && N == 64 && K >= 7;
+    // 64 -> 64 channels with 7 or more taps (vocoder stage 3, k = 7 / 11), when the caller asks for it (pair64): as a pair each CTA
+    // keeps its half of the weights RESIDENT (66 / 103 KB; one CTA per SM streams 6 of 11 taps per tile at k = 11) and one issuing
+    // thread drives both SMs' tensor cores.  Measured per launch at 8 x 1024 units (profiles/r02_pair64.txt): conv1 k = 7 98 -> 84 us,
+    // k = 11 162 -> 123 us; the residual conv2 at k = 11 169 -> 134 us; but the k = 7 residual launches and the ones that also add
+    // the running sum are better off as one CTA per SM with the TMA-store epilogue - hence a per-layer choice, not a shape rule.
+    static const bool pair64_on = !(getenv("PB_TC_PAIR64") != nullptr && atoi(getenv("PB_TC_PAIR64")) == 0);
+    return pair64_on && pair64 != 0 && Cin == 64 && N == 64 && K >= 7;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -773,7 +775,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.lo_off = a.Cin >= 64 ? p.a_tile_bytes : (a.Cin == 32 ? 64 : 32);
     p.a_layout = cin_t == 16 ? 4 : 2;
     p.a_sbo = 8 * p.a_row_bytes;
-    p.cluster = tc_use_cluster(a.Cin, a.N, a.K) ? 1 : 0;      // (always the 3-product form: the packed layout is the pair layout)
+    p.cluster = tc_use_cluster(a.Cin, a.N, a.K, a.pair64) ? 1 : 0;      // (always the 3-product form: the packed layout is the pair layout)
     p.b_block_bytes = 2 * p.ksteps * NT * 32;           // one (n tile, channel chunk, tap): ksteps x {hi, lo} planes
     p.kpb = 32768 / (2 * NT * 32);                       // k-steps per streamed sub-block (<= 32 KB: 6+ MMAs per barrier round trip)
     if (p.kpb < 1) p.kpb = 1;
@@ -807,7 +809,7 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     static const int force_2cta = getenv("PB_TC_2CTA") ? atoi(getenv("PB_TC_2CTA")) : -1;
     const bool want_2cta = force_2cta >= 0 ? (force_2cta != 0 && NT <= 128) : NT <= 16;
     p.tma_out = (a.out != nullptr && a.U == 1 && tma_out_mode > 0 && !want_2cta &&
-                 (tma_out_mode == 2 || !p.cluster)) ? 1 : 0;
+                 (tma_out_mode == 2 || !p.cluster || (NT == 64 && a.res && a.accin))) ? 1 : 0;
     uint32_t stage_bytes = p.tma_out ? (uint32_t)TC_MAX_GROUPS * 4u * 2048u : 0u;
     auto budget = [&](uint32_t limit) { return limit - 1024u - p.smem_a_off - stage_bytes; };   // barriers + bias + alignment slack
     if (p.tma_out && !p.cluster && budget(TC_SMEM_LIMIT) < w_all + 2u * (uint32_t)p.a_stage_bytes) {
@@ -900,7 +902,8 @@ int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     p.n_groups = a.n_groups > 0 ? a.n_groups : (env_groups > 0 ? env_groups : (ctas_per_sm == 2 ? 1 : TC_MAX_GROUPS));
     // PB_TC_EPI_SPLIT (dev switch): 0 = off, 1 = the CTA-pair layers (default), 2 = every one-CTA-per-SM layer
     static const int epi_split_env = getenv("PB_TC_EPI_SPLIT") ? atoi(getenv("PB_TC_EPI_SPLIT")) : 1;
-    p.epi_split = (ctas_per_sm == 1 && (epi_split_env >= 2 || (epi_split_env == 1 && p.cluster))) ? 1 : 0;
+    // (pairs with a 64-wide tile keep whole tiles per group: 4 items over 3 groups split 2 / 1 / 1 - measured 118 vs 84 us at k = 7)
+    p.epi_split = (ctas_per_sm == 1 && (epi_split_env >= 2 || (epi_split_env == 1 && p.cluster && NT >= 128))) ? 1 : 0;
     if (p.epi_split) {
         if (p.n_groups > NT / 16) p.n_groups = NT / 16;       // every group needs an item in every tile
     } else if (p.n_groups > p.n_acc) p.n_groups = p.n_acc;
@@ -1003,6 +1006,7 @@ struct PackDev {
     int convtr, Cout, Kt, U;
     int fmt;
     int cluster;      // CTA-pair layout: block = [rank 0: ksteps x 4 KB][rank 1: ...], rank = (n % NT) / (NT / 2)
+    int pair64;
 };
 
 __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
@@ -1063,7 +1067,7 @@ __global__ void tc_pack_kernel(const PackDev d, uint8_t* __restrict__ packed) {
 static int pack_common(PackDev d, uint8_t* packed, cudaStream_t st) {
     d.cin_t = tc_cin_tile(d.Cin);
     d.NT = tc_n_tile(d.N);
-    d.cluster = tc_use_cluster(d.Cin, d.N, d.K) ? 1 : 0;
+    d.cluster = tc_use_cluster(d.Cin, d.N, d.K, d.pair64) ? 1 : 0;
     PB_REQUIRE(d.cin_t > 0 && d.NT > 0, PB_ERR_INVALID, "tc_pack: unsupported Cin=%d / N=%d", d.Cin, d.N);
     d.ksteps = d.cin_t / 16;
     d.nchunks = d.Cin / d.cin_t;
@@ -1075,9 +1079,10 @@ static int pack_common(PackDev d, uint8_t* packed, cudaStream_t st) {
     return PB_OK;
 }
 
-int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt) {
+int tc_pack_conv_weight(const float* w, uint8_t* packed, int Cout, int Cin, int K, cudaStream_t st, int fmt, int pair64) {
     PackDev d{};
     d.fmt = fmt;
+    d.pair64 = pair64;
     d.w = w; d.s_n = (int64_t)Cin * K; d.s_ci = K; d.s_j = 1; d.Cin = Cin; d.N = Cout; d.K = K;
     return pack_common(d, packed, st);
 }

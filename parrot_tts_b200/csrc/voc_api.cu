@@ -14,6 +14,7 @@ namespace {
 struct ConvSlot {          // one convolution's packed parameters inside the arena
     size_t w_off = 0, b_off = 0;
     int Cin = 0, Cout = 0, K = 0, D = 1, co_tile = 0;
+    int pair64 = 0;           // this layer runs on CTA pairs with resident weight halves (tc_use_cluster): fixed at plan time
     bool transposed = false;
     std::string key;
 };
@@ -51,11 +52,11 @@ struct pb_voc {
 static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
 
 static void plan_slot(pb_voc* h, ConvSlot& s, const std::string& key, int Cin, int Cout, int K, int D, bool transposed,
-                      int co_tile) {
-    s.key = key; s.Cin = Cin; s.Cout = Cout; s.K = K; s.D = D; s.transposed = transposed; s.co_tile = co_tile;
+                      int co_tile, int pair64 = 0) {
+    s.key = key; s.Cin = Cin; s.Cout = Cout; s.K = K; s.D = D; s.transposed = transposed; s.co_tile = co_tile; s.pair64 = pair64;
     size_t wbytes = (size_t)Cin * Cout * K * sizeof(float);
     if (h->cfg.conv_mode != 0 && Cout > 1)   // tensor-core operand: a transposed conv becomes U phases x 3 taps (D carries U)
-        wbytes = transposed ? tc_packed_weight_bytes(Cin, D * Cout, 3) : tc_packed_weight_bytes(Cin, Cout, K);
+        wbytes = transposed ? tc_packed_weight_bytes(Cin, D * Cout, 3) : tc_packed_weight_bytes(Cin, Cout, K, pair64);
     s.w_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + wbytes);
     s.b_off = h->arena_bytes; h->arena_bytes = align_up(h->arena_bytes + (size_t)Cout * sizeof(float));
 }
@@ -105,9 +106,11 @@ extern "C" int pb_voc_create(const pb_voc_cfg* cfg, pb_voc** out) {
             for (int m = 0; m < cfg->num_dilations; ++m) {
                 const std::string p = "resblocks." + std::to_string(i * cfg->num_kernels + j);
                 ConvSlot a, b;
-                plan_slot(h, a, p + ".convs1." + std::to_string(m), cout, cout, cfg->resblock_kernel_sizes[j],
-                          cfg->resblock_dilation_sizes[j][m], false, cr);
-                plan_slot(h, b, p + ".convs2." + std::to_string(m), cout, cout, cfg->resblock_kernel_sizes[j], 1, false, cr);
+                // 64-channel layers with >= 7 taps: conv1 always as a CTA pair; conv2 only at >= 11 taps (measured per launch,
+                // see tc_use_cluster).  The shape rule inside tc_use_cluster ignores the flag for every other layer.
+                const int kk = cfg->resblock_kernel_sizes[j];
+                plan_slot(h, a, p + ".convs1." + std::to_string(m), cout, cout, kk, cfg->resblock_dilation_sizes[j][m], false, cr, 1);
+                plan_slot(h, b, p + ".convs2." + std::to_string(m), cout, cout, kk, 1, false, cr, kk >= 11 ? 1 : 0);
                 h->rb1.push_back(a);
                 h->rb2.push_back(b);
             }
@@ -198,7 +201,7 @@ static int finalize_conv(pb_voc* h, const ConvSlot& s, float* scratch, cudaStrea
     } else if (h->cfg.conv_mode != 0) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(h->A(s.w_off));
         if (s.transposed) PB_TRY(tc_pack_convtr_weight(scratch, dst, s.Cin, s.Cout, s.K, s.D, st));
-        else PB_TRY(tc_pack_conv_weight(scratch, dst, s.Cout, s.Cin, s.K, st));
+        else PB_TRY(tc_pack_conv_weight(scratch, dst, s.Cout, s.Cin, s.K, st, 0, s.pair64));
     } else if (s.transposed) {
         PB_TRY(launch_pack_conv_weight(scratch, s.K, (int64_t)s.Cout * s.K, h->A(s.w_off), s.Cout, s.Cin, s.K, s.co_tile, st));
     } else {
@@ -427,12 +430,12 @@ static int voc_forward_tc(pb_voc* h, const float* x, const int64_t* code, const 
                 TcConvArgs a;
                 a.x = cur; a.w = W(s1); a.bias = h->A(s1.b_off); a.out = XT; a.lens = lens; a.len_mul = mul;
                 a.B = B; a.L = (int)Lo; a.Cin = C; a.N = C; a.out_C = C; a.U = 1; a.K = s1.K; a.D = s1.D;
-                a.post_slope = 0.1f; a.single_pass = single;
+                a.post_slope = 0.1f; a.single_pass = single; a.pair64 = s1.pair64;
                 PB_TRY(launch_tc_conv(a, sj));
                 TcConvArgs b2;
                 b2.x = XT; b2.w = W(s2); b2.bias = h->A(s2.b_off); b2.res = cur; b2.res_unslope = 10.f;
                 b2.lens = lens; b2.len_mul = mul; b2.B = B; b2.L = (int)Lo; b2.Cin = C; b2.N = C; b2.out_C = C; b2.U = 1;
-                b2.K = s2.K; b2.D = 1; b2.single_pass = single;
+                b2.K = s2.K; b2.D = 1; b2.single_pass = single; b2.pair64 = s2.pair64;
                 if (m + 1 < c.num_dilations) {
                     bf* dst = (cur == XA) ? XB : XA;
                     b2.out = dst; b2.post_slope = 0.1f;
@@ -709,14 +712,14 @@ extern "C" int pb_conv1d_tc(const float* x, const float* w, const float* bias, c
     uint8_t* wp = nullptr;
     PB_TRY(g.get(&xs, (size_t)B * L * 2 * Cin));
     PB_TRY(g.get(&ys, (size_t)B * L * 2 * Cout));
-    PB_TRY(g.get(&wp, tc_packed_weight_bytes(Cin, Cout, K)));
+    PB_TRY(g.get(&wp, tc_packed_weight_bytes(Cin, Cout, K, 1)));
     if (res) PB_TRY(g.get(&rs, (size_t)B * L * 2 * Cout));
     PB_TRY(launch_f32_to_split(x, L, xs, B, Cin, L, pre_slope, st));
     if (res) PB_TRY(launch_f32_to_split(res, L, rs, B, Cout, L, 1.f, st));
-    PB_TRY(tc_pack_conv_weight(w, wp, Cout, Cin, K, st));
+    PB_TRY(tc_pack_conv_weight(w, wp, Cout, Cin, K, st, 0, 1));
     TcConvArgs a;
     a.x = xs; a.w = wp; a.bias = bias; a.res = rs; a.out = ys; a.B = B; a.L = L; a.Cin = Cin; a.N = Cout; a.out_C = Cout;
-    a.U = 1; a.K = K; a.D = dilation; a.post_slope = post_slope; a.single_pass = debug_flags & 1;
+    a.U = 1; a.K = K; a.D = dilation; a.post_slope = post_slope; a.single_pass = debug_flags & 1; a.pair64 = 1;
     PB_TRY(launch_tc_conv(a, st));
     PB_TRY(launch_split_to_f32(ys, y, L, B, Cout, L, st));
     PB_CUDA(cudaStreamSynchronize(st));
