@@ -696,7 +696,7 @@ bool tc_use_cluster(int Cin, int N, int K, int pair64) {
     // k = 11 162 -> 123 us; the residual conv2 at k = 11 169 -> 134 us; but the k = 7 residual launches and the ones that also add
     // the running sum are better off as one CTA per SM with the TMA-store epilogue - hence a per-layer choice, not a shape rule.
     static const bool pair64_on = !(getenv("PB_TC_PAIR64") != nullptr && atoi(getenv("PB_TC_PAIR64")) == 0);
-    return pair64_on && pair64 != 0 && Cin == 64 && N == 64 && K >= 7;
+    return pair64_on && pair64 != 0 && Cin == 64 && N == 64 && K >= 7;      // (k = 3 as a pair: 66 -> 74 us conv1, 105 -> 127 us conv2)
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
