@@ -371,3 +371,33 @@ def test_fused_head_argmax_equals_argmax_of_the_logits():
         m.head.bias[7] = -0.0; m.head.bias[3] = 1.0; m.head.bias[900] = 1.0
     ids1, _ = m.infer_device(batch)
     assert torch.equal(ids1, torch.full_like(ids1, 3))
+
+
+def test_infer_ragged_single_speaker_and_zero_duration_items():
+    """Ragged mode on a single-speaker model (no speaker row to add: the encoder output is still zeroed past each item's end) and with
+    an item whose characters all round to zero units."""
+    import json
+    import tempfile
+    d = tempfile.mkdtemp(prefix="parrot_one_spk_ragged_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({"only": 0}, f)
+    cfg = configs.default_tte_config(root_path=d)
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, 1, seed=35)
+    m = Parrot(cfg, VOCAB, 0)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(DEV)
+    g = _gen(14)
+    lens = [11, 4, 17]
+    phones = torch.zeros(3, 17, dtype=torch.long)
+    for b, n in enumerate(lens):
+        phones[b, :n] = torch.randint(2, VOCAB, (n,), generator=g)
+    ids, n_units = m.infer_ragged(phones.to(DEV), torch.tensor(lens))
+    for b, n in enumerate(lens):
+        one = {"phones": phones[b:b + 1, :n], "src_mask": torch.ones(1, n, dtype=torch.bool), "speaker": torch.zeros(1, dtype=torch.long)}
+        ids_ref, r = tte_oracle.parrot_infer(sd, one)
+        assert int(n_units[b]) == len(ids_ref[0]) and ids[b, :int(n_units[b])].cpu().tolist() == ids_ref[0], b
+    # durations forced to zero for one item: proj.bias very negative -> exp(.) - 1 rounds to 0 everywhere -> T = 0 for the whole batch
+    with torch.no_grad():
+        m.duration_predictor.proj.weight.zero_(); m.duration_predictor.proj.bias.fill_(-20.0)
+    ids0, n0 = m.infer_ragged(phones.to(DEV), torch.tensor(lens))
+    assert ids0.shape == (3, 0) and n0.tolist() == [0, 0, 0]
