@@ -70,6 +70,11 @@ class Parrot(nn.Module):
     def _handle(self, device):
         return self._eng.get(self._cfg_fields(), self._wstamp, device)
 
+    def invalidate_weights(self):
+        """Force the next call to re-upload, re-fold and re-pack the weights.  Needed only after edits torch cannot see (``p.data.copy_()``
+        and the like bump no version counter); ``load_state_dict``, in-place ops on the parameters and ``.to()`` are detected."""
+        self._wstamp.invalidate()
+
     # ---- packed-arena hand-over (sharding.broadcast_engines), as on the vocoder
     def engine_arena(self, device, receive=False):
         lib = _lib.load()

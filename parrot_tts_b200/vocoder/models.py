@@ -150,6 +150,14 @@ class Generator(nn.Module):
             self._wstamp = WeightStamp(self)
         return (str(device), int(self.conv_mode)) + self._wstamp.stamp()
 
+    def invalidate_weights(self):
+        """Force the next forward to re-upload, re-fold and re-pack the weights.  Needed only after edits torch cannot see
+        (``p.data.copy_()`` and the like bump no version counter); ``load_state_dict``, in-place ops, ``remove_weight_norm`` and
+        ``.to()`` are detected."""
+        if self._wstamp is None:
+            self._wstamp = WeightStamp(self)
+        self._wstamp.invalidate()
+
     def _engine(self, device):
         """pb_voc handle holding the folded + packed copy of the current parameters."""
         stamp = self._stamp(device)

@@ -52,3 +52,19 @@ def test_tte_stamp_tracks_parameters_and_buffers():
     c = m._wstamp.stamp()
     assert c != b
     assert m._wstamp.tensors()["head.weight"] is m.head.weight
+
+
+def test_unrelated_registrations_do_not_stale_an_engine_and_invalidate_does():
+    """the process-wide registration counter only refreshes the cached tensor list; it is not part of the comparison key, so
+    building another model (or any nn.Module) leaves an existing engine's stamp unchanged.  `.data` edits are invisible to torch's
+    version counters: `invalidate_weights()` is the explicit way."""
+    h = configs.default_vocoder_config()
+    gen = CodeGenerator(h)
+    s0 = gen._stamp("cuda:0")
+    torch.nn.Linear(4, 4)                                     # unrelated registrations anywhere in the process
+    CodeGenerator(h)
+    assert gen._stamp("cuda:0") == s0
+    gen.conv_post.bias.data.add_(1.0)                         # not seen ...
+    assert gen._stamp("cuda:0") == s0
+    gen.invalidate_weights()                                  # ... unless said
+    assert gen._stamp("cuda:0") != s0
