@@ -642,6 +642,15 @@ def supplementary(b, skip):
     streaming = {"workload": "cfg5: 16 384 units streamed as 16 chunks of 1024 units (+32-unit halo), host codes -> int16 PCM on host",
                  "time_to_first_chunk_ms": first_ms, "steady_samples_per_s": n5 / all_s, "rtf_16k": n5 / all_s / 16000.0,
                  "total_ms": all_s * 1e3}
+    def run_stream_ahead():
+        c5 = code5_h.to(dev, non_blocking=True)
+        return sum(pcm.size for _, pcm in stream_generate(voc, c5, spk5, chunk_units=1024, halo_units=32, pcm16=True, lookahead=1, host=True))
+
+    run_stream_ahead()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); n5l = run_stream_ahead(); all_l = time.perf_counter() - t0
+    streaming["lookahead_1"] = {"steady_samples_per_s": n5l / all_l, "total_ms": all_l * 1e3,
+                                "note": "stream_generate(lookahead=1, host=True): chunk i is copied to the host on a copy stream while chunk i + 1 runs"}
     try:
         run_stream(False, stream_graphs)           # captures one CUDA graph per window length (3)
         torch.cuda.synchronize()

@@ -127,10 +127,13 @@ def stream_chunks(n_units, chunk_units=1024, halo_units=32):
     return out
 
 
-def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32, pcm16=False, graphs=None):
+def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32, pcm16=False, graphs=None, lookahead=0, host=False):
     """Long-form synthesis in chunks (BASELINE configs[4]): yields (first_sample, audio) per chunk, audio f32 [B, n] on the
     device (or int16 with ``pcm16=True``), n = hop * (b - a).  ``code`` i64 [B, T] on the device.  Each chunk is one
     ``generator(code=window, spkr=spkr)`` call on the window of units it needs; nothing is recomputed beyond the two halos.
+    ``host=True`` yields numpy arrays: every chunk is copied to pinned host memory on a copy stream as soon as its own kernels are
+    done.  ``lookahead=k`` launches k further chunks before a chunk is handed over, so that the copy (and the consumer) of chunk i
+    overlap the kernels of chunk i + 1 - steady-state throughput; the first chunk then arrives k launches later.
     ``graphs={}`` replays one CUDA graph per distinct window length instead (the dict can be kept for the next stream; a yielded
     chunk is then a view of the graph's static output buffer, valid until the next chunk of the same window length)."""
     T = code.shape[1]
@@ -140,6 +143,9 @@ def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32,
         for n in sorted({hi - lo for lo, hi, _, _ in chunks}, reverse=True):
             if (n, bool(pcm16)) not in graphs:
                 graphs[(n, bool(pcm16))] = GraphedGenerator(generator, code.shape[0], n, pcm16=pcm16)
+    if lookahead and graphs is not None:
+        raise ValueError("lookahead needs the plain path: a graph's output buffer is overwritten by the next chunk of the same window length")
+    held, copy_stream = [], None
     for lo, hi, a, b in chunks:
         if graphs is not None:
             out = graphs[(hi - lo, bool(pcm16))](code[:, lo:hi], spkr)
@@ -148,4 +154,32 @@ def stream_generate(generator, code, spkr=None, chunk_units=1024, halo_units=32,
             if spkr is not None:
                 kw["spkr"] = spkr
             out = generator.forward_pcm16(**kw) if pcm16 else generator(**kw)      # int16 straight from conv_post's epilogue
-        yield a * hop, out[:, 0, (a - lo) * hop:(b - lo) * hop]
+        piece = out[:, 0, (a - lo) * hop:(b - lo) * hop]
+        done = None
+        if host:      # the chunk leaves for pinned host memory on a copy stream as soon as ITS kernels are done, whatever is queued behind
+            dev = piece.device
+            if copy_stream is None:
+                copy_stream = torch.cuda.Stream(dev)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                buf = torch.empty(piece.shape, dtype=piece.dtype, pin_memory=True)
+                buf.copy_(piece, non_blocking=True)
+                piece.record_stream(copy_stream)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            piece = buf
+        held.append((a * hop, piece, done))
+        if len(held) > lookahead:       # hand chunk i over only once chunk i + lookahead is launched: its copy overlaps their kernels
+            yield _hand_over(held.pop(0))
+    while held:
+        yield _hand_over(held.pop(0))
+
+
+def _hand_over(item):
+    first, piece, done = item
+    if done is None:
+        return first, piece
+    done.synchronize()
+    return first, piece.numpy()

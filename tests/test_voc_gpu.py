@@ -354,6 +354,14 @@ def test_cuda_graph_replay_equals_direct_forward():
     graphs = {}
     viag = torch.cat([w.clone() for _, w in stream_generate(gen, code, spkr, chunk_units=128, halo_units=32, graphs=graphs)], dim=1)
     assert sorted(graphs) == [(76, False), (160, False), (192, False)] and torch.equal(plain, viag)
+    ahead = list(stream_generate(gen, code, spkr, chunk_units=128, halo_units=32, lookahead=1))
+    assert [o for o, _ in ahead] == [0, 128 * 320, 256 * 320] and torch.equal(torch.cat([w for _, w in ahead], dim=1), plain)
+    with pytest.raises(ValueError):
+        list(stream_generate(gen, code, spkr, chunk_units=128, halo_units=32, graphs=graphs, lookahead=1))
+    on_host = list(stream_generate(gen, code, spkr, chunk_units=128, halo_units=32, lookahead=1, host=True, pcm16=True))
+    want = ops.wav_to_pcm16(plain).cpu().numpy()
+    assert all(isinstance(w, np.ndarray) and w.dtype == np.int16 for _, w in on_host)
+    assert np.array_equal(np.concatenate([w for _, w in on_host], axis=1), want)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
