@@ -12,6 +12,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 struct Cfg {
     int N, iters, a_layout, a_lbo, a_sbo, a_shift, a_kstep, b_layout, b_lbo, b_sbo, b_kstep, n_acc, ksteps, a_tiles, a_tile_bytes, b_tiles, b_tile_bytes;
+    int alt_N;      // 2CTA probe: != 0 -> every second MMA uses this N (alternating instruction shapes, as the stacked + lo pair of tc_conv does)
+    int alt_grouped;   // != 0 -> the 4 MMAs of shape N first, then the 4 of shape alt_N (same work, shapes grouped)
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -127,7 +129,7 @@ static void run(const char* name, Cfg c, int grid) {
 
 
 // ---- cta_group::2: M = 256 over a CTA pair; each CTA holds its own 128 A rows and N/2 rows of B ----------------------
-template <int KS>
+template <int KS, int ALT>      // ALT: 0 = one instruction shape, 1 = shapes N / alt_N alternating, 2 = grouped (compile time: the plain loop stays as measured in round 1)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(Cfg c, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -152,6 +154,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(Cfg c, l
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t idesc_alt = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((c.alt_N ? c.alt_N : c.N) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     long long t0 = 0;
     const bool leader = elect_one();
     if (threadIdx.x == 0 && rank == 0) {
@@ -173,6 +176,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(Cfg c, l
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t aa = a_lo + (h ? a_flip : 0), bb = b_lo + (h ? b_flip : 0), dd = d + (h ? d_flip : 0);
                     if (leader) {
+                        if (ALT == 2) {
+#pragma unroll
+                            for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+                                for (int ks = 0; ks < KS; ++ks) {
+                                    const uint64_t da = ((uint64_t)a_hi << 32) | (aa + ks * a_step);
+                                    const uint64_t db = ((uint64_t)b_hi << 32) | (bb + ks * b_step);
+                                    asm volatile(
+                                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(dd), "l"(da), "l"(db), "r"(pass ? idesc_alt : idesc), "r"(1u)
+                                        : "memory");
+                                }
+                        } else {
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint64_t da = ((uint64_t)a_hi << 32) | (aa + ks * a_step);
@@ -181,6 +197,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(Cfg c, l
                                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(dd), "l"(da), "l"(db), "r"(idesc), "r"(1u)
                                 : "memory");
+                            if (ALT == 1) {
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(dd), "l"(da), "l"(db), "r"(idesc_alt), "r"(1u)
+                                    : "memory");
+                            }
+                        }
                         }
                     }
                     __syncwarp();
@@ -210,7 +233,7 @@ static void run2(const char* name, Cfg c, int grid) {
     long long* d;
     cudaMalloc(&d, grid * sizeof(long long));
     const int smem = c.a_tiles * c.a_tile_bytes + c.b_tiles * c.b_tile_bytes + 2048;
-    auto kern = probe2<4>;
+    auto kern = c.alt_N == 0 ? probe2<4, 0> : (c.alt_grouped ? probe2<4, 2> : probe2<4, 1>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     for (int r = 0; r < 2; ++r) {
         kern<<<grid, 128, smem>>>(c, d);
@@ -271,6 +294,21 @@ int main() {
         run2("2CTA: A sw128, B noswz (N/2 rows per CTA)", c, 148);
         c.b_layout = 2; c.b_lbo = 16; c.b_sbo = 1024; c.b_kstep = 32; c.b_tile_bytes = Nh * 128;
         if (Nh >= 8) run2("2CTA: A sw128, B sw128", c, 148);
+    }
+    {   // the stacked + lo pair of tc_conv's CTA-pair path: N = 256 and N = 128 MMAs alternating vs grouped (cycles per PAIR of MMAs / 2)
+        Cfg c{};
+        c.N = 256; c.iters = 2000; c.ksteps = 8; c.n_acc = 1;      // 8 MMAs per 4 k-steps
+        c.a_layout = 2; c.a_lbo = 16; c.a_sbo = 1024; c.a_shift = 0; c.a_kstep = 32; c.a_tiles = 2; c.a_tile_bytes = 144 * 128;
+        c.b_layout = 0; c.b_lbo = 128 * 16; c.b_sbo = 128; c.b_kstep = 128 * 32; c.b_tiles = 2; c.b_tile_bytes = 4 * 128 * 32;
+        c.alt_N = 128; c.alt_grouped = 0;
+        run2("2CTA: N=256 / N=128 ALTERNATING (avg of the two)", c, 148);
+        c.alt_grouped = 1;
+        run2("2CTA: N=256 x4 then N=128 x4 GROUPED (avg)", c, 148);
+        c.N = 128; c.alt_N = 64; c.alt_grouped = 0;
+        c.b_lbo = 64 * 16; c.b_kstep = 64 * 32; c.b_tile_bytes = 4 * 64 * 32;
+        run2("2CTA: N=128 / N=64 ALTERNATING (avg)", c, 148);
+        c.alt_grouped = 1;
+        run2("2CTA: N=128 x4 then N=64 x4 GROUPED (avg)", c, 148);
     }
     return 0;
 }
