@@ -135,3 +135,40 @@ def test_tte_cfg3_full_size_vs_eager_torch():
         "torch": torch.__version__,
         "note": "eager = nn.MultiheadAttention slow path restated (scores materialised), cuBLAS fp32, TF32 off"})
     assert t_ours < t_ref, (t_ours, t_ref)
+
+
+def test_ragged_pipeline_full_size_equals_every_utterance_alone():
+    """BASELINE configs[3] lengths (up to 512 chars -> 4096 units): a bucket run through serving.SpeechPipeline (ragged TTE ->
+    device hand-over -> ragged vocoder -> int16) gives, for every utterance, BITWISE the unit ids and the int16 PCM of that utterance
+    run alone (Parrot.infer_device at batch 1 + generate()): tile counts, attention key tiles and CTA-pair placement all differ between
+    the two, the per-row arithmetic must not."""
+    import numpy as np
+    from parrot_tts_b200.serving import SpeechPipeline
+    from parrot_tts_b200.vocoder import generate
+    d = tempfile.mkdtemp(prefix="parrot_fullsize_ragged_")
+    with open(os.path.join(d, "speakers.json"), "w") as f:
+        json.dump({f"s{i}": i for i in range(10)}, f)
+    cfg = configs.default_tte_config(root_path=d, max_len=4200)
+    sd_t = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=0, dur_mode="const8")
+    tte = Parrot(cfg, 150, 0)
+    tte.load_state_dict(sd_t)
+    tte = tte.eval().to(DEV)
+    h = configs.default_vocoder_config()
+    voc = CodeGenerator(h)
+    voc.load_state_dict(synth.synth_vocoder_state_dict(h, seed=0))
+    voc = voc.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    n_chars = [512, 470, 466, 300, 64, 33]
+    phones = [torch.randint(2, 150, (n,), generator=g) for n in n_chars]
+    spk = [3, 1, 4, 1, 5, 9]
+    pipe = SpeechPipeline(tte, voc, max_batch=3, max_pad_ratio=1.1)
+    audio = pipe(phones, spk)
+    assert sorted(len(b) for b in pipe.last_batches) == [1, 1, 1, 3]                    # 512 / 470 / 466 share a bucket
+    for i, ph in enumerate(phones):
+        one = {"phones": ph.view(1, -1).to(DEV), "src_mask": torch.ones(1, ph.numel(), dtype=torch.bool, device=DEV),
+               "speaker": torch.tensor([spk[i]], device=DEV)}
+        ids, n = tte.infer_device(one)
+        assert int(n[0]) == 8 * n_chars[i] == pipe.last_units[i].numel()
+        assert torch.equal(pipe.last_units[i], ids[0]), i
+        ref, _ = generate(h, voc, dict(code=ids, spkr=torch.tensor([[spk[i]]], device=DEV)))
+        assert audio[i].shape == ref.shape == (320 * 8 * n_chars[i],) and np.array_equal(audio[i], ref), i
