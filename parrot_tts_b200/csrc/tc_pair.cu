@@ -23,9 +23,8 @@ namespace pb {
 namespace {
 
 constexpr int TP_M = 128;
-constexpr int TP_GROUPS = 3;      // epilogue warpgroups, tiles round-robin
-constexpr int TP_STAGES = 3;      // conv1 accumulator / xt tile / conv2 accumulator stages (tiles in flight)
-constexpr int TP_THREADS = 128 + 128 * TP_GROUPS;
+constexpr int TP_MAX_GROUPS = 4;  // NG epilogue warpgroups take the tiles round-robin, each with its own conv1 accumulator / xt tile /
+                                  // conv2 accumulator stage: NG tiles in flight (template parameter: 3 or 4, chosen per layer on the host)
 constexpr int TP_MAX_XST = 6;
 constexpr uint32_t TP_SMEM_LIMIT = 232448;
 
@@ -48,14 +47,17 @@ struct PairParams {
     int acc_cols, tmem_cols;
     int tma_out;                   // epilogue B writes through per-warp staging tiles + TMA stores
     uint32_t smem_stage_off;
+    int ablate;                    // profiling only (PB_TP_ABLATE): 1 no MMAs, 2 no output stores, 4 no residual / running-sum loads,
+                                   // 8 no x loads, 16 no xt stores, 32 no epilogue arithmetic - results are wrong by design
 };
 
 }  // namespace
 
-template <bool ACC, int KSTEPS>
-__global__ void __launch_bounds__(TP_THREADS, 1)
+template <bool ACC, int KSTEPS, int NG>
+__global__ void __launch_bounds__(128 + 128 * NG, 1)
 tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap_tail,
                const PairParams p) {
+    constexpr int TP_GROUPS = NG, TP_STAGES = NG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
@@ -120,9 +122,12 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             if (elect_one()) {
                 uint8_t* dst = sm + p.smem_x_off + xs * p.x_stage_bytes;
                 // the box is at most 256 rows: the tile is loaded as two boxes of x_rows / 2 rows
-                mbar_expect_tx(&full_x[xs], (uint32_t)(p.x_rows * p.row_bytes));
-                tma_load_3d(dst, &xmap, 0, row0, b, &full_x[xs]);
-                tma_load_3d(dst + (p.x_rows / 2) * p.row_bytes, &xmap, 0, row0 + p.x_rows / 2, b, &full_x[xs]);
+                if (p.ablate & 8) mbar_arrive(&full_x[xs]);
+                else {
+                    mbar_expect_tx(&full_x[xs], (uint32_t)(p.x_rows * p.row_bytes));
+                    tma_load_3d(dst, &xmap, 0, row0, b, &full_x[xs]);
+                    tma_load_3d(dst + (p.x_rows / 2) * p.row_bytes, &xmap, 0, row0 + p.x_rows / 2, b, &full_x[xs]);
+                }
             }
             __syncwarp();
             if (++xs == (uint32_t)p.n_x_stages) { xs = 0; xph ^= 1; }
@@ -150,6 +155,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         auto conv = [&](uint32_t d_tmem, uint32_t a_lo0, uint32_t tap_step, uint32_t w_lo) {
             uint32_t acc = 0;
             uint32_t a_tap = a_lo0, b_tap = w_lo;
+            if (p.ablate & 1) return;
 #pragma unroll 1
             for (int j = 0; j < K; ++j) {
 #pragma unroll
@@ -228,6 +234,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             {
                 const int tm = o0 - p.p2 + row;                    // sequence position of this xt row
                 const bool in_seq = tm >= 0 && tm < valid;         // conv2 sees zeros outside the (valid) sequence
+                const bool edge = __any_sync(0xffffffffu, !in_seq);   // (warp-uniform: the common tile skips the zeroing altogether)
                 if (ACC) {      // running-sum row this thread adds in epilogue B: pull it into L2 a conv ahead (row <= 128 B)
                     const int to = o0 + row;
                     if (row < p.m_out && to < p.L)
@@ -244,18 +251,31 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     tmem_ld16x2_sum(taddr, taddr + (uint32_t)C, v);
                     const float4* bp = reinterpret_cast<const float4*>(bias1 + n0);
                     uint32_t hw[8], lw[8];
+                    if (p.ablate & 32) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) { hw[k2] = __float_as_uint(v[2 * k2]); lw[k2] = __float_as_uint(v[2 * k2 + 1]); }
+                    } else {
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const float4 bv = bp[k4];
-                        v[4 * k4] += bv.x; v[4 * k4 + 1] += bv.y; v[4 * k4 + 2] += bv.z; v[4 * k4 + 3] += bv.w;
+                        add2(v[4 * k4], v[4 * k4 + 1], bv.x, bv.y);
+                        add2(v[4 * k4 + 2], v[4 * k4 + 3], bv.z, bv.w);
                     }
 #pragma unroll
                     for (int k2 = 0; k2 < 8; ++k2) {
                         float a0 = v[2 * k2], a1 = v[2 * k2 + 1];
-                        a0 = in_seq ? fmaxf(a0, a0 * p.mid_slope) : 0.f;
-                        a1 = in_seq ? fmaxf(a1, a1 * p.mid_slope) : 0.f;
+                        float t0 = a0, t1 = a1;
+                        mul2(t0, t1, p.mid_slope, p.mid_slope);
+                        a0 = fmaxf(a0, t0);
+                        a1 = fmaxf(a1, t1);
                         split2(a0, a1, 0, hw[k2], lw[k2]);
                     }
+                    if (edge && !in_seq) {                         // rows outside the sequence: only in a sequence's first / last tiles
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) hw[k2] = lw[k2] = 0u;
+                    }
+                    }
+                    if (p.ablate & 16) continue;
                     // 16-byte chunks of the row: hi channels n0.. -> chunks n0/8, n0/8 + 1; lo -> lo_off/16 + the same
                     const uint32_t ch = (uint32_t)n0 >> 3, cl = ((uint32_t)p.lo_off >> 4) + ch;
                     *reinterpret_cast<uint4*>(mrow + ((ch ^ swz) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -276,7 +296,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 const size_t row_el = ((size_t)b * p.L + to) * pitch;
                 uint4 R[4], A[4];
                 auto request = [&](int n0) {
-                    if (!row_ok) return;
+                    if (!row_ok || (p.ablate & 4)) return;
                     ld_global_nc_v8(p.res + row_el + n0, R[0], R[1]);
                     ld_global_nc_v8(p.res + row_el + C + n0, R[2], R[3]);
                     if (ACC) {
@@ -297,20 +317,26 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&b_empty[st]);
                     }
-                    if (row_ok) {
+                    if (row_ok && (p.ablate & 32)) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) { hw[k2] = __float_as_uint(v[2 * k2]); lw[k2] = __float_as_uint(v[2 * k2 + 1]); }
+                    }
+                    if (row_ok && !(p.ablate & 32)) {
                         const float4* bp = reinterpret_cast<const float4*>(bias2 + n0);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const float4 bv = bp[k4];
-                            v[4 * k4] += bv.x; v[4 * k4 + 1] += bv.y; v[4 * k4 + 2] += bv.z; v[4 * k4 + 3] += bv.w;
+                            add2(v[4 * k4], v[4 * k4 + 1], bv.x, bv.y);
+                            add2(v[4 * k4 + 2], v[4 * k4 + 3], bv.z, bv.w);
                         }
                         const uint32_t hh[8] = {R[0].x, R[0].y, R[0].z, R[0].w, R[1].x, R[1].y, R[1].z, R[1].w};
                         const uint32_t ll[8] = {R[2].x, R[2].y, R[2].z, R[2].w, R[3].x, R[3].y, R[3].z, R[3].w};
 #pragma unroll
                         for (int k2 = 0; k2 < 8; ++k2) {
                             const float2 r = join2(hh[k2], ll[k2], 0);
-                            v[2 * k2] += fminf(r.x, r.x * p.res_unslope);
-                            v[2 * k2 + 1] += fminf(r.y, r.y * p.res_unslope);
+                            float tx = r.x, ty = r.y;
+                            mul2(tx, ty, p.res_unslope, p.res_unslope);
+                            add2(v[2 * k2], v[2 * k2 + 1], fminf(r.x, tx), fminf(r.y, ty));      // undo the stored leaky relu
                         }
                         if (ACC) {
                             const uint32_t ah[8] = {A[0].x, A[0].y, A[0].z, A[0].w, A[1].x, A[1].y, A[1].z, A[1].w};
@@ -318,27 +344,31 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 #pragma unroll
                             for (int k2 = 0; k2 < 8; ++k2) {
                                 const float2 r = join2(ah[k2], al[k2], 0);
-                                v[2 * k2] = r.x + v[2 * k2];
-                                v[2 * k2 + 1] = r.y + v[2 * k2 + 1];
+                                add2(v[2 * k2], v[2 * k2 + 1], r.x, r.y);
                             }
                         }
                         const float sc = live ? p.scale : 0.f;
 #pragma unroll
                         for (int k2 = 0; k2 < 8; ++k2) {
-                            float a0 = v[2 * k2] * sc, a1 = v[2 * k2 + 1] * sc;
-                            a0 = fmaxf(a0, a0 * p.post_slope);
-                            a1 = fmaxf(a1, a1 * p.post_slope);
+                            float a0 = v[2 * k2], a1 = v[2 * k2 + 1];
+                            mul2(a0, a1, sc, sc);
+                            float t0 = a0, t1 = a1;
+                            mul2(t0, t1, p.post_slope, p.post_slope);
+                            a0 = fmaxf(a0, t0);
+                            a1 = fmaxf(a1, t1);
                             split2(a0, a1, 0, hw[k2], lw[k2]);
                         }
                         if (n0 + 16 < C) request(n0 + 16);
-                        if (!p.tma_out) {
+                    }
+                    if (row_ok) {
+                        if (!p.tma_out && !(p.ablate & 2)) {
                             __nv_bfloat16* oh = p.out + row_el + n0;
                             __nv_bfloat16* ol = oh + C;
                             st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
                             st_global_v8(ol, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
                         }
                     }
-                    if (p.tma_out) {
+                    if (p.tma_out && !(p.ablate & 2)) {
                         // the warp parks its [32 rows x 16 ch] hi / lo tiles in shared memory (32B swizzle) and one lane hands them to
                         // the TMA unit: row-per-thread 32-byte global stores cost ~50 L1 wavefronts per instruction.  The last warp of a
                         // tile owns fewer than 32 output rows (m_out < 128): it uses the map whose box has exactly that many.
@@ -397,6 +427,8 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     PairParams p{};
     p.w1 = a.w1; p.w2 = a.w2; p.bias1 = a.bias1; p.bias2 = a.bias2; p.res = a.x; p.accin = a.accin; p.out = a.out;
     p.lens = a.lens; p.len_mul = a.len_mul;
+    static const int ablate = getenv("PB_TP_ABLATE") ? atoi(getenv("PB_TP_ABLATE")) : 0;
+    p.ablate = ablate;
     p.B = a.B; p.L = a.L; p.C = a.C; p.K = a.K; p.D = a.D;
     p.p1 = (a.K - 1) * a.D / 2; p.p2 = (a.K - 1) / 2; p.m_out = TP_M - (a.K - 1);
     p.ksteps = a.C / 16;
@@ -412,13 +444,20 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     p.smem_w1_off = 2048;
     p.smem_w2_off = p.smem_w1_off + (uint32_t)round_up(p.w_bytes, 1024);
     p.smem_mid_off = p.smem_w2_off + (uint32_t)round_up(p.w_bytes, 1024);
-    p.smem_x_off = p.smem_mid_off + (uint32_t)TP_STAGES * (uint32_t)p.mid_bytes;
+    // Tiles in flight (= epilogue groups = accumulator / xt stages).  The k <= 7 launches are bound by the per-tile chain conv1 -> xt ->
+    // conv2 -> output, not by the tensor pipe: a fourth group buys 4-8 % there (per launch at 8 x 1024 units: k = 3 107 -> 99 us at
+    // C = 16, 115 -> 110 at C = 32; k = 7 152 -> 140 / 153 -> 141).  At k = 11 (tensor-bound; fewer x stages) and with the running sum
+    // (96 registers per thread: spills) it costs 5-15 us, so those keep three.  PB_TP_GROUPS=3/4 forces it where it fits.
+    static const int ng_env = getenv("PB_TP_GROUPS") ? atoi(getenv("PB_TP_GROUPS")) : 0;
+    int ng = ng_env == 3 || ng_env == 4 ? ng_env : (!a.accin && a.K <= 7 ? 4 : 3);
+    if (ng == 4 && (p.smem_mid_off + 4u * (uint32_t)p.mid_bytes + 2u * (uint32_t)p.x_stage_bytes + 2048u > TP_SMEM_LIMIT || 8 * 2 * a.C > 512)) ng = 3;
+    p.smem_x_off = p.smem_mid_off + (uint32_t)ng * (uint32_t)p.mid_bytes;
     const uint32_t left = TP_SMEM_LIMIT - 1024u - p.smem_x_off;
     // TMA-store epilogue: 2 KB of staging per epilogue warp, when at least 3 xt stages remain (PB_TC_TMA_OUT=0 disables).  Measured
     // per launch on B200: -6 us at C = 32 (k = 3), but +5 .. +30 us at C = 16, where the kernel is bound by shared-memory traffic
     // (narrow A-operand reads + the xt tile) and the staging tiles add to it - so 32-channel layers only.
     static const int tma_out_mode = getenv("PB_TC_TMA_OUT") ? atoi(getenv("PB_TC_TMA_OUT")) : 1;
-    const uint32_t stage_bytes = (uint32_t)TP_GROUPS * 4u * 2048u;
+    const uint32_t stage_bytes = (uint32_t)ng * 4u * 2048u;
     p.tma_out = (tma_out_mode > 0 && a.C == 32 && left >= stage_bytes + 3u * (uint32_t)p.x_stage_bytes && p.m_out > 96) ? 1 : 0;
     p.n_x_stages = (int)((left - (p.tma_out ? stage_bytes : 0u)) / (uint32_t)p.x_stage_bytes);
     if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
@@ -435,7 +474,7 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     p.idesc_stack = (1u << 4) | ab_fmt | ((uint32_t)((2 * a.C) >> 3) << 17) | ((uint32_t)(TP_M >> 4) << 24);
     p.acc_cols = 2 * a.C;
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * TP_STAGES * p.acc_cols) p.tmem_cols *= 2;
+    while (p.tmem_cols < 2 * ng * p.acc_cols) p.tmem_cols *= 2;
 
     // x tile = two boxes of x_rows / 2 rows (a TMA box holds at most 256 rows)
     CUtensorMap xmap;
@@ -448,32 +487,28 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     }
 
     static int n_sm = 0;
+    typedef void (*PairKernel)(CUtensorMap, CUtensorMap, CUtensorMap, PairParams);
+    static const PairKernel kernels[2][2][2] = {      // [accin][ksteps - 1][ng - 3]
+        {{tc_pair_kernel<false, 1, 3>, tc_pair_kernel<false, 1, 4>}, {tc_pair_kernel<false, 2, 3>, tc_pair_kernel<false, 2, 4>}},
+        {{tc_pair_kernel<true, 1, 3>, tc_pair_kernel<true, 1, 4>}, {tc_pair_kernel<true, 2, 3>, tc_pair_kernel<true, 2, 4>}}};
     static bool attr_set = false;
     if (!attr_set) {
         int dev = 0;
         PB_CUDA(cudaGetDevice(&dev));
         PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        for (int i = 0; i < 8; ++i)
+            PB_CUDA(cudaFuncSetAttribute(kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
         attr_set = true;
     }
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(128u + 128u * (unsigned)ng); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool no_pdl = getenv("PB_TC_NO_PDL") != nullptr;      // dev switch, as in tc_conv.cu
     cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-    if (p.ksteps == 1) {
-        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 1>, xmap, omap, omap_tail, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 1>, xmap, omap, omap_tail, p));
-    } else {
-        if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<true, 2>, xmap, omap, omap_tail, p));
-        else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair_kernel<false, 2>, xmap, omap, omap_tail, p));
-    }
+    PB_CUDA(cudaLaunchKernelEx(&cfg, kernels[a.accin ? 1 : 0][p.ksteps - 1][ng - 3], xmap, omap, omap_tail, p));
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -5,6 +5,7 @@
   PB_TC_CLUSTER=0     single-CTA path instead of CTA pairs
   PB_TC_PAIR64=0      the 64-channel k = 7 / 11 layers as one CTA per SM instead of CTA pairs
   PB_TC_CL_RESIDENT=0 CTA pairs always stream their weights (no resident halves)
+  PB_TP_GROUPS=3/4    tiles in flight in the fused ResBlock-step kernel of the 32 / 16-channel stages (default: per layer)
 Each case runs in a fresh interpreter because the library reads its switches once.
 """
 import os
@@ -16,7 +17,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
-SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_TC_PAIR64", "PB_TC_CL_RESIDENT", "PB_LIB_VARIANT")
+SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_TC_PAIR64", "PB_TC_CL_RESIDENT", "PB_TP_GROUPS", "PB_LIB_VARIANT")
 
 CODE = r"""
 import sys, numpy as np, torch
@@ -86,3 +87,9 @@ def test_cta_pair_placement_switches_are_bit_identical(tmp_path, baseline, switc
     # where a layer runs (one CTA per SM, a CTA pair streaming its weights, a pair with resident halves) changes neither the order of
     # the K loop nor the products: same bits
     _same(baseline, _run(tmp_path, switch.lower(), {switch: "0"}))
+
+
+@pytest.mark.parametrize("groups", ["3", "4"])
+def test_fused_pair_groups_are_bit_identical(tmp_path, baseline, groups):
+    # how many tiles the fused conv1 -> conv2 kernel keeps in flight is scheduling only
+    _same(baseline, _run(tmp_path, "tpgroups" + groups, {"PB_TP_GROUPS": groups}))
