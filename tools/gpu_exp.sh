@@ -1,17 +1,15 @@
 #!/bin/bash
-# scratch: tc_pair issue order (PB_TP_ORDER) x tiles in flight (PB_TP_GROUPS), per-launch, same box
+# scratch: validation of the settled fused-pair kernels + per-launch list, same box
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_voc_gpu.py tests/test_switches_gpu.py -x -q -m gpu 2>&1 | tail -4
 run() {  # name env...
   local name=$1; shift
   env "$@" timeout 300 ncu -k regex:tc_pair --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/ablp_$name.csv \
       python tools/prof_voc.py 8 1024 1 0 > /dev/null 2>&1; echo "$name rc=$?"
 }
-run o0 PB_TP_ORDER=0
-run o1 PB_TP_ORDER=1
-run o1g3 PB_TP_ORDER=1 PB_TP_GROUPS=3
-run o1g4 PB_TP_ORDER=1 PB_TP_GROUPS=4
-run o0b PB_TP_ORDER=0
-python - o0 o1 o1g3 o1g4 o0b <<'PY'
+run t0 PB_TP_TOEPLITZ=0
+run tdef PB_X=1
+python - t0 tdef <<'PY'
 import csv, sys
 names = [f"s{s} k{k} d{d}" for s in (4, 5) for k in (3, 7, 11) for d in (1, 3, 5)]
 cols = []
@@ -21,7 +19,7 @@ for a in sys.argv[1:]:
     cols.append([float(r[h.index("Metric Value")].replace(",", "")) / 1e3 for r in rows[1:] if r[h.index("Metric Name")] == "gpu__time_duration.sum"])
 print(f"{'launch':12s} " + " ".join(f"{a:>7s}" for a in sys.argv[1:]))
 for i, n in enumerate(names):
-    print(f"{n:12s} " + " ".join(f"{c[i]:7.1f}" if i < len(c) else "    nan" for c in cols))
+    if i >= 9: print(f"{n:12s} " + " ".join(f"{c[i]:7.1f}" if i < len(c) else "    nan" for c in cols))
 print(f"{'total us':12s} " + " ".join(f"{sum(c[:18]):7.0f}" for c in cols))
 PY
-for o in 0 1; do PB_TP_ORDER=$o python tools/dev_ab.py 8 1024; done 2>&1 | grep AB
+for o in 0 x 0 x; do if [ $o = x ]; then python tools/dev_ab.py 32 2048; else PB_TP_TOEPLITZ=0 python tools/dev_ab.py 32 2048; fi; done 2>&1 | grep AB
