@@ -60,6 +60,52 @@ def test_voc_oracle_vs_reference(seed, B, T):
     np.testing.assert_allclose(wav2.numpy(), ref.numpy(), atol=2e-5, rtol=0)
 
 
+def test_voc_oracle_vs_reference_other_geometry():
+    """The HiFi-GAN shape of tests/test_voc_gpu.py::test_other_hifigan_geometry_matches_oracle (x16, kernels 5 / 9, dilations (1, 2, 4) /
+    (1, 3, 5)): the reference builds it from the same `h` (utils/vocoder/models.py:72-93) - pins the oracle there too."""
+    h = configs.default_vocoder_config()
+    h.update({"upsample_rates": [4, 2, 2], "upsample_kernel_sizes": [8, 4, 4], "upsample_initial_channel": 128,
+              "resblock_kernel_sizes": [5, 9], "resblock_dilation_sizes": [[1, 2, 4], [1, 3, 5]], "code_hop_size": 16})
+    sd = synth.synth_vocoder_state_dict(h, seed=23, weight_norm=True)
+    gen = ref_shim.load_reference_vocoder(h)
+    gen.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(77)
+    code = torch.randint(0, 1000, (3, 300), generator=g)
+    spkr = torch.randint(0, 10, (3, 1), generator=g)
+    with torch.no_grad():
+        ref = gen(code=code, spkr=spkr)
+    wav = voc_oracle.code_generator_forward(sd, h, code, spkr)
+    assert ref.shape == (3, 1, 4800)
+    np.testing.assert_allclose(wav.numpy(), ref.numpy(), atol=2e-5, rtol=0)
+
+
+@pytest.mark.parametrize("n_head", [2, 4])
+def test_tte_oracle_vs_reference_other_geometry(n_head):
+    """The transformer shape of tests/test_tte_gpu.py::test_other_transformer_geometry_matches_oracle (2 / 3 layers, FFN 512 x 5 taps,
+    500 codes, 2 or 4 heads), built by the reference from the same config (modules/parrot.py:22-53)."""
+    cfg = configs.default_tte_config()
+    tr = cfg["transformer"]
+    tr["encoder"]["n_layer"], tr["decoder"]["n_layer"] = 2, 3
+    tr["encoder"]["n_head"] = tr["decoder"]["n_head"] = n_head
+    tr["conv_n_filter"], tr["conv_kernel_sizes"] = 512, [5, 1]
+    cfg["preprocess"]["hubert_codes"] = 500
+    sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=31)
+    ref = ref_shim.load_reference_parrot(cfg, 150, 0, 10)
+    ref.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(12)
+    phones = torch.randint(2, 150, (3, 41), generator=g)
+    phones[1, 17:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([1, 7, 3])}
+    with torch.no_grad():
+        logits, _, tgt_mask, log_dur = ref(batch, inference=True)
+        ids_ref = ref.infer(batch)
+    ids, r = tte_oracle.parrot_infer(sd, batch, n_head=n_head)
+    assert ids == ids_ref and logits.shape[-1] == 500
+    assert torch.equal(r["tgt_mask"], tgt_mask)
+    np.testing.assert_allclose(r["log_dur"].numpy(), log_dur.numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(r["logits"].numpy(), logits.numpy(), atol=5e-4, rtol=0)
+
+
 def test_tte_oracle_vs_reference_single_speaker():
     # speakers.json with one entry: the reference builds no speaker_emb (modules/parrot.py:28-32) and adds nothing (:98-99)
     cfg = configs.default_tte_config()

@@ -401,3 +401,38 @@ def test_infer_ragged_single_speaker_and_zero_duration_items():
         m.duration_predictor.proj.weight.zero_(); m.duration_predictor.proj.bias.fill_(-20.0)
     ids0, n0 = m.infer_ragged(phones.to(DEV), torch.tensor(lens))
     assert ids0.shape == (3, 0) and n0.tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("mode,n_head", [(0, 2), (1, 2), (0, 4)])
+def test_other_transformer_geometry_matches_oracle(mode, n_head):
+    """A transformer shape the reference's default.yaml does not use (modules/parrot.py builds any of them from the config): 2 encoder /
+    3 decoder layers, FFN 512 filters with a 5-tap first conv, 500 unit codes, and (fp32 path) 4 heads of 64.  Ids identical to the oracle
+    wherever its top-2 margin is clear, durations and masks identical."""
+    cfg = _cfg()
+    tr = cfg["transformer"]
+    tr["encoder"]["n_layer"], tr["decoder"]["n_layer"] = 2, 3
+    tr["encoder"]["n_head"] = tr["decoder"]["n_head"] = n_head
+    tr["conv_n_filter"], tr["conv_kernel_sizes"] = 512, [5, 1]
+    cfg["preprocess"]["hubert_codes"] = 500
+    sd = synth.synth_tte_state_dict(cfg, VOCAB, 0, NSPK, seed=31)
+    m = Parrot(cfg, VOCAB, 0)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(DEV)
+    m.gemm_mode = mode
+    g = _gen(12)
+    phones = torch.randint(2, VOCAB, (3, 41), generator=g)
+    phones[1, 17:] = 0
+    batch = {"phones": phones, "src_mask": phones != 0, "speaker": torch.tensor([1, 7, 3])}
+    ids_ref, r = tte_oracle.parrot_infer(sd, batch, n_head=n_head)
+    assert r["logits"].shape[-1] == 500 and tte_oracle._n_layers(sd, "encoder_layers") == 2 and tte_oracle._n_layers(sd, "decoder_layers") == 3
+    ids = m.infer(_to_dev(batch))
+    logits, _, tgt_mask, log_dur = m(_to_dev(batch), inference=True)
+    assert torch.equal(tgt_mask.cpu(), r["tgt_mask"])
+    assert torch.allclose(log_dur.cpu(), r["log_dur"], atol=5e-5, rtol=0)
+    assert torch.allclose(logits.cpu(), r["logits"], atol=3e-3, rtol=0), float((logits.cpu() - r["logits"]).abs().max())
+    top2 = torch.topk(r["logits"], 2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]
+    for b, (a, e) in enumerate(zip(ids, ids_ref)):
+        assert len(a) == len(e)
+        for t, (u, v) in enumerate(zip(a, e)):
+            assert u == v or margin[b, t] < 1e-4, (b, t, float(margin[b, t]))
