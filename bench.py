@@ -411,7 +411,7 @@ def resblock_roofline(b, sec_ms, units, ms_step, workload):
     traffic, traffic_src = measured_traffic(workload)
     r = {
         "bound": "hbm",
-        "kernel": "tc_conv_kernel + tc_pair_kernel (the 90 ResBlock1 dilated convs as tcgen05 implicit GEMMs on split-bf16 operands; "
+        "kernel": "tc_conv_kernel + tc_pair_kernel + tc_pair16_kernel (the 90 ResBlock1 dilated convs as tcgen05 implicit GEMMs on split-bf16 operands; "
                   "lrelu + bias + residual + resblock mean fused in the epilogues)",
         "achieved": achieved, "peak": b.hbm_peak, "unit": "GB/s", "frac": achieved / b.hbm_peak,
         "traffic": traffic, "traffic_source": traffic_src,

@@ -11,7 +11,7 @@ def load(f):
         if r[im] != "gpu__time_duration.sum":
             continue
         per[r[iid]] = (r[ik].split("(")[0].replace("void ", "").replace("pb::", ""), float(r[iv].replace(",", "")) / 1e3)
-    out = [v for v in per.values() if v[0].startswith(("tc_conv_kernel", "tc_pair_kernel", "conv_post", "voc_embed"))]
+    out = [v for v in per.values() if v[0].startswith(("tc_conv_kernel", "tc_pair_kernel", "tc_pair16_kernel", "conv_post", "voc_embed"))]
     return out
 
 def label(i):      # launch index inside one tensor-core forward (80 launches: embed, conv_pre, 5 x (ups + 18 or 9 resblock launches), conv_post)

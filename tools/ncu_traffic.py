@@ -15,7 +15,7 @@ def launches(f):
     for r in rows[1:]:
         d = per.setdefault(r[iid], {"name": r[ik].split("(")[0].replace("void ", "").replace("pb::", "")})
         d[r[im]] = float(r[iv].replace(",", ""))
-    return [d for d in per.values() if d["name"].startswith(("tc_conv_kernel", "tc_pair_kernel", "conv_post", "voc_embed"))]
+    return [d for d in per.values() if d["name"].startswith(("tc_conv_kernel", "tc_pair_kernel", "tc_pair16_kernel", "conv_post", "voc_embed"))]
 
 
 def resblock_indices():      # inside one tensor-core forward: embed, conv_pre, 5 x (ups, 18 or 9 resblock launches), conv_post

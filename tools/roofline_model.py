@@ -54,7 +54,15 @@ def expected(B, T):
             for m in range(N_DIL):
                 last = m == N_DIL - 1
                 extra = (1 if (last and j > 0) else 0)              # running ResBlock sum read back
-                if c <= 32:                                           # fused pair: tiles of 128 xt rows -> 128 - (k - 1) output rows
+                if c == 16 and k >= 7 and not extra:
+                    # tc_pair16: super tile = 4 conv1 M tiles -> 4 (512 - (k - 1)) // 4 output rows; conv2 time-grouped (G = 4):
+                    # G + k - 1 k-steps of {N = 128 stacked, N = 64}
+                    m_out = 4 * ((512 - (k - 1)) // 4)
+                    tiles = -(-rows // m_out)
+                    cyc = tiles * (4 * k * kstep_cycles(16) + (4 + k - 1) * (mma_cycles(128) + mma_cycles(64)))
+                    out.append(dict(name=f"s{i + 1} k{k} d{(1, 3, 5)[m]} pair C={c} tg", cycles=cyc,
+                                    bytes=act * (1 + 1 + extra) + 2 * w(c, c, k)))
+                elif c <= 32:                                         # fused pair: tiles of 128 xt rows -> 128 - (k - 1) output rows
                     tiles = -(-rows // (128 - (k - 1)))
                     cyc = tiles * 2 * k * (c // 16) * kstep_cycles(c)
                     halo = 128.0 / (128 - (k - 1))
