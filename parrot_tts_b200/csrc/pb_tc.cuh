@@ -79,6 +79,7 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st);
 // 3-D TMA map over split 16-bit activations [B][L][2C] (box: box_c channels x rows positions), shared by tc_conv.cu / tc_pair.cu
 int tc_make_tmap_act(CUtensorMap* map, const __nv_bfloat16* base, int C, int L, int B, int box_c, int rows, bool sw128);
 int tc_make_tmap_out(CUtensorMap* map, __nv_bfloat16* base, int C, int L, int B, int rows);
+int tc_make_tmap_grouped16(CUtensorMap* map, const __nv_bfloat16* base, int L, int B, int rows);
 
 // layout conversion (test entry points, embedding stage): f32 [B][C][L] (row stride pitch) <-> split-bf16 [B][L][2C]
 int launch_f32_to_split(const float* x, int64_t pitch, __nv_bfloat16* y, int B, int C, int L, float pre_slope, cudaStream_t st);

@@ -748,6 +748,23 @@ int tc_make_tmap_out(CUtensorMap* map, __nv_bfloat16* base, int C, int L, int B,
     return PB_OK;
 }
 
+// 4-D map over a split 16-channel tensor [B][L][32] seen as [B][L / 4 groups][4 positions][32] (tc_pair16_kernel's epilogue B: a
+// box = one position of `rows` consecutive groups = `rows` 64-byte rows, 64B swizzle; L must be a multiple of 4)
+int tc_make_tmap_grouped16(CUtensorMap* map, const __nv_bfloat16* base, int L, int B, int rows) {
+    EncodeTiledFn fn = encode_fn();
+    PB_REQUIRE(fn != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    PB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && L % 4 == 0, PB_ERR_INVALID, "tc_pair16: base alignment / L=%d not a multiple of 4", L);
+    PB_REQUIRE(rows >= 1 && rows <= 256, PB_ERR_INVALID, "tc_pair16: box of %d rows", rows);
+    cuuint64_t gdim[4] = {32, 4, (cuuint64_t)(L / 4), (cuuint64_t)B};
+    cuuint64_t gstr[3] = {64, 256, (cuuint64_t)64 * L};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_REQUIRE(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled(grouped16) failed (%d): L=%d B=%d rows=%d", (int)r, L, B, rows);
+    return PB_OK;
+}
+
 int launch_tc_conv(const TcConvArgs& a, cudaStream_t st) {
     PB_REQUIRE(a.x && a.w && (a.out || a.out_f32 || a.argmax_key), PB_ERR_INVALID, "tc_conv: null tensor");
     PB_REQUIRE(!a.argmax_key || (a.U == 1 && a.argmax_n > 0 && a.argmax_n <= a.N && !a.res && !a.accin), PB_ERR_INVALID,

@@ -441,16 +441,17 @@ struct Pair16Params {
     int B, L, K, D;
     int p1, p2, rows_out, m_out, n_ksteps2;
     int x_rows, x_stage_bytes, n_x_stages, w1_bytes;
-    uint32_t smem_bias_off, smem_w1_off, smem_w2_off, smem_xt_off, smem_x_off;
+    uint32_t smem_bias_off, smem_w1_off, smem_w2_off, smem_xt_off, smem_rz_off, smem_x_off;
     int tiles_t, total_tiles;
     float mid_slope, post_slope, scale, res_unslope;
     int ablate;                    // PB_TP_ABLATE (profiling): 1 no MMAs, 2 no output stores, 4 no residual / running-sum loads, 64 no accumulator reads
 };
 }  // namespace
 
-template <bool ACC>
+template <bool ACC, bool TMAE>
 __global__ void __launch_bounds__(T16_THREADS, 1)
-tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p) {
+tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap omap,
+                 const __grid_constant__ CUtensorMap omap_tail, const Pair16Params p) {
     constexpr int C = T16_C;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -462,7 +463,9 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
     uint64_t* mid_full = a_empty + 8;                // [2] the stage's xt planes are complete
     uint64_t* b_full = mid_full + 2;                 // [2] conv2 accumulator ready
     uint64_t* w_full = b_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    uint64_t* rz_full = w_full + 1;                  // (TMAE) the residual rows of a super tile are in shared memory
+    uint64_t* rz_empty = rz_full + 1;                // (TMAE) ... and its output rows have left it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rz_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sm_base = smem_u32(sm);
@@ -473,6 +476,8 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
         for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(&mid_full[s], 16); mbar_init(&b_full[s], 1); }
         mbar_init(w_full, 1);
+        mbar_init(rz_full, 1); mbar_init(rz_empty, 16);
+        if (TMAE) { prefetch_tmap(&rmap); prefetch_tmap(&omap); prefetch_tmap(&omap_tail); }
         fence_mbar_init();
     }
     {   // biases; zeroed xt planes (the positions past 511 are read, never used: keep them finite); the Toeplitz operand of conv2
@@ -570,6 +575,24 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
                 }
                 __syncwarp();
                 if (++xs == (uint32_t)p.n_x_stages) { xs = 0; xph ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // =========================== (TMAE) residual rows of every super tile -> shared memory ===========================
+        // Four boxes, one per position g of a group: `rows` consecutive groups x 64 bytes (hi | lo), 64B-swizzled - the layout in which
+        // a lane's row is a conflict-free 16-byte access.  Single buffer: refilled once every epilogue warp's output store has read it.
+        if (TMAE) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            int i = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+                const int b = tile / tiles_per_b, rem = tile - b * tiles_per_b;
+                if (i > 0) mbar_wait(rz_empty, (uint32_t)(i - 1) & 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(rz_full, 4u * 128u * 64u);
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_4d(sm + p.smem_rz_off + g * 8192, &rmap, 0, g, rem * p.rows_out, b, rz_full);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 3) {
@@ -686,7 +709,7 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
             const int tile = blockIdx.x + i * (int)gridDim.x;
             const int b = tile / tiles_per_b, rem = tile - b * tiles_per_b;
             const int to = rem * p.m_out + 4 * row + grp;
-            if (!(row < p.rows_out && to < p.L) || (p.ablate & 4)) return;
+            if (TMAE || !(row < p.rows_out && to < p.L) || (p.ablate & 4)) return;
             const size_t row_el = ((size_t)b * p.L + to) * 32;
             ld_global_nc_v8(p.res + row_el, R[0], R[1]);
             ld_global_nc_v8(p.res + row_el + C, R[2], R[3]);
@@ -704,13 +727,24 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
             const bool row_ok = row < p.rows_out && to < p.L;
             const bool live = to < valid_of(b);
             const size_t row_el = ((size_t)b * p.L + to) * 32;
+            uint8_t* rrow = sm + p.smem_rz_off + grp * 8192 + row * 64;      // (TMAE) this thread's residual row, then its output row
+            const uint32_t rsw = ((uint32_t)row >> 1) & 3u;                     // 64B swizzle: 16-byte chunk ^= (row / 2) % 4
+            if (TMAE) {
+                mbar_wait(rz_full, (uint32_t)i & 1u);
+                R[0] = *reinterpret_cast<const uint4*>(rrow + ((0u ^ rsw) << 4));
+                R[1] = *reinterpret_cast<const uint4*>(rrow + ((1u ^ rsw) << 4));
+                R[2] = *reinterpret_cast<const uint4*>(rrow + ((2u ^ rsw) << 4));
+                R[3] = *reinterpret_cast<const uint4*>(rrow + ((3u ^ rsw) << 4));
+            }
             mbar_wait(&b_full[st], n & 1u);
             tc_fence_after();
             float v[16];
             const uint32_t taddr = tmem_base + lane_off + 256u + st * 128u + 16u * (uint32_t)grp;
             if (p.ablate & 64) { for (int z = 0; z < 16; ++z) v[z] = 1.0f; } else tmem_ld16x2_sum(taddr, taddr + 64u, v);
             tc_fence_before();          // (ordered before conv2(i + 2) by this warp's mid_full arrival of A(i + 2))
-            if (!row_ok || (p.ablate & 32)) return;
+            if (!TMAE && (!row_ok || (p.ablate & 32))) return;
+            uint32_t hw[8], lw[8];
+            if (row_ok) {
             const float4* bp = reinterpret_cast<const float4*>(bias2);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
@@ -737,7 +771,6 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
                 }
             }
             const float sc = live ? p.scale : 0.f;
-            uint32_t hw[8], lw[8];
 #pragma unroll
             for (int k2 = 0; k2 < 8; ++k2) {
                 float a0 = v[2 * k2], a1 = v[2 * k2 + 1];
@@ -748,7 +781,30 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
                 a1 = fmaxf(a1, t1);
                 split2(a0, a1, 0, hw[k2], lw[k2]);
             }
-            if (p.ablate & 2) return;
+            }
+            if (TMAE) {
+                // the output row replaces the residual row in place; one lane hands the warp's 32 rows (the last warp: rows_out - 96) to
+                // the TMA unit, which clips the groups past the end of the sequence
+                if (row_ok) {
+                    *reinterpret_cast<uint4*>(rrow + ((0u ^ rsw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(rrow + ((1u ^ rsw) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    *reinterpret_cast<uint4*>(rrow + ((2u ^ rsw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    *reinterpret_cast<uint4*>(rrow + ((3u ^ rsw) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!(p.ablate & 2) && o0 + 128 * q < p.L) {
+                        tma_store_4d(q == 3 ? &omap_tail : &omap, sm + p.smem_rz_off + grp * 8192 + q * 2048, 0, grp, rem * p.rows_out + q * 32, b);
+                        bulk_commit_group();
+                        bulk_wait_group_read<0>();
+                    }
+                    mbar_arrive(rz_empty);
+                }
+                __syncwarp();
+                return;
+            }
+            if (p.ablate & 2 || !row_ok) return;
             __nv_bfloat16* oh = p.out + row_el;
             st_global_v8(oh, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
             st_global_v8(oh + C, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
@@ -761,6 +817,7 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const Pair16Params p)
         }
     }
 
+    if (TMAE && warp >= 4 && lane == 0) bulk_wait_group<0>();      // this lane's TMA stores have completed
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -796,7 +853,13 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
     p.smem_w1_off = 2048;
     p.smem_w2_off = p.smem_w1_off + (uint32_t)round_up(p.w1_bytes, 1024);
     p.smem_xt_off = p.smem_w2_off + (uint32_t)p.n_ksteps2 * 4096u;
-    p.smem_x_off = p.smem_xt_off + 4u * (uint32_t)T16_XT_PLANE;
+    // epilogue B through shared memory + TMA (residual rows in, output rows out, both as 128-byte wavefronts) instead of row-per-lane
+    // global accesses 256 bytes apart (32 wavefronts each): not with the running sum (a second 32 KB buffer does not fit), and the
+    // grouped maps need L % 4 == 0.  PB_TP_TMAE=0 disables.
+    static const int tmae_env = getenv("PB_TP_TMAE") ? atoi(getenv("PB_TP_TMAE")) : 1;
+    const bool tmae = tmae_env != 0 && !a.accin && a.L % 4 == 0;
+    p.smem_rz_off = p.smem_xt_off + 4u * (uint32_t)T16_XT_PLANE;
+    p.smem_x_off = p.smem_rz_off + (tmae ? 32768u : 0u);
     const uint32_t left = TP_SMEM_LIMIT - 1024u - p.smem_x_off;
     p.n_x_stages = (int)(left / (uint32_t)p.x_stage_bytes);
     if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
@@ -812,6 +875,12 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
 
     CUtensorMap xmap;
     PB_TRY(tc_make_tmap_act(&xmap, a.x, 16, a.L, a.B, 32, p.x_rows / 2, false));
+    CUtensorMap rmap = xmap, omap = xmap, omap_tail = xmap;      // only read when tmae
+    if (tmae) {
+        PB_TRY(tc_make_tmap_grouped16(&rmap, a.x, a.L, a.B, 128));
+        PB_TRY(tc_make_tmap_grouped16(&omap, a.out, a.L, a.B, 32));
+        PB_TRY(tc_make_tmap_grouped16(&omap_tail, a.out, a.L, a.B, p.rows_out - 96));
+    }
 
     static int n_sm = 0;
     static bool attr_set = false;
@@ -819,8 +888,9 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
         int dev = 0;
         PB_CUDA(cudaGetDevice(&dev));
         PB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
-        PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
         attr_set = true;
     }
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
@@ -831,8 +901,9 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool no_pdl = getenv("PB_TC_NO_PDL") != nullptr;
     cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-    if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<true>, xmap, p));
-    else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false>, xmap, p));
+    if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<true, false>, xmap, rmap, omap, omap_tail, p));
+    else if (tmae) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false, true>, xmap, rmap, omap, omap_tail, p));
+    else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false, false>, xmap, rmap, omap, omap_tail, p));
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -1,10 +1,26 @@
 #!/bin/bash
-# scratch: does backing off in mbarrier waits (fewer shared-memory polls while the tensor core streams its operands) help? same box
+# scratch: TMA-staged epilogue B of the time-grouped kernel (PB_TP_TMAE) - correctness, then per launch, same box
 mkdir -p gpurun_out
-for v in base sleep32 sleep200; do
-  PB_LIB_VARIANT=$( [ $v = base ] && echo "" || echo $v ) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/abl_$v.csv \
-      python tools/prof_voc.py 8 1024 1 0 > /dev/null 2>&1; echo "$v rc=$?"
-done
-python tools/ablate_table.py gpurun_out/abl_base.csv gpurun_out/abl_sleep32.csv gpurun_out/abl_sleep200.csv > gpurun_out/sleep_table.txt
-grep -n "launch\|s1 k3 d1\|s1 k11 d1\|s2 k7 d1\|s3 k\|s4 k\|s5 k\|total" gpurun_out/sleep_table.txt
-for v in "" sleep32 sleep200; do PB_LIB_VARIANT=$v python tools/dev_ab.py 8 1024; done 2>&1 | grep AB
+timeout 600 python -m pytest tests/test_switches_gpu.py tests/test_voc_gpu.py -x -q -m gpu -k "time_grouped or golden or ragged or rectangle or other_" 2>&1 | tail -4
+run() {  # name env...
+  local name=$1; shift
+  env "$@" timeout 300 ncu -k regex:tc_pair --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/ablp_$name.csv \
+      python tools/prof_voc.py 8 1024 1 0 > /dev/null 2>&1; echo "$name rc=$?"
+}
+run t0 PB_TP_TOEPLITZ=0
+run t1e0 PB_TP_TOEPLITZ=1 PB_TP_TMAE=0
+run t1e1 PB_TP_TOEPLITZ=1 PB_TP_TMAE=1
+run def PB_X=1
+python - t0 t1e0 t1e1 def <<'PY'
+import csv, sys
+names = [f"s{s} k{k} d{d}" for s in (4, 5) for k in (3, 7, 11) for d in (1, 3, 5)]
+cols = []
+for a in sys.argv[1:]:
+    rows = [r for r in csv.reader(l for l in open(f"gpurun_out/ablp_{a}.csv") if l.startswith('"'))]
+    h = rows[0]
+    cols.append([float(r[h.index("Metric Value")].replace(",", "")) / 1e3 for r in rows[1:] if r[h.index("Metric Name")] == "gpu__time_duration.sum"])
+print(f"{'launch':12s} " + " ".join(f"{a:>7s}" for a in sys.argv[1:]))
+for i, n in enumerate(names):
+    if i >= 9: print(f"{n:12s} " + " ".join(f"{c[i]:7.1f}" if i < len(c) else "    nan" for c in cols))
+print(f"{'18 pairs':12s} " + " ".join(f"{sum(c[:18]):7.0f}" for c in cols))
+PY
