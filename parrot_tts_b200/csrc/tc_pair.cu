@@ -450,8 +450,8 @@ struct Pair16Params {
 
 template <bool ACC, bool TMAE>
 __global__ void __launch_bounds__(T16_THREADS, 1)
-tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap omap,
-                 const __grid_constant__ CUtensorMap omap_tail, const Pair16Params p) {
+tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap amap,
+                 const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap_tail, const Pair16Params p) {
     constexpr int C = T16_C;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -477,7 +477,7 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         for (int s = 0; s < 2; ++s) { mbar_init(&mid_full[s], 16); mbar_init(&b_full[s], 1); }
         mbar_init(w_full, 1);
         mbar_init(rz_full, 1); mbar_init(rz_empty, 16);
-        if (TMAE) { prefetch_tmap(&rmap); prefetch_tmap(&omap); prefetch_tmap(&omap_tail); }
+        if (TMAE) { prefetch_tmap(&rmap); prefetch_tmap(&omap); prefetch_tmap(&omap_tail); if (ACC) prefetch_tmap(&amap); }
         fence_mbar_init();
     }
     {   // biases; zeroed xt planes (the positions past 511 are read, never used: keep them finite); the Toeplitz operand of conv2
@@ -588,9 +588,11 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const int b = tile / tiles_per_b, rem = tile - b * tiles_per_b;
                 if (i > 0) mbar_wait(rz_empty, (uint32_t)(i - 1) & 1u);
                 if (elect_one()) {
-                    mbar_expect_tx(rz_full, 4u * 128u * 64u);
-                    for (int g = 0; g < 4; ++g)
+                    mbar_expect_tx(rz_full, (ACC ? 8u : 4u) * 128u * 64u);
+                    for (int g = 0; g < 4; ++g) {
                         tma_load_4d(sm + p.smem_rz_off + g * 8192, &rmap, 0, g, rem * p.rows_out, b, rz_full);
+                        if (ACC) tma_load_4d(sm + p.smem_rz_off + 32768 + g * 8192, &amap, 0, g, rem * p.rows_out, b, rz_full);   // running sum
+                    }
                 }
                 __syncwarp();
             }
@@ -652,7 +654,7 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int tm = o0 - p.p2 + tau;
             const bool in_seq = tm >= 0 && tm < valid_of(b);
             const bool edge = __any_sync(0xffffffffu, !in_seq);
-            if (ACC) {      // the running-sum row this thread adds in epilogue B of the same tile: pull it into L2 now
+            if (ACC && !TMAE) {      // the running-sum row this thread adds in epilogue B of the same tile: pull it into L2 now
                 const int to = o0 + 4 * row + grp;
                 if (row < p.rows_out && to < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.accin + ((size_t)b * p.L + to) * 32));
             }
@@ -735,6 +737,12 @@ tc_pair16_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 R[1] = *reinterpret_cast<const uint4*>(rrow + ((1u ^ rsw) << 4));
                 R[2] = *reinterpret_cast<const uint4*>(rrow + ((2u ^ rsw) << 4));
                 R[3] = *reinterpret_cast<const uint4*>(rrow + ((3u ^ rsw) << 4));
+                if (ACC) {
+                    A[0] = *reinterpret_cast<const uint4*>(rrow + 32768 + ((0u ^ rsw) << 4));
+                    A[1] = *reinterpret_cast<const uint4*>(rrow + 32768 + ((1u ^ rsw) << 4));
+                    A[2] = *reinterpret_cast<const uint4*>(rrow + 32768 + ((2u ^ rsw) << 4));
+                    A[3] = *reinterpret_cast<const uint4*>(rrow + 32768 + ((3u ^ rsw) << 4));
+                }
             }
             mbar_wait(&b_full[st], n & 1u);
             tc_fence_after();
@@ -837,6 +845,13 @@ bool tc_pair_supported(int C, int K, int D) {
 }
 
 // C = 16: conv2 time-grouped (tc_pair16_kernel)
+static bool pair16_tma_epilogue(const TcPairArgs& a) {      // residual (+ running-sum) staging fits beside two x stages, and L % 4 == 0
+    static const int tmae_env = getenv("PB_TP_TMAE") ? atoi(getenv("PB_TP_TMAE")) : 1;
+    const uint32_t fixed = 2048u + (uint32_t)round_up(a.K * 1024, 1024) + (uint32_t)(T16_G + a.K - 1) * 4096u + 4u * (uint32_t)T16_XT_PLANE;
+    const uint32_t x_stage = (uint32_t)round_up(round_up(TP_M + (a.K - 1) * a.D, 16) * 64, 1024);
+    return tmae_env != 0 && a.L % 4 == 0 && fixed + (a.accin ? 65536u : 32768u) + 2u * x_stage + 2048u <= TP_SMEM_LIMIT;
+}
+
 static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
     Pair16Params p{};
     p.w1 = a.w1; p.w2 = a.w2; p.bias1 = a.bias1; p.bias2 = a.bias2; p.res = a.x; p.accin = a.accin; p.out = a.out;
@@ -853,13 +868,13 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
     p.smem_w1_off = 2048;
     p.smem_w2_off = p.smem_w1_off + (uint32_t)round_up(p.w1_bytes, 1024);
     p.smem_xt_off = p.smem_w2_off + (uint32_t)p.n_ksteps2 * 4096u;
-    // epilogue B through shared memory + TMA (residual rows in, output rows out, both as 128-byte wavefronts) instead of row-per-lane
-    // global accesses 256 bytes apart (32 wavefronts each): not with the running sum (a second 32 KB buffer does not fit), and the
-    // grouped maps need L % 4 == 0.  PB_TP_TMAE=0 disables.
-    static const int tmae_env = getenv("PB_TP_TMAE") ? atoi(getenv("PB_TP_TMAE")) : 1;
-    const bool tmae = tmae_env != 0 && !a.accin && a.L % 4 == 0;
+    // epilogue B through shared memory + TMA (residual and running-sum rows in, output rows out, all as 128-byte wavefronts) instead of
+    // row-per-lane global accesses 256 bytes apart (32 wavefronts each): where the staging (32 KB, 64 KB with the running sum) fits beside
+    // two x stages and L % 4 == 0 (the grouped maps).  PB_TP_TMAE=0 disables.
     p.smem_rz_off = p.smem_xt_off + 4u * (uint32_t)T16_XT_PLANE;
-    p.smem_x_off = p.smem_rz_off + (tmae ? 32768u : 0u);
+    const uint32_t rz_bytes = a.accin ? 65536u : 32768u;          // (+ the running-sum rows)
+    const bool tmae = pair16_tma_epilogue(a);
+    p.smem_x_off = p.smem_rz_off + (tmae ? rz_bytes : 0u);
     const uint32_t left = TP_SMEM_LIMIT - 1024u - p.smem_x_off;
     p.n_x_stages = (int)(left / (uint32_t)p.x_stage_bytes);
     if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
@@ -875,9 +890,10 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
 
     CUtensorMap xmap;
     PB_TRY(tc_make_tmap_act(&xmap, a.x, 16, a.L, a.B, 32, p.x_rows / 2, false));
-    CUtensorMap rmap = xmap, omap = xmap, omap_tail = xmap;      // only read when tmae
+    CUtensorMap rmap = xmap, amap = xmap, omap = xmap, omap_tail = xmap;      // only read when tmae
     if (tmae) {
         PB_TRY(tc_make_tmap_grouped16(&rmap, a.x, a.L, a.B, 128));
+        if (a.accin) PB_TRY(tc_make_tmap_grouped16(&amap, a.accin, a.L, a.B, 128));
         PB_TRY(tc_make_tmap_grouped16(&omap, a.out, a.L, a.B, 32));
         PB_TRY(tc_make_tmap_grouped16(&omap_tail, a.out, a.L, a.B, p.rows_out - 96));
     }
@@ -891,6 +907,7 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
         PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
         PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
         PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
+        PB_CUDA(cudaFuncSetAttribute(tc_pair16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_LIMIT));
         attr_set = true;
     }
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
@@ -901,9 +918,10 @@ static int launch_tc_pair16(const TcPairArgs& a, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool no_pdl = getenv("PB_TC_NO_PDL") != nullptr;
     cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-    if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<true, false>, xmap, rmap, omap, omap_tail, p));
-    else if (tmae) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false, true>, xmap, rmap, omap, omap_tail, p));
-    else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false, false>, xmap, rmap, omap, omap_tail, p));
+    if (a.accin && tmae) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<true, true>, xmap, rmap, amap, omap, omap_tail, p));
+    else if (a.accin) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<true, false>, xmap, rmap, amap, omap, omap_tail, p));
+    else if (tmae) PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false, true>, xmap, rmap, amap, omap, omap_tail, p));
+    else PB_CUDA(cudaLaunchKernelEx(&cfg, tc_pair16_kernel<false, false>, xmap, rmap, amap, omap, omap_tail, p));
     PB_COUNT_LAUNCH();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -913,11 +931,12 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     PB_REQUIRE(a.x && a.w1 && a.w2 && a.out && a.bias1 && a.bias2, PB_ERR_INVALID, "tc_pair: null tensor");
     PB_REQUIRE(tc_pair_supported(a.C, a.K, a.D), PB_ERR_INVALID, "tc_pair: C=%d K=%d D=%d unsupported", a.C, a.K, a.D);
     PB_REQUIRE(a.B > 0 && a.L > 0, PB_ERR_INVALID, "tc_pair: bad shape");
-    // C = 16: time-grouped conv2 where it pays - k >= 7 without the running sum (per launch at 8 x 1024 units, same box: k = 11
-    // 174-181 -> 161 us, k = 7 139 -> 134; with the running sum its row-per-lane accesses 256 bytes apart cost more than the MMAs save:
-    // 184-190 -> 201-204; k = 3 is not tensor-bound: 100 -> 110).  PB_TP_TOEPLITZ=0 / 1 forces it off / on for every 16-channel pair.
+    // C = 16: time-grouped conv2 where it pays - k >= 7 (per launch at 8 x 1024 units, same box: k = 11 170 -> 148 us, with the running
+    // sum 180 -> 159; k = 7 128 -> 113 / 143 -> 142; k = 3 is not tensor-bound: 103 -> 104).  With the running sum only when its rows
+    // can be staged through shared memory too: as row-per-lane global accesses they cost more than the MMAs save (190 -> 201 us).
+    // PB_TP_TOEPLITZ=0 / 1 forces it off / on for every 16-channel pair.
     static const int toeplitz_env = getenv("PB_TP_TOEPLITZ") ? atoi(getenv("PB_TP_TOEPLITZ")) : -1;
-    if (a.C == 16 && a.K >= 3 && (toeplitz_env < 0 ? (a.K >= 7 && !a.accin) : toeplitz_env != 0)) return launch_tc_pair16(a, st);
+    if (a.C == 16 && a.K >= 3 && (toeplitz_env < 0 ? (a.K >= 7 && (!a.accin || pair16_tma_epilogue(a))) : toeplitz_env != 0)) return launch_tc_pair16(a, st);
     PairParams p{};
     p.w1 = a.w1; p.w2 = a.w2; p.bias1 = a.bias1; p.bias2 = a.bias2; p.res = a.x; p.accin = a.accin; p.out = a.out;
     p.lens = a.lens; p.len_mul = a.len_mul;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch: TMA-staged epilogue B of the time-grouped kernel (PB_TP_TMAE) - correctness, then per launch, same box
+# scratch: TMA-staged epilogue B with the running sum - correctness, then per launch, same box
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_switches_gpu.py tests/test_voc_gpu.py -x -q -m gpu -k "time_grouped or golden or ragged or rectangle or other_" 2>&1 | tail -4
 run() {  # name env...
@@ -8,10 +8,8 @@ run() {  # name env...
       python tools/prof_voc.py 8 1024 1 0 > /dev/null 2>&1; echo "$name rc=$?"
 }
 run t0 PB_TP_TOEPLITZ=0
-run t1e0 PB_TP_TOEPLITZ=1 PB_TP_TMAE=0
-run t1e1 PB_TP_TOEPLITZ=1 PB_TP_TMAE=1
 run def PB_X=1
-python - t0 t1e0 t1e1 def <<'PY'
+python - t0 def <<'PY'
 import csv, sys
 names = [f"s{s} k{k} d{d}" for s in (4, 5) for k in (3, 7, 11) for d in (1, 3, 5)]
 cols = []
