@@ -10,5 +10,5 @@ timeout 600 ncu --metrics $M --clock-control none -c 600 --csv --log-file gpurun
 timeout 900 ncu --metrics $M --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_voc_cfg3.csv python tools/prof_voc.py 32 2048 1 0 > /dev/null 2>&1; echo "list voc cfg3 rc=$?"
 timeout 600 ncu --metrics $M --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_tte_cfg3.csv python tools/prof_tte.py > /dev/null 2>&1; echo "list tte rc=$?"
 mkdir -p /tmp/ncu
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:tc_pair16 -s 2 -c 1 -f -o /tmp/ncu/pair16 python tools/prof_voc.py 8 1024 1 0 > /tmp/ncu/pair16.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:tc_pair16 -s 3 -c 1 -f -o /tmp/ncu/pair16 python tools/prof_voc.py 8 1024 1 0 > /tmp/ncu/pair16.log 2>&1
 ncu -i /tmp/ncu/pair16.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_tc_pair16_s5_k11.csv 2>/dev/null; echo "full pair16 rc=$? $(wc -c < gpurun_out/r02_ncu_full_tc_pair16_s5_k11.csv)"

@@ -54,7 +54,7 @@ def expected(B, T):
             for m in range(N_DIL):
                 last = m == N_DIL - 1
                 extra = (1 if (last and j > 0) else 0)              # running ResBlock sum read back
-                if c == 16 and k >= 7 and not extra:
+                if c == 16 and k >= 7:
                     # tc_pair16: super tile = 4 conv1 M tiles -> 4 (512 - (k - 1)) // 4 output rows; conv2 time-grouped (G = 4):
                     # G + k - 1 k-steps of {N = 128 stacked, N = 64}
                     m_out = 4 * ((512 - (k - 1)) // 4)
