@@ -47,6 +47,7 @@ struct PairParams {
     int acc_cols, tmem_cols;
     int tma_out;                   // epilogue B writes through per-warp staging tiles + TMA stores
     uint32_t smem_stage_off;
+    int res_smem;                  // epilogue B reads the residual rows from the x tile in shared memory (held until then)
     int ablate;                    // profiling only (PB_TP_ABLATE): 1 no MMAs, 2 no output stores, 4 no residual / running-sum loads,
                                    // 8 no x loads, 16 no xt stores, 32 no epilogue arithmetic, 64 no accumulator reads - results are wrong by design
 };
@@ -78,7 +79,7 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     if (threadIdx.x == 0) {
         prefetch_tmap(&xmap);
         if (p.tma_out) { prefetch_tmap(&omap); prefetch_tmap(&omap_tail); }
-        for (int s = 0; s < TP_MAX_XST; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+        for (int s = 0; s < TP_MAX_XST; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], p.res_smem ? 5 : 1); }
         for (int s = 0; s < TP_STAGES; ++s) {
             mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 4);
             mbar_init(&mid_full[s], 4); mbar_init(&mid_empty[s], 1);
@@ -295,10 +296,26 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 const bool live = to < valid;
                 const size_t row_el = ((size_t)b * p.L + to) * pitch;
                 uint4 R[4], A[4];
+                // The residual is x itself, and the x tile of this tile is still in shared memory (res_smem: its stage is released by
+                // conv1's commit AND these four warps): a row-per-lane global load costs 32 L1 wavefronts, its 16-byte chunks here 4.
+                const uint32_t xs_i = (uint32_t)i % (uint32_t)p.n_x_stages;
+                const int xr = p.p1 + p.p2 + row;                                  // this output row inside the x tile
+                const uint8_t* xrow = sm + p.smem_x_off + xs_i * p.x_stage_bytes + xr * p.row_bytes;
+                const uint32_t xsw = sw128 ? (uint32_t)(xr & 7) : (uint32_t)((xr >> 1) & 3);
+                // (the TMA writes of that tile are ordered before these reads through full_x -> conv1's issuer -> its commit on a_full -> this
+                // warp's wait on a_full in epilogue A: no wait on full_x here)
                 auto request = [&](int n0) {
                     if (!row_ok || (p.ablate & 4)) return;
-                    ld_global_nc_v8(p.res + row_el + n0, R[0], R[1]);
-                    ld_global_nc_v8(p.res + row_el + C + n0, R[2], R[3]);
+                    if (p.res_smem) {
+                        const uint32_t ch = (uint32_t)n0 >> 3, cl = ((uint32_t)p.lo_off >> 4) + ch;
+                        R[0] = *reinterpret_cast<const uint4*>(xrow + ((ch ^ xsw) << 4));
+                        R[1] = *reinterpret_cast<const uint4*>(xrow + (((ch + 1) ^ xsw) << 4));
+                        R[2] = *reinterpret_cast<const uint4*>(xrow + ((cl ^ xsw) << 4));
+                        R[3] = *reinterpret_cast<const uint4*>(xrow + (((cl + 1) ^ xsw) << 4));
+                    } else {
+                        ld_global_nc_v8(p.res + row_el + n0, R[0], R[1]);
+                        ld_global_nc_v8(p.res + row_el + C + n0, R[2], R[3]);
+                    }
                     if (ACC) {
                         ld_global_v8(p.accin + row_el + n0, A[0], A[1]);
                         ld_global_v8(p.accin + row_el + C + n0, A[2], A[3]);
@@ -391,6 +408,10 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                             bulk_commit_group();
                         }
                     }
+                }
+                if (p.res_smem) {      // the residual rows have been consumed: this warp's share of the x stage's release
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_x[xs_i]);
                 }
             }
             rem += stride;
@@ -974,6 +995,11 @@ int launch_tc_pair(const TcPairArgs& a, cudaStream_t st) {
     p.tma_out = (tma_out_mode > 0 && a.C == 32 && left >= stage_bytes + 3u * (uint32_t)p.x_stage_bytes && p.m_out > 96) ? 1 : 0;
     p.n_x_stages = (int)((left - (p.tma_out ? stage_bytes : 0u)) / (uint32_t)p.x_stage_bytes);
     if (p.n_x_stages > TP_MAX_XST) p.n_x_stages = TP_MAX_XST;
+    // the residual from the x tile (held until epilogue B): needs a stage per tile in flight and one to prefetch into.  At C = 32 a lane's
+    // residual row is its own 128-byte line (32 L1 wavefronts per global load): k = 3 112 -> 105 us, k = 7 with the running sum 179 -> 171;
+    // at C = 16 (two rows per line) nothing: 104.5 -> 105.  PB_TP_RES_SMEM=0 disables, 2 forces it on at C = 16 too.
+    static const int res_smem_env = getenv("PB_TP_RES_SMEM") ? atoi(getenv("PB_TP_RES_SMEM")) : 1;
+    p.res_smem = ((res_smem_env == 2 || (res_smem_env == 1 && a.C == 32)) && p.n_x_stages >= ng + 1) ? 1 : 0;
     PB_REQUIRE(p.n_x_stages >= 2, PB_ERR_INVALID, "tc_pair: tile does not fit in shared memory (C=%d K=%d D=%d)", a.C, a.K, a.D);
     p.smem_stage_off = p.smem_x_off + (uint32_t)p.n_x_stages * (uint32_t)p.x_stage_bytes;
     const uint32_t smem_bytes = p.smem_stage_off + (p.tma_out ? stage_bytes : 0u) + 1024;

@@ -7,6 +7,7 @@
   PB_TC_CL_RESIDENT=0 CTA pairs always stream their weights (no resident halves)
   PB_TP_GROUPS=3/4    tiles in flight in the fused ResBlock-step kernel of the 32 / 16-channel stages (default: per layer)
   PB_TP_TOEPLITZ=0/1  time-grouped conv2 in the 16-channel fused kernel never / for every kernel size (default: k >= 7)
+  PB_TP_RES_SMEM=0    the tap-by-tap fused kernel re-reads the residual rows from global memory instead of the x tile in shared memory
   PB_TP_TMAE=0        ... with its residual / output rows as row-per-lane global accesses instead of shared-memory staging + TMA
 Each case runs in a fresh interpreter because the library reads its switches once.
 """
@@ -19,7 +20,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
-SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_TC_PAIR64", "PB_TC_CL_RESIDENT", "PB_TP_GROUPS", "PB_TP_TOEPLITZ", "PB_TP_TMAE", "PB_LIB_VARIANT")
+SWITCHES = ("PB_VOC_CHAINS", "PB_TC_TMA_OUT", "PB_TC_EPI_SPLIT", "PB_TC_CLUSTER", "PB_TC_PAIR64", "PB_TC_CL_RESIDENT", "PB_TP_GROUPS", "PB_TP_TOEPLITZ", "PB_TP_TMAE", "PB_TP_RES_SMEM", "PB_LIB_VARIANT")
 
 CODE = r"""
 import sys, numpy as np, torch
@@ -108,3 +109,10 @@ def test_time_grouped_kernel_epilogue_paths_are_bit_identical(tmp_path, baseline
     # residual rows in / output rows out through shared memory and TMA, or straight from / to global memory: the same arithmetic
     _same(baseline, _run(tmp_path, "tmae0", {"PB_TP_TMAE": "0", "PB_TP_TOEPLITZ": "1"}))
     _same(baseline, _run(tmp_path, "tmae1", {"PB_TP_TMAE": "1", "PB_TP_TOEPLITZ": "1"}))
+
+
+def test_residual_from_the_x_tile_is_bit_identical(tmp_path, baseline):
+    # the x tile a fused pair loaded for conv1 holds the residual rows of its outputs: same values as the global re-read
+    _same(baseline, _run(tmp_path, "ressmem0", {"PB_TP_RES_SMEM": "0"}))
+    _same(baseline, _run(tmp_path, "ressmem0t0", {"PB_TP_RES_SMEM": "0", "PB_TP_TOEPLITZ": "0"}))
+    _same(baseline, _run(tmp_path, "ressmem2t0", {"PB_TP_RES_SMEM": "2", "PB_TP_TOEPLITZ": "0"}))
