@@ -5,14 +5,18 @@
 // K-major layout TMA would have produced) and is the A operand of conv2's MMAs.  HBM traffic per pair drops from five tensor
 // passes (read x, write xt, read xt, read x, write out) to ~2.2 (x with halo, out; the residual re-read hits L2).
 //
+// Two kernels.  tc_pair_kernel (C = 32, and C = 16 at k = 3) takes the taps one by one:
 // Tile: conv1 produces 128 rows of xt, conv2 the 128 - (K-1) output rows they support (tiles advance by that many rows; the
 // K-1 garbage rows an M = 128 MMA computes past them are never stored).  Both weight sets stay resident in shared memory.
 //   warp 0       producer: TMA loads of the x tile (128 + (K-1) d rows, zero fill = conv padding)
 //   warps 1, 3   MMA issuers: warp 1 issues conv1 of every tile (running ahead), warp 3 conv2, so the tensor pipe works on the
 //                next tiles while the epilogue warps turn conv1(i)'s accumulator into the shared-memory operand
-//   warp 2       TMEM owner (two conv1 + two conv2 accumulator stages)
-//   warps 4..11  two epilogue groups taking alternate tiles: epilogue A (TMEM -> bias, leaky relu, edge zeros -> swizzled smem),
-//                then epilogue B (TMEM -> bias, residual, running sum, scale, activation, length mask -> global)
+//   warp 2       TMEM owner (NG conv1 + NG conv2 accumulator stages)
+//   warps 4..    NG = 3 or 4 epilogue groups taking the tiles round-robin: epilogue A (TMEM -> bias, leaky relu, edge zeros -> swizzled
+//                smem), then epilogue B (TMEM -> bias, residual - at C = 32 from the x tile still in shared memory -, running sum, scale,
+//                activation, length mask -> global, at C = 32 through per-warp staging tiles + TMA stores)
+// tc_pair16_kernel (C = 16, k >= 7) evaluates conv2 time-grouped against a block-Toeplitz operand: see its own header below.
+// Both produce the same bits (tests/test_switches_gpu.py); launch_tc_pair chooses per layer.
 #include <stdlib.h>
 
 #include "pb_tc.cuh"
