@@ -16,14 +16,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
+from oracle.geometries import other_tte_config, other_vocoder_config  # noqa: E402
 from parrot_tts_b200 import configs, synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 VOCAB, PAD, NSPK = 150, 0, 10
 
 
-def tte_case(name, phones, speaker, seed=0, dur_mode="spread", stride=5):
-    cfg = configs.default_tte_config()
+def tte_case(name, phones, speaker, seed=0, dur_mode="spread", stride=5, cfg=None):
+    cfg = cfg or configs.default_tte_config()
     sd = synth.synth_tte_state_dict(cfg, VOCAB, PAD, NSPK, seed=seed, dur_mode=dur_mode)
     model = ref_shim.load_reference_parrot(cfg, VOCAB, PAD, NSPK)
     model.load_state_dict(sd, strict=True)
@@ -49,8 +50,8 @@ def tte_case(name, phones, speaker, seed=0, dur_mode="spread", stride=5):
     print(name, "T =", logits.shape[1], "lens", [len(x) for x in ids_list], "min margin", float((top2[..., 0] - top2[..., 1]).min()))
 
 
-def voc_case(name, code, spkr, seed=0, x=None):
-    h = configs.default_vocoder_config()
+def voc_case(name, code, spkr, seed=0, x=None, h=None):
+    h = h or configs.default_vocoder_config()
     sd = synth.synth_vocoder_state_dict(h, seed=seed, weight_norm=True, n_speaker=NSPK)
     gen = ref_shim.load_reference_vocoder(h)
     gen.load_state_dict(sd, strict=True)
@@ -89,9 +90,22 @@ def mel_case(name, seed=0):
     print(name, tuple(mel.shape), "range", float(mel.min()), float(mel.max()))
 
 
+def other_geometries():
+    """Fixtures at the two other geometries (tests/test_*_gpu.py::test_other_*_geometry_matches_reference_golden)."""
+    g3 = torch.Generator().manual_seed(77)
+    voc_case("voc_geom_x16_t300", torch.randint(0, 1000, (3, 300), generator=g3), torch.randint(0, 10, (3,), generator=g3), seed=23,
+             h=other_vocoder_config())
+    g4 = torch.Generator().manual_seed(12)
+    ph = torch.randint(2, VOCAB, (3, 41), generator=g4)
+    ph[1, 17:] = PAD
+    tte_case("tte_geom_l23_s41", ph, [1, 7, 3], seed=31, stride=16, cfg=other_tte_config())
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--other-geometries" in sys.argv:      # only the fixtures added last (the others are not rewritten)
+        return other_geometries()
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(1234)
     # TTE: one utterance; a ragged padded batch (rectangle semantics, SURVEY.md hard part 3)
@@ -116,6 +130,7 @@ def main():
     ph[3, 31:] = PAD
     tte_case("tte_b4_s256_ragged", ph, [1, 8, 0, 5], seed=2, stride=128)
     mel_case("mel_b2_n16384")
+    other_geometries()
 
 
 if __name__ == "__main__":

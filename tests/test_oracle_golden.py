@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import tte_oracle, voc_oracle
+from oracle import geometries, tte_oracle, voc_oracle
 from parrot_tts_b200 import configs, synth
 
 
@@ -14,10 +14,10 @@ def _load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name + ".npz"))
 
 
-@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged", "tte_cfg1_s64", "tte_b4_s256_ragged"])
+@pytest.mark.parametrize("name", ["tte_b1_s16", "tte_b3_ragged", "tte_cfg1_s64", "tte_b4_s256_ragged", "tte_geom_l23_s41"])
 def test_tte_oracle_matches_golden(golden_dir, name):
     g = _load(golden_dir, name)
-    cfg = configs.default_tte_config()
+    cfg = geometries.other_tte_config() if "geom" in name else configs.default_tte_config()
     sd = synth.synth_tte_state_dict(cfg, int(g["vocab"]), 0, int(g["n_speaker"]), seed=int(g["seed"]), dur_mode=str(g["dur_mode"]))
     batch = {"phones": torch.from_numpy(g["phones"]), "src_mask": torch.from_numpy(g["src_mask"]),
              "speaker": torch.from_numpy(g["speaker"])}
@@ -44,10 +44,10 @@ def test_round_half_even():
     assert tte_oracle.round_durations(ld).tolist() == [0, 2, 2, 0, 0]
 
 
-@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40", "voc_cfg1_t512"])
+@pytest.mark.parametrize("name", ["voc_b1_t24", "voc_b2_t40", "voc_cfg1_t512", "voc_geom_x16_t300"])
 def test_voc_oracle_matches_golden(golden_dir, name):
     g = _load(golden_dir, name)
-    h = configs.default_vocoder_config()
+    h = geometries.other_vocoder_config() if "geom" in name else configs.default_vocoder_config()
     sd = synth.synth_vocoder_state_dict(h, seed=int(g["seed"]), weight_norm=True)
     wav = voc_oracle.code_generator_forward(sd, h, torch.from_numpy(g["code"]), torch.from_numpy(g["spkr"]))
     assert wav.shape == g["wav"].shape

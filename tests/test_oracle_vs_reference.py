@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ref_shim, tte_oracle, voc_oracle
+from oracle import geometries, ref_shim, tte_oracle, voc_oracle
 from parrot_tts_b200 import configs, synth
 
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
@@ -61,11 +61,9 @@ def test_voc_oracle_vs_reference(seed, B, T):
 
 
 def test_voc_oracle_vs_reference_other_geometry():
-    """The HiFi-GAN shape of tests/test_voc_gpu.py::test_other_hifigan_geometry_matches_oracle (x16, kernels 5 / 9, dilations (1, 2, 4) /
+    """The HiFi-GAN shape of tests/test_voc_gpu.py::test_other_hifigan_geometry_matches_reference_golden (x16, kernels 5 / 9, dilations (1, 2, 4) /
     (1, 3, 5)): the reference builds it from the same `h` (utils/vocoder/models.py:72-93) - pins the oracle there too."""
-    h = configs.default_vocoder_config()
-    h.update({"upsample_rates": [4, 2, 2], "upsample_kernel_sizes": [8, 4, 4], "upsample_initial_channel": 128,
-              "resblock_kernel_sizes": [5, 9], "resblock_dilation_sizes": [[1, 2, 4], [1, 3, 5]], "code_hop_size": 16})
+    h = geometries.other_vocoder_config()
     sd = synth.synth_vocoder_state_dict(h, seed=23, weight_norm=True)
     gen = ref_shim.load_reference_vocoder(h)
     gen.load_state_dict(sd, strict=True)
@@ -81,14 +79,9 @@ def test_voc_oracle_vs_reference_other_geometry():
 
 @pytest.mark.parametrize("n_head", [2, 4])
 def test_tte_oracle_vs_reference_other_geometry(n_head):
-    """The transformer shape of tests/test_tte_gpu.py::test_other_transformer_geometry_matches_oracle (2 / 3 layers, FFN 512 x 5 taps,
+    """The transformer shape of tests/test_tte_gpu.py::test_other_transformer_geometry_matches_reference_golden (2 / 3 layers, FFN 512 x 5 taps,
     500 codes, 2 or 4 heads), built by the reference from the same config (modules/parrot.py:22-53)."""
-    cfg = configs.default_tte_config()
-    tr = cfg["transformer"]
-    tr["encoder"]["n_layer"], tr["decoder"]["n_layer"] = 2, 3
-    tr["encoder"]["n_head"] = tr["decoder"]["n_head"] = n_head
-    tr["conv_n_filter"], tr["conv_kernel_sizes"] = 512, [5, 1]
-    cfg["preprocess"]["hubert_codes"] = 500
+    cfg = geometries.other_tte_config(n_head=n_head)
     sd = synth.synth_tte_state_dict(cfg, 150, 0, 10, seed=31)
     ref = ref_shim.load_reference_parrot(cfg, 150, 0, 10)
     ref.load_state_dict(sd, strict=True)

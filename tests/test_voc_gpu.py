@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from oracle import voc_oracle
+from oracle import geometries, voc_oracle
 from parrot_tts_b200 import _lib, configs, ops, synth
 from parrot_tts_b200.vocoder import CodeGenerator, Generator
 
@@ -509,29 +509,27 @@ def test_mel_distance_of_generated_audio_vs_oracle():
     assert float((m_dev - m_ref).abs().mean()) < 1e-3, float((m_dev - m_ref).abs().mean())
 
 
-def test_other_hifigan_geometry_matches_oracle(mode=1):
+def test_other_hifigan_geometry_matches_reference_golden(golden_dir, mode=1):
     """A HiFi-GAN shape the reference config does not use (utils/vocoder/models.py builds any of them from `h`): three upsampling
-    stages x16, two ResBlock kernels 5 / 9 with dilations (1, 2, 4) / (1, 3, 5).  Exercises the kernels at other tap counts and
-    dilations than 3 / 7 / 11 x (1, 3, 5): the 64-channel layers as single CTAs (k = 5) and CTA pairs (k = 9), the fused 32-channel
-    pairs, the 16-channel pairs tap-by-tap (k = 5) and time-grouped (k = 9), a mean over two ResBlocks.  The tensor-core path (the
-    default) takes any odd kernel size; the fp32 SIMT validation path is compiled for the reference's 3 / 7 / 11 x (1, 3, 5) only and
-    says so."""
-    h = configs.default_vocoder_config()
-    h.update({"upsample_rates": [4, 2, 2], "upsample_kernel_sizes": [8, 4, 4], "upsample_initial_channel": 128,
-              "resblock_kernel_sizes": [5, 9], "resblock_dilation_sizes": [[1, 2, 4], [1, 3, 5]], "code_hop_size": 16})
-    sd = synth.synth_vocoder_state_dict(h, seed=23, weight_norm=True)
+    stages x16, two ResBlock kernels 5 / 9 with dilations (1, 2, 4) / (1, 3, 5) - against the vector recorded from the reference's own
+    module (oracle/gen_golden.py --other-geometries), and item by item against the oracle in ragged mode.  Exercises the kernels at
+    other tap counts and dilations than 3 / 7 / 11 x (1, 3, 5): the 64-channel layers as single CTAs (k = 5) and CTA pairs (k = 9), the
+    fused 32-channel pairs, the 16-channel pairs tap-by-tap (k = 5) and time-grouped (k = 9), a mean over two ResBlocks.  The
+    tensor-core path (the default) takes any odd kernel size; the fp32 SIMT validation path is compiled for the reference's
+    3 / 7 / 11 x (1, 3, 5) only and says so."""
+    g = np.load(os.path.join(golden_dir, "voc_geom_x16_t300.npz"))
+    h = geometries.other_vocoder_config()
+    sd = synth.synth_vocoder_state_dict(h, seed=int(g["seed"]), weight_norm=True)
     gen = CodeGenerator(h)
     gen.conv_mode = mode
     gen.load_state_dict(sd, strict=True)
     gen = gen.to(DEV)
-    g = _gen(77)
+    code, spkr = torch.from_numpy(g["code"]), torch.from_numpy(g["spkr"])
     lens = [300, 41, 1]
-    code = torch.randint(0, 1000, (3, max(lens)), generator=g)
-    spkr = torch.randint(0, 10, (3, 1), generator=g)
     got = gen(code=code.to(DEV), spkr=spkr.to(DEV)).cpu()
-    ref = voc_oracle.code_generator_forward(sd, h, code, spkr)
-    assert got.shape == ref.shape == (3, 1, 16 * max(lens))
-    assert (got - ref).abs().max() < WAV_TIGHT, float((got - ref).abs().max())
+    assert got.shape == g["wav"].shape == (3, 1, 16 * max(lens))
+    err = float((got - torch.from_numpy(g["wav"])).abs().max())
+    assert err < WAV_TIGHT, err
     rag = gen(code=code.to(DEV), spkr=spkr.to(DEV), lens=torch.tensor(lens)).cpu()
     for i, n in enumerate(lens):
         alone = voc_oracle.code_generator_forward(sd, h, code[i:i + 1, :n], spkr[i:i + 1])
